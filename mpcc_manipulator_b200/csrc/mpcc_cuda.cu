@@ -1,0 +1,722 @@
+// libmpcc_b200.so: CUDA kernels of the batched MPCC control cycle and the C ABI (include/mpcc_cuda.h).
+// sm_100a only.  There is no CPU fallback: every entry point fails with MPCC_ERR_CUDA if no device works.
+#include "../../include/mpcc_cuda.h"
+#include "mpcc_types.h"
+#include "dev_panda.cuh"
+#include "dev_track.cuh"
+#include "dev_stage.cuh"
+#include "dev_qp.cuh"
+#include "dev_sqp.cuh"
+#include "mlp_kernel.cuh"
+#include "host/params_io.h"
+#include "host/track_fit.h"
+
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <stdexcept>
+
+using namespace mpcc;
+
+static_assert(PARAMS_DOUBLES == MPCC_PARAMS_DOUBLES, "params layout");
+static_assert(TRACK_DOUBLES == MPCC_TRACK_DOUBLES, "track layout");
+static_assert(sizeof(StageLin) == MPCC_STAGE_LIN_DOUBLES * sizeof(double), "stage lin layout");
+static_assert(RB_DOUBLES == MPCC_RB_DOUBLES, "robot data layout");
+
+constexpr int MAX_SQP_ITER = 128;
+constexpr int FILT_DOUBLES = 2 * (MAX_SQP_ITER + 2);
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+struct CycleArgs {
+    int B, N, S;
+    double Ts;
+    const Params* params; int params_per_instance;
+    const TrackTable* tracks; const int32_t* track_id;
+    double* x0; const double* u0; const double* obs;  // [B][9], [B][8], [B][4] (AoS)
+    double* warm;      // [S*17][B]  (SoA) warm start == SQP iterate
+    double* step;      // [S*17][B]
+    double* trial;     // [S*17][B]
+    double* filt;      // [FILT_DOUBLES][B]
+    double* ws;        // [S*STAGE_WS][B]
+    WarmFlags* flags;  // [B]
+    double* qs;        // [7][B*S]
+    double* rb;        // [150][B*S]
+    double* u_out;     // [B][8]
+    double* horizon;   // [B][S][17]
+    int32_t* status; int32_t* iters; int32_t* ok; int32_t* qp_iters; int32_t* qp_fail;
+    QpOptions qp;
+};
+
+// prologue of runMPC_ (mpc.cpp:104-124): one thread per instance
+__global__ void k_prologue(CycleArgs a) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.B) return;
+    const Params& P = a.params[a.params_per_instance ? b : 0];
+    const TrackTable& T = a.tracks[a.track_id[b]];
+    double x0[NX], u0[NU];
+    for (int i = 0; i < NX; i++) x0[i] = a.x0[b * NX + i];
+    for (int i = 0; i < NU; i++) u0[i] = a.u0[b * NU + i];
+    WarmFlags fl = a.flags[b];
+    WsRef warm{a.warm + b, (size_t)a.B};
+    cycle_prologue(P, T, a.Ts, a.N, x0, u0, warm, fl);
+    a.flags[b] = fl;
+    a.x0[b * NX + 7] = x0[7];
+    a.x0[b * NX + 8] = x0[8];
+    const size_t NS = (size_t)a.B * a.S;
+    for (int k = 0; k < a.S; k++)
+        for (int j = 0; j < DOF; j++) a.qs[(size_t)j * NS + (size_t)b * a.S + k] = warm[k * HZ + j];
+}
+
+// kinematic part of RobotData::update (robot_data.h:55-64): one thread per (instance, stage)
+__global__ void k_kin(const double* __restrict__ qs, double* __restrict__ rb, int NS) {
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= NS) return;
+    double q[DOF];
+#pragma unroll
+    for (int j = 0; j < DOF; j++) q[j] = qs[(size_t)j * NS + n];
+    PandaKin kin;
+    panda_kinematics(q, kin);
+#pragma unroll
+    for (int j = 0; j < DOF; j++) rb[(size_t)(RB_Q + j) * NS + n] = q[j];
+#pragma unroll
+    for (int i = 0; i < 3; i++) rb[(size_t)(RB_P + i) * NS + n] = kin.p[i];
+#pragma unroll
+    for (int i = 0; i < 9; i++) rb[(size_t)(RB_R + i) * NS + n] = kin.R[i];
+#pragma unroll
+    for (int i = 0; i < 21; i++) { rb[(size_t)(RB_JV + i) * NS + n] = kin.Jv[i]; rb[(size_t)(RB_JW + i) * NS + n] = kin.Jw[i]; }
+    rb[(size_t)RB_MANIP * NS + n] = panda_manipulability_from(kin.Jv, kin.Jw);
+    double dm[DOF];
+    panda_dmanipulability(q, dm);
+#pragma unroll
+    for (int j = 0; j < DOF; j++) rb[(size_t)(RB_DMANIP + j) * NS + n] = dm[j];
+}
+
+// SQP loop + epilogue (osqp_interface.cpp:398-590, mpc.cpp:140-188): one thread per instance
+__global__ void k_sqp_thread(CycleArgs a) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.B) return;
+    const Params& P = a.params[a.params_per_instance ? b : 0];
+    const TrackTable& T = a.tracks[a.track_id[b]];
+    const size_t B = (size_t)a.B, NS = B * a.S;
+    WsRef guess{a.warm + b, B}, step{a.step + b, B}, trial{a.trial + b, B}, filt{a.filt + b, B}, ws{a.ws + b, B};
+    double cur_u[NU], x0[NX];
+    for (int i = 0; i < NU; i++) cur_u[i] = a.u0[b * NU + i];
+    for (int i = 0; i < NX; i++) x0[i] = a.x0[b * NX + i];
+    SqpResult r = sqp_solve(P, T, a.Ts, a.N, guess, step, trial, filt, cur_u, a.rb + (size_t)b * a.S, NS, 1, ws, a.qp, nullptr);
+    WarmFlags fl = a.flags[b];
+    bool ok = cycle_epilogue(a.N, r, x0, guess, fl);
+    a.flags[b] = fl;
+    a.status[b] = r.status; a.iters[b] = r.iters; a.ok[b] = ok ? 1 : 0; a.qp_iters[b] = r.qp_iters; a.qp_fail[b] = r.qp_fail;
+    for (int j = 0; j < NU; j++) a.u_out[b * NU + j] = guess[NX + j];
+    double* h = a.horizon + (size_t)b * a.S * HZ;
+    for (int e = 0; e < a.S * HZ; e++) h[e] = guess[e];
+}
+
+// ---- probe kernels ------------------------------------------------------------------------------
+__global__ void k_eval_stage(const Params* params, const TrackTable* tracks, double Ts, int N, const double* x, const double* u, const double* up,
+                             const double* un, const double* xn, const double* rb, const int32_t* k, int n, double* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    StageLin sl;
+    memset(&sl, 0, sizeof(sl));
+    RbView rv{rb + (size_t)i * RB_DOUBLES, 1};
+    stage_eval<true>(params[0], tracks[0], Ts, N, k[i], x + i * NX, u + i * NU, up + i * DOF, un + i * DOF, xn + i * NX, rv, sl);
+    const double* src = (const double*)&sl;
+    for (int e = 0; e < LIN_SIZE; e++) out[(size_t)i * LIN_SIZE + e] = src[e];
+}
+__global__ void k_eval_track(const TrackTable* tracks, const double* s, int n, double* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    TrackPoint tp;
+    track_eval_pos(tracks[0], s[i], tp);
+    double* o = out + (size_t)i * 21;
+    for (int c = 0; c < 3; c++) { o[c] = tp.pos[c]; o[3 + c] = tp.dpos[c]; o[6 + c] = tp.ddpos[c]; }
+    track_eval_rot(tracks[0], s[i], o + 9, o + 18);
+}
+// solveOCP on given warm starts and RobotData (both AoS), logging the SQP iterations
+__global__ void k_solve_ocp(CycleArgs a, double* guess, const double* rb, const double* cur_u, int n, double* steps, double* alphas,
+                            int32_t* qp_ok, int max_log, int32_t* n_logged) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n) return;
+    const Params& P = a.params[a.params_per_instance ? b : 0];
+    const TrackTable& T = a.tracks[a.track_id[b]];
+    const size_t B = (size_t)a.B;
+    const int HN = a.S * HZ;
+    WsRef g{guess + (size_t)b * HN, 1}, step{a.step + b, B}, trial{a.trial + b, B}, filt{a.filt + b, B}, ws{a.ws + b, B};
+    SqpLogRef lg{steps ? steps + (size_t)b * max_log * HN : nullptr, alphas + (size_t)b * max_log, qp_ok + (size_t)b * max_log, max_log, 0};
+    SqpResult r = sqp_solve(P, T, a.Ts, a.N, g, step, trial, filt, cur_u + b * NU, rb + (size_t)b * a.S * RB_DOUBLES, 1, RB_DOUBLES, ws, a.qp,
+                            max_log > 0 ? &lg : nullptr);
+    a.status[b] = r.status; a.iters[b] = r.iters;
+    n_logged[b] = lg.n;
+}
+__global__ void k_transpose_rb_out(const double* rb_soa, int NS, int n, double* rb_aos) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * RB_DOUBLES) return;
+    int s = i / RB_DOUBLES, e = i % RB_DOUBLES;
+    rb_aos[i] = rb_soa[(size_t)e * NS + s];
+}
+__global__ void k_scatter_q(const double* q_aos, int n, int NS, double* qs) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NS * DOF) return;
+    int j = i / NS, s = i % NS;
+    qs[i] = (s < n) ? q_aos[s * DOF + j] : 0.0;
+}
+__global__ void k_warm_io(double* warm_soa, double* hor_aos, int B, int HN, int to_aos) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)B * HN) return;
+    int b = (int)(i / HN), e = (int)(i % HN);
+    if (to_aos) hor_aos[i] = warm_soa[(size_t)e * B + b];
+    else warm_soa[(size_t)e * B + b] = hor_aos[i];
+}
+// Integrator::simTimeStep (integrator.cpp:55-68): (int)(ts/1e-3) RK4 steps of the (linear) model
+__global__ void k_sim_step(const double* x, const double* u, double ts, int B, double* xn) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const double fine = 0.001;
+    const int steps = (int)(ts / fine);
+    double s[NX];
+    for (int i = 0; i < NX; i++) s[i] = x[b * NX + i];
+    const double* uu = u + b * NU;
+    for (int it = 0; it < steps; it++) {
+        // RK4 on f = [dq; vs; dVs] (model.cpp:31-45), written out stage by stage like integrator.cpp:29-43
+        double k1[NX], k2[NX], k3[NX], k4[NX];
+        for (int i = 0; i < 7; i++) k1[i] = k2[i] = k3[i] = k4[i] = uu[i];
+        k1[8] = k2[8] = k3[8] = k4[8] = uu[7];
+        k1[7] = s[8];
+        k2[7] = s[8] + fine / 2. * k1[8];
+        k3[7] = s[8] + fine / 2. * k2[8];
+        k4[7] = s[8] + fine * k3[8];
+        for (int i = 0; i < NX; i++) s[i] = s[i] + fine * (k1[i] / 6. + k2[i] / 3. + k3[i] / 3. + k4[i] / 6.);
+    }
+    for (int i = 0; i < NX; i++) xn[b * NX + i] = s[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CK(call)                                                                                                     \
+    do {                                                                                                             \
+        cudaError_t e_ = (call);                                                                                     \
+        if (e_ != cudaSuccess) return fail(MPCC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+struct mpcc_cuda_handle {
+    mpcc_cuda_config cfg;
+    int B, N, S;
+    size_t NS;
+    cudaStream_t stream = nullptr;
+    bool have_nn = false, have_params = false, have_track = false;
+    int n_param_sets = 0, n_tracks = 0;
+    int num_sms = 148;
+    // device memory
+    Params* d_params = nullptr;
+    TrackTable* d_tracks = nullptr;
+    int32_t* d_track_id = nullptr;
+    double *d_x0 = nullptr, *d_u0 = nullptr, *d_obs = nullptr, *d_obs_dummy = nullptr;
+    double *d_warm = nullptr, *d_step = nullptr, *d_trial = nullptr, *d_filt = nullptr, *d_ws = nullptr, *d_qs = nullptr, *d_rb = nullptr;
+    WarmFlags* d_flags = nullptr;
+    double *d_u_out = nullptr, *d_horizon = nullptr;
+    int32_t *d_status = nullptr, *d_iters = nullptr, *d_ok = nullptr, *d_qp_iters = nullptr, *d_qp_fail = nullptr;
+    double *d_wpack = nullptr, *d_bias = nullptr, *d_w_out_env = nullptr, *d_w_out_self = nullptr;
+    int64_t launches = 0;
+    std::vector<double> h_params;  // host copy of set 0 (validation)
+    std::vector<void*> allocs;
+
+    template <class T>
+    cudaError_t alloc(T** p, size_t count) {
+        cudaError_t e = cudaMalloc((void**)p, count * sizeof(T));
+        if (e == cudaSuccess) { allocs.push_back(*p); e = cudaMemsetAsync(*p, 0, count * sizeof(T), stream); }
+        return e;
+    }
+};
+
+static CycleArgs make_args(mpcc_cuda_handle* h, double* d_x0, const double* d_u0, const double* d_obs) {
+    CycleArgs a;
+    a.B = h->B; a.N = h->N; a.S = h->S; a.Ts = h->cfg.Ts;
+    a.params = h->d_params; a.params_per_instance = (h->n_param_sets > 1) ? 1 : 0;
+    a.tracks = h->d_tracks; a.track_id = h->d_track_id;
+    a.x0 = d_x0; a.u0 = d_u0; a.obs = d_obs;
+    a.warm = h->d_warm; a.step = h->d_step; a.trial = h->d_trial; a.filt = h->d_filt; a.ws = h->d_ws; a.flags = h->d_flags;
+    a.qs = h->d_qs; a.rb = h->d_rb; a.u_out = h->d_u_out; a.horizon = h->d_horizon;
+    a.status = h->d_status; a.iters = h->d_iters; a.ok = h->d_ok; a.qp_iters = h->d_qp_iters; a.qp_fail = h->d_qp_fail;
+    a.qp = QpOptions{h->cfg.qp_max_iter, h->cfg.qp_eps};
+    return a;
+}
+
+static int launch_robot_data(mpcc_cuda_handle* h, const double* d_obs, int S_for_obs) {
+    const int NS = (int)h->NS;
+    k_kin<<<(NS + 127) / 128, 128, 0, h->stream>>>(h->d_qs, h->d_rb, NS);
+    MlpArgs m;
+    m.wpack = h->d_wpack; m.bias = h->d_bias; m.w_out_env = h->d_w_out_env; m.w_out_self = h->d_w_out_self;
+    m.qs = h->d_qs; m.obs = d_obs; m.rb = h->d_rb; m.NS = NS; m.S = S_for_obs;
+    m.n_tiles = (NS + MLP_TILE_S - 1) / MLP_TILE_S;
+    int grid = m.n_tiles < h->num_sms ? m.n_tiles : h->num_sms;
+    k_mlp<<<grid, MLP_THREADS, MLP_SMEM_BYTES, h->stream>>>(m);
+    h->launches += 2;
+    CK(cudaGetLastError());
+    return MPCC_OK;
+}
+
+static int check_ready(mpcc_cuda_handle* h) {
+    if (!h) return fail(MPCC_ERR_INVALID, "null handle");
+    if (!h->have_nn) return fail(MPCC_ERR_STATE, "networks not uploaded (mpcc_cuda_upload_nn / mpcc_cuda_load_nn)");
+    if (!h->have_params) return fail(MPCC_ERR_STATE, "parameters not set (mpcc_cuda_set_params)");
+    if (!h->have_track) return fail(MPCC_ERR_STATE, "track not set (mpcc_cuda_set_tracks)");
+    return MPCC_OK;
+}
+
+extern "C" {
+
+const char* mpcc_cuda_last_error(void) { return g_err.c_str(); }
+
+int mpcc_cuda_create(const mpcc_cuda_config* cfg, mpcc_cuda_handle** out) {
+    if (!cfg || !out) return fail(MPCC_ERR_INVALID, "null argument");
+    if (cfg->batch < 1) return fail(MPCC_ERR_INVALID, "batch must be >= 1");
+    if (cfg->horizon < 2 || cfg->horizon > MAX_N) return fail(MPCC_ERR_INVALID, "horizon must be in [2, 64]");
+    if (!(cfg->Ts > 0)) return fail(MPCC_ERR_INVALID, "Ts must be positive");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return fail(MPCC_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(MPCC_ERR_INVALID, "device ordinal out of range");
+    CK(cudaSetDevice(cfg->device));
+    mpcc_cuda_handle* h = new mpcc_cuda_handle();
+    h->cfg = *cfg;
+    if (h->cfg.qp_max_iter <= 0) h->cfg.qp_max_iter = 60;
+    if (!(h->cfg.qp_eps > 0)) h->cfg.qp_eps = 1e-9;
+    h->B = cfg->batch; h->N = cfg->horizon; h->S = cfg->horizon + 1; h->NS = (size_t)h->B * h->S;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, cfg->device));
+    h->num_sms = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    const size_t B = h->B, S = h->S, HN = S * HZ;
+    cudaError_t ae = cudaSuccess;
+    auto A = [&](cudaError_t r) { if (ae == cudaSuccess) ae = r; };
+    A(h->alloc(&h->d_track_id, B));
+    A(h->alloc(&h->d_x0, B * NX)); A(h->alloc(&h->d_u0, B * NU)); A(h->alloc(&h->d_obs, B * 4)); A(h->alloc(&h->d_obs_dummy, B * 4));
+    A(h->alloc(&h->d_warm, B * HN)); A(h->alloc(&h->d_step, B * HN)); A(h->alloc(&h->d_trial, B * HN));
+    A(h->alloc(&h->d_filt, B * FILT_DOUBLES)); A(h->alloc(&h->d_ws, B * S * STAGE_WS));
+    A(h->alloc(&h->d_qs, h->NS * DOF)); A(h->alloc(&h->d_rb, h->NS * RB_DOUBLES));
+    A(h->alloc(&h->d_flags, B));
+    A(h->alloc(&h->d_u_out, B * NU)); A(h->alloc(&h->d_horizon, B * HN));
+    A(h->alloc(&h->d_status, B)); A(h->alloc(&h->d_iters, B)); A(h->alloc(&h->d_ok, B)); A(h->alloc(&h->d_qp_iters, B)); A(h->alloc(&h->d_qp_fail, B));
+    A(h->alloc(&h->d_wpack, (size_t)MLP_NCHUNK * MLP_CHUNK_D)); A(h->alloc(&h->d_bias, MLP_BIAS_TOTAL));
+    A(h->alloc(&h->d_w_out_env, 9 * 256)); A(h->alloc(&h->d_w_out_self, 64));
+    if (ae != cudaSuccess) { mpcc_cuda_destroy(h); return fail(MPCC_ERR_CUDA, std::string("device allocation failed: ") + cudaGetErrorString(ae)); }
+    std::vector<double> dummy(B * 4);
+    for (size_t b = 0; b < B; b++) { dummy[4 * b] = 3; dummy[4 * b + 1] = 3; dummy[4 * b + 2] = 3; dummy[4 * b + 3] = 0; }  // mpc.cpp:97-100
+    CK(cudaMemcpyAsync(h->d_obs_dummy, dummy.data(), dummy.size() * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaFuncSetAttribute(k_mlp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_SMEM_BYTES));
+    CK(cudaStreamSynchronize(h->stream));
+    *out = h;
+    return MPCC_OK;
+}
+
+int mpcc_cuda_destroy(mpcc_cuda_handle* h) {
+    if (!h) return MPCC_OK;
+    cudaSetDevice(h->cfg.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (void* p : h->allocs) cudaFree(p);
+    if (h->d_params) cudaFree(h->d_params);
+    if (h->d_tracks) cudaFree(h->d_tracks);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return MPCC_OK;
+}
+
+int mpcc_cuda_upload_nn(mpcc_cuda_handle* h, const double* self_w, const double* self_b, const double* env_w, const double* env_b) {
+    if (!h || !self_w || !self_b || !env_w || !env_b) return fail(MPCC_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(h->cfg.device));
+    const double* eW[5];
+    const double* sW[3];
+    const int e_out[5] = {256, 256, 256, 256, 9}, e_in[5] = {30, 256, 256, 256, 256};
+    const int s_out[3] = {256, 64, 1}, s_in[3] = {21, 256, 64};
+    size_t o = 0;
+    for (int l = 0; l < 5; l++) { eW[l] = env_w + o; o += (size_t)e_out[l] * e_in[l]; }
+    o = 0;
+    for (int l = 0; l < 3; l++) { sW[l] = self_w + o; o += (size_t)s_out[l] * s_in[l]; }
+    std::vector<double> pack((size_t)MLP_NCHUNK * MLP_CHUNK_D);
+    pack_mlp_weights(eW, sW, pack.data());
+    std::vector<double> bias(MLP_BIAS_TOTAL);
+    std::memcpy(&bias[MLP_BIAS_ENV], env_b, (4 * 256 + 9) * 8);
+    std::memcpy(&bias[MLP_BIAS_SELF0], self_b, (256 + 64 + 1) * 8);
+    CK(cudaMemcpyAsync(h->d_wpack, pack.data(), pack.size() * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_bias, bias.data(), bias.size() * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_w_out_env, eW[4], 9 * 256 * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_w_out_self, sW[2], 64 * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->have_nn = true;
+    return MPCC_OK;
+}
+
+int mpcc_cuda_load_nn(mpcc_cuda_handle* h, const char* self_path, const char* env_path) {
+    if (!h || !self_path || !env_path) return fail(MPCC_ERR_INVALID, "null argument");
+    try {
+        auto load = [](const std::string& p, const std::vector<std::pair<int, int>>& dims) {
+            bool packed = p.size() > 4 && p.substr(p.size() - 4) == ".f64";
+            MlpWeights m = packed ? load_mlp_packed(p) : load_mlp_text(p, dims);
+            if (m.W.size() != dims.size()) throw std::runtime_error("nn: unexpected layer count in '" + p + "'");
+            for (size_t l = 0; l < dims.size(); l++)
+                if (m.out_dim[l] != dims[l].first || m.in_dim[l] != dims[l].second) throw std::runtime_error("nn: unexpected layer shape in '" + p + "'");
+            return m;
+        };
+        MlpWeights s = load(self_path, {{256, 21}, {64, 256}, {1, 64}});
+        MlpWeights e = load(env_path, {{256, 30}, {256, 256}, {256, 256}, {256, 256}, {9, 256}});
+        std::vector<double> sw, sb, ew, eb;
+        for (auto& w : s.W) sw.insert(sw.end(), w.begin(), w.end());
+        for (auto& b : s.b) sb.insert(sb.end(), b.begin(), b.end());
+        for (auto& w : e.W) ew.insert(ew.end(), w.begin(), w.end());
+        for (auto& b : e.b) eb.insert(eb.end(), b.begin(), b.end());
+        return mpcc_cuda_upload_nn(h, sw.data(), sb.data(), ew.data(), eb.data());
+    } catch (const std::exception& ex) {
+        return fail(MPCC_ERR_IO, ex.what());
+    }
+}
+
+int mpcc_cuda_set_params(mpcc_cuda_handle* h, const double* params, int32_t n_sets) {
+    if (!h || !params) return fail(MPCC_ERR_INVALID, "null argument");
+    if (n_sets != 1 && n_sets != h->B) return fail(MPCC_ERR_INVALID, "n_sets must be 1 or batch");
+    for (int s = 0; s < n_sets; s++) {
+        const Params& p = *(const Params*)(params + (size_t)s * PARAMS_DOUBLES);
+        if (p.max_iter < 1 || p.max_iter > MAX_SQP_ITER) return fail(MPCC_ERR_INVALID, "sqp.max_iter must be in [1, 128]");
+        if (p.line_search_max_iter < 1) return fail(MPCC_ERR_INVALID, "sqp.line_search_max_iter must be >= 1");
+        if (p.do_SOC != 0 || p.use_BFGS != 0) return fail(MPCC_ERR_INVALID, "sqp.do_SOC / sqp.use_BFGS are not implemented on this path (reference defaults: false)");
+        for (int i = 0; i < NX; i++) if (!(p.Tx[i] > 0)) return fail(MPCC_ERR_INVALID, "normalization entries must be positive");
+        for (int i = 0; i < NU; i++) if (!(p.Tu[i] > 0)) return fail(MPCC_ERR_INVALID, "normalization entries must be positive");
+    }
+    CK(cudaSetDevice(h->cfg.device));
+    if (h->d_params && h->n_param_sets != n_sets) { CK(cudaFree(h->d_params)); h->d_params = nullptr; }
+    if (!h->d_params) CK(cudaMalloc((void**)&h->d_params, (size_t)n_sets * sizeof(Params)));
+    CK(cudaMemcpyAsync(h->d_params, params, (size_t)n_sets * sizeof(Params), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->n_param_sets = n_sets;
+    h->h_params.assign(params, params + PARAMS_DOUBLES);
+    h->have_params = true;
+    return MPCC_OK;
+}
+
+int mpcc_load_params_json(const char* model_path, const char* cost_path, const char* bounds_path, const char* normalization_path,
+                          const char* sqp_path, const char* const* over_keys, const double* over_vals, int32_t n_over, double* params_out) {
+    if (!model_path || !cost_path || !bounds_path || !normalization_path || !sqp_path || !params_out) return fail(MPCC_ERR_INVALID, "null argument");
+    try {
+        PathToJson p;
+        p.param_path = model_path; p.cost_path = cost_path; p.bounds_path = bounds_path; p.normalization_path = normalization_path; p.sqp_path = sqp_path;
+        ParamValue ov;
+        for (int i = 0; i < n_over; i++) {
+            std::string k = over_keys[i];
+            size_t dot = k.find('.');
+            if (dot == std::string::npos) return fail(MPCC_ERR_INVALID, "override key must be written file.key: " + k);
+            std::string f = k.substr(0, dot), key = k.substr(dot + 1);
+            if (f == "model" || f == "param") ov.param[key] = over_vals[i];
+            else if (f == "cost") ov.cost[key] = over_vals[i];
+            else if (f == "bounds") ov.bounds[key] = over_vals[i];
+            else if (f == "normalization") ov.normalization[key] = over_vals[i];
+            else if (f == "sqp") ov.sqp[key] = over_vals[i];
+            else return fail(MPCC_ERR_INVALID, "unknown override file: " + f);
+        }
+        Params pr = load_params(p, ov);
+        std::memcpy(params_out, &pr, sizeof(pr));
+        return MPCC_OK;
+    } catch (const std::exception& ex) {
+        return fail(MPCC_ERR_IO, ex.what());
+    }
+}
+
+int mpcc_fit_track(int32_t n, const double* X, const double* Y, const double* Z, const double* R, double* table_out) {
+    if (!X || !Y || !Z || !R || !table_out) return fail(MPCC_ERR_INVALID, "null argument");
+    try {
+        Waypoints w;
+        w.X.assign(X, X + n); w.Y.assign(Y, Y + n); w.Z.assign(Z, Z + n); w.R.assign(R, R + (size_t)9 * n);
+        fit_track(w, *(TrackTable*)table_out);
+        return MPCC_OK;
+    } catch (const std::exception& ex) {
+        return fail(MPCC_ERR_INVALID, ex.what());
+    }
+}
+
+int mpcc_load_track_json(const char* track_path, const double* init_position3, double* table_out) {
+    if (!track_path || !table_out) return fail(MPCC_ERR_INVALID, "null argument");
+    try {
+        Waypoints w = load_track_json(track_path);
+        if (init_position3) shift_track(w, init_position3);
+        fit_track(w, *(TrackTable*)table_out);
+        return MPCC_OK;
+    } catch (const std::exception& ex) {
+        return fail(MPCC_ERR_IO, ex.what());
+    }
+}
+
+int mpcc_cuda_reset(mpcc_cuda_handle* h) {
+    if (!h) return fail(MPCC_ERR_INVALID, "null handle");
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaMemsetAsync(h->d_flags, 0, (size_t)h->B * sizeof(WarmFlags), h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return MPCC_OK;
+}
+
+int mpcc_cuda_set_tracks(mpcc_cuda_handle* h, const double* tables, int32_t n_tracks, const int32_t* track_of_instance) {
+    if (!h || !tables || n_tracks < 1) return fail(MPCC_ERR_INVALID, "bad argument");
+    std::vector<int32_t> ids(h->B, 0);
+    if (track_of_instance)
+        for (int b = 0; b < h->B; b++) {
+            if (track_of_instance[b] < 0 || track_of_instance[b] >= n_tracks) return fail(MPCC_ERR_INVALID, "track index out of range");
+            ids[b] = track_of_instance[b];
+        }
+    CK(cudaSetDevice(h->cfg.device));
+    if (h->d_tracks && h->n_tracks != n_tracks) { CK(cudaFree(h->d_tracks)); h->d_tracks = nullptr; }
+    if (!h->d_tracks) CK(cudaMalloc((void**)&h->d_tracks, (size_t)n_tracks * sizeof(TrackTable)));
+    CK(cudaMemcpyAsync(h->d_tracks, tables, (size_t)n_tracks * sizeof(TrackTable), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_track_id, ids.data(), ids.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->n_tracks = n_tracks;
+    h->have_track = true;
+    return mpcc_cuda_reset(h);
+}
+
+int mpcc_cuda_run_cycle_device(mpcc_cuda_handle* h, double* d_x0, const double* d_u0, const double* d_obs) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (!d_x0 || !d_u0) return fail(MPCC_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(h->cfg.device));
+    const double* obs = d_obs ? d_obs : h->d_obs_dummy;
+    CycleArgs a = make_args(h, d_x0, d_u0, obs);
+    h->launches = 0;
+    k_prologue<<<(h->B + 63) / 64, 64, 0, h->stream>>>(a);
+    h->launches++;
+    rc = launch_robot_data(h, obs, h->S);
+    if (rc) return rc;
+    k_sqp_thread<<<(h->B + 31) / 32, 32, 0, h->stream>>>(a);
+    h->launches++;
+    CK(cudaGetLastError());
+    return MPCC_OK;
+}
+
+int mpcc_cuda_read_results(mpcc_cuda_handle* h, double* u_out, double* horizon, int32_t* status, int32_t* sqp_iters, int32_t* ok) {
+    if (!h) return fail(MPCC_ERR_INVALID, "null handle");
+    CK(cudaSetDevice(h->cfg.device));
+    const size_t B = h->B;
+    if (u_out) CK(cudaMemcpyAsync(u_out, h->d_u_out, B * NU * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (horizon) CK(cudaMemcpyAsync(horizon, h->d_horizon, B * h->S * HZ * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (status) CK(cudaMemcpyAsync(status, h->d_status, B * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (sqp_iters) CK(cudaMemcpyAsync(sqp_iters, h->d_iters, B * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (ok) CK(cudaMemcpyAsync(ok, h->d_ok, B * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return MPCC_OK;
+}
+
+int mpcc_cuda_run_cycle(mpcc_cuda_handle* h, double* x0, const double* u0, const double* obs, double* u_out, double* horizon,
+                        int32_t* status, int32_t* sqp_iters, int32_t* ok) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (!x0 || !u0) return fail(MPCC_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(h->cfg.device));
+    const size_t B = h->B;
+    CK(cudaMemcpyAsync(h->d_x0, x0, B * NX * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_u0, u0, B * NU * 8, cudaMemcpyHostToDevice, h->stream));
+    if (obs) CK(cudaMemcpyAsync(h->d_obs, obs, B * 4 * 8, cudaMemcpyHostToDevice, h->stream));
+    rc = mpcc_cuda_run_cycle_device(h, h->d_x0, h->d_u0, obs ? h->d_obs : nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(x0, h->d_x0, B * NX * 8, cudaMemcpyDeviceToHost, h->stream));
+    return mpcc_cuda_read_results(h, u_out, horizon, status, sqp_iters, ok);
+}
+
+int mpcc_cuda_result_pointers(mpcc_cuda_handle* h, double** d_u_out, double** d_horizon, int32_t** d_status, int32_t** d_iters, int32_t** d_ok) {
+    if (!h) return fail(MPCC_ERR_INVALID, "null handle");
+    if (d_u_out) *d_u_out = h->d_u_out;
+    if (d_horizon) *d_horizon = h->d_horizon;
+    if (d_status) *d_status = h->d_status;
+    if (d_iters) *d_iters = h->d_iters;
+    if (d_ok) *d_ok = h->d_ok;
+    return MPCC_OK;
+}
+void* mpcc_cuda_stream(mpcc_cuda_handle* h) { return h ? (void*)h->stream : nullptr; }
+int mpcc_cuda_synchronize(mpcc_cuda_handle* h) {
+    if (!h) return fail(MPCC_ERR_INVALID, "null handle");
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamSynchronize(h->stream));
+    return MPCC_OK;
+}
+
+int mpcc_cuda_get_warm_state(mpcc_cuda_handle* h, double* horizon, int32_t* valid, int32_t* failed) {
+    if (!h) return fail(MPCC_ERR_INVALID, "null handle");
+    CK(cudaSetDevice(h->cfg.device));
+    const int HN = h->S * HZ;
+    const size_t tot = (size_t)h->B * HN;
+    if (horizon) {
+        k_warm_io<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(h->d_warm, h->d_trial, h->B, HN, 1);  // d_trial is free between cycles
+        CK(cudaGetLastError());
+        // d_trial is SoA-sized scratch; here it temporarily holds the AoS copy
+        CK(cudaMemcpyAsync(horizon, h->d_trial, tot * 8, cudaMemcpyDeviceToHost, h->stream));
+    }
+    std::vector<WarmFlags> fl(h->B);
+    CK(cudaMemcpyAsync(fl.data(), h->d_flags, fl.size() * sizeof(WarmFlags), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int b = 0; b < h->B; b++) { if (valid) valid[b] = fl[b].valid; if (failed) failed[b] = fl[b].failed; }
+    return MPCC_OK;
+}
+int mpcc_cuda_set_warm_state(mpcc_cuda_handle* h, const double* horizon, const int32_t* valid, const int32_t* failed) {
+    if (!h || !horizon || !valid || !failed) return fail(MPCC_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(h->cfg.device));
+    const int HN = h->S * HZ;
+    const size_t tot = (size_t)h->B * HN;
+    CK(cudaMemcpyAsync(h->d_trial, horizon, tot * 8, cudaMemcpyHostToDevice, h->stream));
+    k_warm_io<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(h->d_warm, h->d_trial, h->B, HN, 0);
+    CK(cudaGetLastError());
+    std::vector<WarmFlags> fl(h->B);
+    for (int b = 0; b < h->B; b++) { fl[b].valid = valid[b]; fl[b].failed = failed[b]; }
+    CK(cudaMemcpyAsync(h->d_flags, fl.data(), fl.size() * sizeof(WarmFlags), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return MPCC_OK;
+}
+
+int mpcc_cuda_sim_time_step(mpcc_cuda_handle* h, const double* x, const double* u, double ts, double* x_next) {
+    if (!h || !x || !u || !x_next) return fail(MPCC_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(h->cfg.device));
+    const size_t B = h->B;
+    double* d_x = h->d_trial;            // scratch between cycles
+    double* d_xn = h->d_trial + B * NX;
+    CK(cudaMemcpyAsync(d_x, x, B * NX * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_u0, u, B * NU * 8, cudaMemcpyHostToDevice, h->stream));
+    k_sim_step<<<(h->B + 127) / 128, 128, 0, h->stream>>>(d_x, h->d_u0, ts, h->B, d_xn);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(x_next, d_xn, B * NX * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return MPCC_OK;
+}
+
+int mpcc_cuda_eval_robot_data(mpcc_cuda_handle* h, const double* q, const double* obs, int32_t n, double* rb_out) {
+    if (!h || !q || !rb_out) return fail(MPCC_ERR_INVALID, "null argument");
+    if (!h->have_nn) return fail(MPCC_ERR_STATE, "networks not uploaded");
+    if (n < 1 || (size_t)n > h->NS) return fail(MPCC_ERR_INVALID, "n must be in [1, batch*(N+1)]");
+    CK(cudaSetDevice(h->cfg.device));
+    const int NS = (int)h->NS;
+    // stage the AoS inputs in the (idle) workspace, obstacle per SAMPLE (S = 1)
+    double* d_q = h->d_ws;
+    double* d_o = h->d_ws + (size_t)NS * DOF;
+    double* d_out = d_o + (size_t)NS * 4;
+    if ((size_t)NS * (DOF + 4 + RB_DOUBLES) > (size_t)h->B * h->S * STAGE_WS) return fail(MPCC_ERR_INVALID, "workspace too small");
+    CK(cudaMemcpyAsync(d_q, q, (size_t)n * DOF * 8, cudaMemcpyHostToDevice, h->stream));
+    std::vector<double> o((size_t)NS * 4);
+    for (int i = 0; i < NS; i++) {
+        if (obs && i < n) for (int c = 0; c < 4; c++) o[4 * (size_t)i + c] = obs[4 * (size_t)i + c];
+        else { o[4 * (size_t)i] = 3; o[4 * (size_t)i + 1] = 3; o[4 * (size_t)i + 2] = 3; o[4 * (size_t)i + 3] = 0; }
+    }
+    CK(cudaMemcpyAsync(d_o, o.data(), o.size() * 8, cudaMemcpyHostToDevice, h->stream));
+    k_scatter_q<<<(NS * DOF + 255) / 256, 256, 0, h->stream>>>(d_q, n, NS, h->d_qs);
+    int rc = launch_robot_data(h, d_o, 1);
+    if (rc) return rc;
+    k_transpose_rb_out<<<(n * RB_DOUBLES + 255) / 256, 256, 0, h->stream>>>(h->d_rb, NS, n, d_out);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(rb_out, d_out, (size_t)n * RB_DOUBLES * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return MPCC_OK;
+}
+
+int mpcc_cuda_eval_stage(mpcc_cuda_handle* h, const double* x, const double* u, const double* u_prev, const double* u_next,
+                         const double* x_next, const double* rb, const int32_t* k, int32_t n, double* lin_out) {
+    if (!h || !x || !u || !u_prev || !u_next || !x_next || !rb || !k || !lin_out) return fail(MPCC_ERR_INVALID, "null argument");
+    if (!h->have_params || !h->have_track) return fail(MPCC_ERR_STATE, "parameters / track not set");
+    if (n < 1) return fail(MPCC_ERR_INVALID, "n must be >= 1");
+    CK(cudaSetDevice(h->cfg.device));
+    const size_t per = NX + NU + DOF + DOF + NX + RB_DOUBLES + LIN_SIZE + 1;
+    if ((size_t)n * per > (size_t)h->B * h->S * STAGE_WS) return fail(MPCC_ERR_INVALID, "n too large for the workspace");
+    double* p = h->d_ws;
+    double *dx = p; p += (size_t)n * NX;
+    double *du = p; p += (size_t)n * NU;
+    double *dup = p; p += (size_t)n * DOF;
+    double *dun = p; p += (size_t)n * DOF;
+    double *dxn = p; p += (size_t)n * NX;
+    double *drb = p; p += (size_t)n * RB_DOUBLES;
+    double *dout = p; p += (size_t)n * LIN_SIZE;
+    int32_t* dk = (int32_t*)p;
+    CK(cudaMemcpyAsync(dx, x, (size_t)n * NX * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(du, u, (size_t)n * NU * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(dup, u_prev, (size_t)n * DOF * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(dun, u_next, (size_t)n * DOF * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(dxn, x_next, (size_t)n * NX * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(drb, rb, (size_t)n * RB_DOUBLES * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(dk, k, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+    k_eval_stage<<<(n + 63) / 64, 64, 0, h->stream>>>(h->d_params, h->d_tracks, h->cfg.Ts, h->N, dx, du, dup, dun, dxn, drb, dk, n, dout);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(lin_out, dout, (size_t)n * LIN_SIZE * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return MPCC_OK;
+}
+
+int mpcc_cuda_eval_track(mpcc_cuda_handle* h, const double* s, int32_t n, double* out) {
+    if (!h || !s || !out) return fail(MPCC_ERR_INVALID, "null argument");
+    if (!h->have_track) return fail(MPCC_ERR_STATE, "track not set");
+    if (n < 1 || (size_t)n * 22 > (size_t)h->B * h->S * STAGE_WS) return fail(MPCC_ERR_INVALID, "bad n");
+    CK(cudaSetDevice(h->cfg.device));
+    double* ds = h->d_ws;
+    double* dout = h->d_ws + n;
+    CK(cudaMemcpyAsync(ds, s, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+    k_eval_track<<<(n + 127) / 128, 128, 0, h->stream>>>(h->d_tracks, ds, n, dout);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, dout, (size_t)n * 21 * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return MPCC_OK;
+}
+
+int mpcc_cuda_solve_ocp(mpcc_cuda_handle* h, double* guess, const double* rb, const double* cur_u, int32_t n, int32_t* status, int32_t* iters,
+                        double* steps, double* alphas, int32_t max_log, int32_t* n_logged) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (!guess || !rb || !cur_u || !status || !iters) return fail(MPCC_ERR_INVALID, "null argument");
+    if (n < 1 || n > h->B) return fail(MPCC_ERR_INVALID, "n must be in [1, batch]");
+    if (max_log < 0) max_log = 0;
+    if (max_log > 0 && (!alphas || !n_logged)) return fail(MPCC_ERR_INVALID, "log arrays missing");
+    CK(cudaSetDevice(h->cfg.device));
+    const size_t HN = (size_t)h->S * HZ;
+    double *d_g = nullptr, *d_rb = nullptr, *d_cu = nullptr, *d_steps = nullptr, *d_alphas = nullptr;
+    int32_t *d_qpok = nullptr, *d_nl = nullptr;
+    const int ml = max_log > 0 ? max_log : 1;
+    CK(cudaMalloc((void**)&d_g, n * HN * 8));
+    CK(cudaMalloc((void**)&d_rb, (size_t)n * h->S * RB_DOUBLES * 8));
+    CK(cudaMalloc((void**)&d_cu, (size_t)n * NU * 8));
+    if (steps && max_log > 0) CK(cudaMalloc((void**)&d_steps, (size_t)n * ml * HN * 8));
+    CK(cudaMalloc((void**)&d_alphas, (size_t)n * ml * 8));
+    CK(cudaMalloc((void**)&d_qpok, (size_t)n * ml * 4));
+    CK(cudaMalloc((void**)&d_nl, (size_t)n * 4));
+    CK(cudaMemcpyAsync(d_g, guess, n * HN * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_rb, rb, (size_t)n * h->S * RB_DOUBLES * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_cu, cur_u, (size_t)n * NU * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(d_nl, 0, (size_t)n * 4, h->stream));
+    CycleArgs a = make_args(h, h->d_x0, h->d_u0, h->d_obs_dummy);
+    k_solve_ocp<<<(n + 31) / 32, 32, 0, h->stream>>>(a, d_g, d_rb, d_cu, n, d_steps, d_alphas, d_qpok, max_log, d_nl);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(guess, d_g, n * HN * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(status, h->d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(iters, h->d_iters, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (max_log > 0) {
+        if (steps) CK(cudaMemcpyAsync(steps, d_steps, (size_t)n * ml * HN * 8, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(alphas, d_alphas, (size_t)n * ml * 8, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(n_logged, d_nl, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    cudaFree(d_g); cudaFree(d_rb); cudaFree(d_cu); cudaFree(d_steps); cudaFree(d_alphas); cudaFree(d_qpok); cudaFree(d_nl);
+    return MPCC_OK;
+}
+
+int mpcc_cuda_get_stats(mpcc_cuda_handle* h, int64_t* st) {
+    if (!h || !st) return fail(MPCC_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(h->cfg.device));
+    const size_t B = h->B;
+    std::vector<int32_t> status(B), iters(B), ok(B), qi(B), qf(B);
+    CK(cudaMemcpyAsync(status.data(), h->d_status, B * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(iters.data(), h->d_iters, B * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(ok.data(), h->d_ok, B * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(qi.data(), h->d_qp_iters, B * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(qf.data(), h->d_qp_fail, B * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    st[0] = h->launches; st[1] = st[2] = st[3] = st[4] = st[5] = 0;
+    for (size_t b = 0; b < B; b++) { st[1] += iters[b]; st[2] += qi[b]; st[3] += qf[b]; st[4] += (status[b] == SOLVED); st[5] += ok[b]; }
+    return MPCC_OK;
+}
+
+}  // extern "C"
