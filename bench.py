@@ -1,0 +1,414 @@
+#!/usr/bin/env python
+"""Benchmark of the batched MPCC control cycle (BASELINE.json metric: batched MPCC SQP solves/sec, 4096 x N=20).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one process per GPU under torchrun)
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host cores (CPU oracle)
+
+One "step" = one closed-loop control cycle (mpcc::MPC::runMPC for every instance of the batch) followed by the
+plant step that produces the next cycle's inputs.  Workload = BASELINE configs[1] ("C2" in SURVEY.md 8d): 4096
+Panda instances per GPU, perturbed initial joint angles (seeded), same track, N = 20.  Prints ONE JSON line.
+
+`value`: device-resident inputs, CUDA events on the library's stream around every step, L2 flushed between steps.
+`e2e`  : the same cycle through the C-ABI call that takes HOST buffers (mpcc_cuda_run_cycle), pinned memory,
+         host->device and device->host copies inside the timed region.
+`roofline`: dominant kernel's algorithmic FP64 FLOPs / its live CUDA-event duration, against the FP64 FMA peak
+         measured in this run (MEASURED_PEAKS.json has no FP64 figure; the path is fp64 and tcgen05 has no f64 kind).
+`cpu_baseline`: the CPU oracle (restated reference algorithm) on a bounded sample, this box's host cores.
+"""
+import argparse
+import json
+import os
+import select
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "batched MPCC SQP solves/sec (4096xN=20)"
+UNIT = "solves/s"
+# algorithmic FLOPs: minimal MAC counts of both networks with 7 forward-mode tangent columns
+MLP_FLOP_PER_STAGE = 2.0 * 1746688
+KIN_FLOP_PER_STAGE = 2.0 * 9000
+NOMINAL_FP64_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12
+
+
+def q_home():
+    return np.array([0, 0, 0, -np.pi / 2, 0, np.pi / 2, np.pi / 4])
+
+
+def synthetic_inputs(B, seed):
+    """C2: q0 = q_home + U(-0.05, 0.05)^7, s0 = vs0 = 0, u0 = 0."""
+    rng = np.random.default_rng(seed)
+    x0 = np.tile(np.r_[q_home(), 0.0, 0.0], (B, 1))
+    x0[:, :7] += rng.uniform(-0.05, 0.05, (B, 7))
+    return x0, np.zeros((B, 8))
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "power_w_max": max(pw) if pw else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU side: persistent oracle workers (one process per core), driven step by step over pipes
+# ------------------------------------------------------------------------------------------------
+def cpu_worker_main(args):
+    """Child process: owns `per` oracle MPC instances (warm starts persist across steps like on the GPU).
+    Protocol on stdin/stdout: 'step' -> one closed-loop cycle for every instance -> 'done <seconds>'."""
+    from oracle import oracle as O
+    nn = O.OracleNN()
+    ee = O.fk(O.Q_HOME)[0]
+    X, Y, Z, R = O.load_track()
+    X, Y, Z = O.shift_track(X, Y, Z, ee)
+    x0, u0 = synthetic_inputs(args.per, 1000 + args.worker_id)
+    inst = []
+    for b in range(args.per):
+        o = O.OracleMPC(N=args.horizon, nn=nn)
+        o.set_track(X, Y, Z, R)
+        inst.append([o, x0[b], u0[b]])
+    print("ready", flush=True)
+    for line in sys.stdin:
+        if line.strip() != "step":
+            break
+        t0 = time.perf_counter()
+        for it in inst:
+            r = it[0].run(it[1], it[2])
+            it[2] = r["u0"]
+            it[1] = O.sim_time_step(r["x0"], r["u0"], 0.01)
+        print(f"done {time.perf_counter() - t0:.6f}", flush=True)
+
+
+class CpuPool:
+    def __init__(self, workers, per, horizon):
+        self.workers, self.per = workers, per
+        env = dict(os.environ, OMP_NUM_THREADS="1")
+        for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+            env.pop(k, None)
+        self.procs = [subprocess.Popen([sys.executable, str(ROOT / "bench.py"), "--cpu-worker", "--worker-id", str(i), "--per", str(per), "--horizon", str(horizon)],
+                                       stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True, env=env) for i in range(workers)]
+        for p in self.procs:
+            assert p.stdout.readline().strip() == "ready"
+
+    def step(self):
+        """One cycle for every instance of every worker; returns wall seconds."""
+        t0 = time.perf_counter()
+        for p in self.procs:
+            p.stdin.write("step\n"); p.stdin.flush()
+        for p in self.procs:
+            assert p.stdout.readline().startswith("done")
+        return time.perf_counter() - t0
+
+    def close(self):
+        for p in self.procs:
+            try:
+                p.stdin.close(); p.wait(timeout=5)
+            except Exception:
+                p.kill()
+
+
+def build_oracle():
+    subprocess.check_call(["make", "-s", "-C", str(ROOT / "oracle")])
+
+
+def cpu_baseline(horizon, budget_s=14.0):
+    """Bounded sample on the host cores: one process per core, each owning 2 instances; cold cycle untimed."""
+    build_oracle()
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    # single thread first (alone on the machine)
+    one = CpuPool(1, 2, horizon)
+    one.step()
+    t_single, n_single = 0.0, 0
+    while t_single < budget_s * 0.3:
+        t_single += one.step(); n_single += 2
+    one.close()
+    pool = CpuPool(cores, 2, horizon)
+    pool.step()
+    t, n = 0.0, 0
+    while t < budget_s * 0.7:
+        t += pool.step(); n += cores * 2
+    pool.close()
+    return {"value": n / t, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} warm-started closed-loop solves (N={horizon}) of the C2 workload over {cores} processes x 2 instances, oracle/liborc.so (-O2), first (cold) cycle untimed",
+            "single_thread": {"value": n_single / t_single, "cores": 1, "sample": f"{n_single} solves"}}
+
+
+def run_reference(args):
+    """--impl reference: the reference algorithm (CPU oracle port; the reference itself cannot be built here)
+    on every host core.  A step = one closed-loop cycle of a bounded sample batch (cores x 2 instances)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    build_oracle()
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    per = 2
+    pool = CpuPool(cores, per, args.horizon)
+    for _ in range(max(args.warmup, 1)):
+        pool.step()
+    ts = [pool.step() for _ in range(args.steps)]
+    pool.close()
+    total = float(np.sum(ts))
+    n = cores * per * args.steps
+    val = n / total
+    sample = f"{cores * per} instances per step ({cores} processes x {per}), N={args.horizon}, warm-started closed loop"
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "C2: 4096 Panda instances, perturbed q0, default track, N=20 (bounded sample per step)", "horizon": args.horizon, "sample": sample},
+           "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU side
+# ------------------------------------------------------------------------------------------------
+class DevPtr:
+    """Wrap a raw device pointer of the library as a __cuda_array_interface__ object (torch.as_tensor reads it)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 3, "strides": None}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import mpcc_manipulator_b200 as M
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: there is no CPU fallback for the product path (use --impl reference for the host baseline)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    B, N = args.batch, args.horizon
+    S = N + 1
+    mpc = M.BatchMPC(B, N, device=local)
+    # track shifted to the EE position at q_home, as main.cpp does (track.cpp:58-60); FK through the library itself
+    mpc.load_nn()
+    mpc.set_params(M.load_default_params())
+    ee = mpc.eval_robot_data(q_home()[None])[0, 7:10]
+    mpc.set_tracks(M.load_track_json(None, ee))
+
+    stream = torch.cuda.ExternalStream(mpc.stream, device=local)
+    x_host, u_host = synthetic_inputs(B, seed=rank)
+    p_u, p_hor, p_st, p_it, p_ok = mpc.result_pointers()
+    with torch.cuda.stream(stream):
+        x = torch.from_numpy(x_host).cuda(non_blocking=False)
+        xn = torch.empty_like(x)
+        u = torch.from_numpy(u_host).cuda()
+        u_out = torch.as_tensor(DevPtr(p_u, (B, 8), "<f8"), device=f"cuda:{local}")
+        st_out = torch.as_tensor(DevPtr(p_st, (B,), "<i4"), device=f"cuda:{local}")
+        it_out = torch.as_tensor(DevPtr(p_it, (B,), "<i4"), device=f"cuda:{local}")
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")  # > 126 MB L2
+        if world > 1:
+            g_u = torch.empty((world * B, 8), dtype=torch.float64, device=f"cuda:{local}")
+            g_st = torch.empty((world * B, 2), dtype=torch.int32, device=f"cuda:{local}")
+            st_pack = torch.empty((B, 2), dtype=torch.int32, device=f"cuda:{local}")
+    launches = {"n": 0}
+
+    def step():
+        """device-resident closed-loop step: cycle -> (gather) -> plant"""
+        nonlocal x, xn
+        mpc.run_cycle_device(x.data_ptr(), u.data_ptr())
+        launches["n"] += 4
+        with torch.cuda.stream(stream):
+            if world > 1:
+                # the path's only collective: gather the applied controls and per-instance status/iterations
+                st_pack[:, 0] = st_out; st_pack[:, 1] = it_out
+                dist.all_gather_into_tensor(g_u, u_out)
+                dist.all_gather_into_tensor(g_st, st_pack)
+            u.copy_(u_out)
+        mpc.sim_time_step_device(x.data_ptr(), u.data_ptr(), xn.data_ptr())
+        launches["n"] += 1
+        x, xn = xn, x
+
+    for _ in range(args.warmup):
+        step()
+    mpc.synchronize()
+    mpc.set_profiling(True)
+    sampler = ClockSampler(local)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ktimes = np.zeros((args.steps, 4))
+    stats_acc = {}
+    launches["n"] = 0
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        with torch.cuda.stream(stream):
+            flush.zero_()  # L2 flush between timed iterations (outside the event pair)
+            ev[i][0].record(stream)
+        step()
+        with torch.cuda.stream(stream):
+            ev[i][1].record(stream)
+        ktimes[i] = mpc.kernel_times()
+        if i == args.steps - 1:
+            st = mpc.stats()
+            stats_acc = st
+    mpc.synchronize()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if rank == 0 else None
+    step_ms = np.array([a.elapsed_time(b) for a, b in ev])
+    total_ms = float(step_ms.sum())
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms_max = float(t.item())
+    else:
+        total_ms_max = total_ms
+    value = world * B * args.steps / (total_ms_max * 1e-3)
+    mpc.set_profiling(False)
+
+    # ---- e2e: HOST buffers through mpcc_cuda_run_cycle (pinned), copies inside the timed region ----
+    import ctypes as C
+    from mpcc_manipulator_b200 import capi
+    hx = torch.empty((B, 9), dtype=torch.float64).pin_memory(); hu = torch.empty((B, 8), dtype=torch.float64).pin_memory()
+    huo = torch.empty((B, 8), dtype=torch.float64).pin_memory()
+    hst = torch.empty(B, dtype=torch.int32).pin_memory(); hit = torch.empty(B, dtype=torch.int32).pin_memory(); hok = torch.empty(B, dtype=torch.int32).pin_memory()
+    hx.copy_(x.cpu()); hu.copy_(u.cpu())
+    Ts = 0.01
+
+    def e2e_step():
+        rc = capi.lib().mpcc_cuda_run_cycle(mpc.h, C.c_void_p(hx.data_ptr()), C.c_void_p(hu.data_ptr()), None, C.c_void_p(huo.data_ptr()), None,
+                                            C.c_void_p(hst.data_ptr()), C.c_void_p(hit.data_ptr()), C.c_void_p(hok.data_ptr()))
+        if rc != 0:
+            raise RuntimeError(capi.lib().mpcc_cuda_last_error().decode())
+        # host-side plant step (exact for the linear model; integrator.cpp:55-68), next cycle's inputs
+        xs, us = hx.numpy(), huo.numpy()
+        xs[:, :7] += Ts * us[:, :7]
+        xs[:, 7] += Ts * xs[:, 8] + 0.5 * Ts * Ts * us[:, 7]
+        xs[:, 8] += Ts * us[:, 7]
+        hu.copy_(huo)
+
+    e2e_steps = max(3, min(args.steps, 20))
+    for _ in range(2):
+        e2e_step()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    t_e2e = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([t_e2e], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_e2e = float(t.item())
+    e2e_val = world * B * e2e_steps / t_e2e
+    h2d = B * (9 + 8) * 8
+    d2h = B * (9 + 8) * 8 + 3 * B * 4
+
+    out = None
+    if rank == 0:
+        km = ktimes.mean(axis=0)
+        names = ["k_prologue", "k_kin", "k_mlp", "k_sqp"]
+        dom = int(np.argmax(km))
+        peak = M.fp64_peak(local)
+        mlp_flop = B * S * MLP_FLOP_PER_STAGE
+        kernels = {n: round(float(t), 4) for n, t in zip(names, km)}
+        roof = {"bound": "fp64", "kernel": "k_mlp", "achieved": mlp_flop / (km[2] * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                "frac": mlp_flop / (km[2] * 1e-3) / 1e12 / peak, "traffic": None,
+                "peak_source": "FP64 FMA microbenchmark measured in this run (mpcc_cuda_fp64_peak); MEASURED_PEAKS.json holds no FP64 figure; nominal 148 SM x 64 FMA/clk x 1.965 GHz = %.1f" % NOMINAL_FP64_TFLOPS,
+                "algorithmic_flops_per_launch": mlp_flop, "kernel_ms": float(km[2]), "dominant_kernel": names[dom],
+                "kernel_share_of_step": {n: round(float(t / step_ms.mean()), 4) for n, t in zip(names, km)}}
+        hbm_peak = None
+        try:
+            hbm_peak = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"]
+        except Exception:
+            pass
+        alg_bytes = B * ((9 + 8 + 4) * 8 + 2 * (17 * N + 9) * 8 + 64 + 16)
+        roof["hbm"] = {"algorithmic_bytes_per_step": alg_bytes, "achieved_gbs": alg_bytes / (step_ms.mean() * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                       "note": "arithmetic intensity ~1e4 FLOP/B: HBM fraction is tiny by construction (SURVEY 8d)"}
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": "C2 (BASELINE configs[1]): 4096 Panda instances per GPU, q0 = q_home + U(-0.05,0.05) seeded, default track.json, N=20, closed loop",
+                          "batch_per_gpu": B, "horizon": N, "l2": "flushed (256 MiB memset) between timed steps", "parallelism": f"dp{world} (instances sharded, all_gather of u0/status only)"},
+               "latency_ms": {"p50": float(np.percentile(step_ms, 50)), "p99": float(np.percentile(step_ms, 99)), "max": float(step_ms.max())},
+               "clocks": clocks, "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                                         "api": "mpcc_cuda_run_cycle (host buffers, pinned)"},
+               "gpu_launches": launches["n"], "kernels_ms": kernels, "roofline": roof,
+               "last_step_stats": stats_acc, "wall_s_timed_region": t_wall}
+    mpc.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(N)
+        print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--horizon", type=int, default=20)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-worker", action="store_true")
+    ap.add_argument("--worker-id", type=int, default=0)
+    ap.add_argument("--per", type=int, default=2)
+    args = ap.parse_args()
+    if args.cpu_worker:
+        return cpu_worker_main(args)
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -120,6 +120,17 @@ int mpcc_cuda_set_warm_state(mpcc_cuda_handle* h, const double* horizon, const i
 /* Closed-loop plant step for the whole batch: Integrator::simTimeStep (integrator.cpp:55-68). Host buffers. */
 int mpcc_cuda_sim_time_step(mpcc_cuda_handle* h, const double* x, const double* u, double ts, double* x_next);
 
+/* Same plant step on DEVICE buffers ([B][9], [B][8] -> [B][9]), enqueued on the handle's stream. */
+int mpcc_cuda_sim_time_step_device(mpcc_cuda_handle* h, const double* d_x, const double* d_u, double ts, double* d_x_next);
+
+/* Instrumentation (the reference's ComputeTime, osqp_interface.h:71-79, per kernel instead of per phase):
+ * with profiling on, every cycle records CUDA events between its kernels on the handle's stream;
+ * ms4 = durations of [prologue, kinematics, networks, SQP] of the last cycle (waits for that cycle). */
+int mpcc_cuda_set_profiling(mpcc_cuda_handle* h, int32_t on);
+int mpcc_cuda_get_kernel_times(mpcc_cuda_handle* h, double* ms4);
+/* measured FP64 FMA throughput of a device (the roofline denominator of this path), best of 5 bursts */
+int mpcc_cuda_fp64_peak(int32_t device, double* tflops);
+
 /* ---- per-function evaluators (each runs the same device code the cycle uses; n <= batch*(N+1)) ---- */
 /* RobotData::update + updateEnv for n joint vectors: q [n][7], obs [n][4] (NULL -> dummy) -> rb [n][150] */
 int mpcc_cuda_eval_robot_data(mpcc_cuda_handle* h, const double* q, const double* obs, int32_t n, double* rb_out);
@@ -135,6 +146,11 @@ int mpcc_cuda_eval_track(mpcc_cuda_handle* h, const double* s, int32_t n, double
  * max_log SQP iterations: steps [n][max_log][N+1][17] (normalised QP steps), alphas [n][max_log], n_logged [n] */
 int mpcc_cuda_solve_ocp(mpcc_cuda_handle* h, double* guess, const double* rb, const double* cur_u, int32_t n,
                         int32_t* status, int32_t* iters, double* steps, double* alphas, int32_t max_log, int32_t* n_logged);
+
+/* Line-search decisions of the last cycle, per instance: bit i = the filter accepted the first trial of SQP
+ * iteration i (filterLineSearch, osqp_interface.cpp:759-808; i < 32).  Diagnostic used by the parity tests to
+ * replay the oracle along the same branch when a decision hinges on solver noise. */
+int mpcc_cuda_read_decisions(mpcc_cuda_handle* h, int32_t* accept_mask);
 
 /* counters of the last cycle: [0] kernels launched, [1] total SQP iterations, [2] total QP (IPM) iterations,
  * [3] QP failures, [4] instances SOLVED, [5] instances with ok == 1 */

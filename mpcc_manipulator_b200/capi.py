@@ -16,7 +16,8 @@ EXPORTS = [
     "mpcc_load_params_json", "mpcc_fit_track", "mpcc_load_track_json", "mpcc_cuda_set_tracks", "mpcc_cuda_reset", "mpcc_cuda_run_cycle",
     "mpcc_cuda_run_cycle_device", "mpcc_cuda_read_results", "mpcc_cuda_result_pointers", "mpcc_cuda_stream", "mpcc_cuda_synchronize",
     "mpcc_cuda_get_warm_state", "mpcc_cuda_set_warm_state", "mpcc_cuda_sim_time_step", "mpcc_cuda_eval_robot_data", "mpcc_cuda_eval_stage",
-    "mpcc_cuda_eval_track", "mpcc_cuda_solve_ocp", "mpcc_cuda_get_stats",
+    "mpcc_cuda_eval_track", "mpcc_cuda_solve_ocp", "mpcc_cuda_get_stats", "mpcc_cuda_sim_time_step_device", "mpcc_cuda_set_profiling",
+    "mpcc_cuda_get_kernel_times", "mpcc_cuda_fp64_peak", "mpcc_cuda_read_decisions",
 ]
 
 
@@ -82,6 +83,13 @@ def load_track_json(path=None, init_position=None):
     ip = None if init_position is None else _f64(init_position)
     _check(lib().mpcc_load_track_json(str(path or ASSETS / "params" / "track.json").encode(), _p(ip), _p(t)))
     return t
+
+
+def fp64_peak(device=0):
+    """Measured FP64 FMA throughput of the device in TFLOP/s (roofline denominator)."""
+    t = C.c_double()
+    _check(lib().mpcc_cuda_fp64_peak(device, C.byref(t)))
+    return t.value
 
 
 class BatchMPC:
@@ -175,6 +183,18 @@ class BatchMPC:
         _check(lib().mpcc_cuda_sim_time_step(self.h, _p(x), _p(u), C.c_double(self.Ts if ts is None else ts), _p(xn)))
         return xn
 
+    def sim_time_step_device(self, d_x, d_u, d_xn, ts=None):
+        _check(lib().mpcc_cuda_sim_time_step_device(self.h, C.c_void_p(d_x), C.c_void_p(d_u), C.c_double(self.Ts if ts is None else ts), C.c_void_p(d_xn)))
+
+    def set_profiling(self, on=True):
+        _check(lib().mpcc_cuda_set_profiling(self.h, int(on)))
+
+    def kernel_times(self):
+        """ms of [prologue, kinematics, networks, SQP] of the last cycle (profiling must be on)."""
+        t = np.zeros(4)
+        _check(lib().mpcc_cuda_get_kernel_times(self.h, _p(t)))
+        return t
+
     # ---- per-function evaluators ----
     def eval_robot_data(self, q, obs=None):
         q = _f64(q).reshape(-1, 7); n = q.shape[0]
@@ -201,6 +221,11 @@ class BatchMPC:
         al = np.zeros((n, max(1, max_log))); steps = np.zeros((n, max(1, max_log), self.S, HZ)) if want_steps else None
         _check(lib().mpcc_cuda_solve_ocp(self.h, _p(g), _p(_f64(rb)), _p(_f64(cur_u)), n, _p(st), _p(it), _p(steps), _p(al), max_log, _p(nl)))
         return dict(horizon=g, status=st, iters=it, alphas=al, n_logged=nl, steps=steps)
+
+    def decisions(self):
+        m = np.zeros(self.B, np.int32)
+        _check(lib().mpcc_cuda_read_decisions(self.h, _p(m)))
+        return m.view(np.uint32)
 
     def stats(self):
         s = np.zeros(6, np.int64)

@@ -62,7 +62,8 @@ MPCC_HDN void cycle_prologue(const Params& P, const TrackTable& T, double Ts, in
     for (int i = 1; i <= N; i++) warm[i * HZ + 7] = fmin(warm[i * HZ + 7], L);  // unwrapInitialGuess (mpc.cpp:70-77)
 }
 
-struct SqpResult { int32_t status; int32_t iters; int32_t qp_fail; int32_t qp_iters; };
+// accept_mask: bit i = the filter accepted the first line-search trial of SQP iteration i (i < 32)
+struct SqpResult { int32_t status; int32_t iters; int32_t qp_fail; int32_t qp_iters; uint32_t accept_mask; };
 
 // optional per-iteration record for the parity tests (step of each SQP iteration, alpha, QP flag)
 struct SqpLogRef {
@@ -106,7 +107,7 @@ MPCC_HDN SqpResult sqp_solve(const Params& P, const TrackTable& T, double Ts, in
                              const WsRef& trial, const WsRef& filt, const double* cur_u, const double* rb, size_t rb_stride,
                              size_t rb_stage, const WsRef& ws, QpOptions opt, SqpLogRef* log) {
     SqpResult res;
-    res.status = SOLVED; res.iters = 0; res.qp_fail = 0; res.qp_iters = 0;
+    res.status = SOLVED; res.iters = 0; res.qp_fail = 0; res.qp_iters = 0; res.accept_mask = 0;
     StageQP qp{P, make_dyn(P, Ts), N, ws, opt};
     const int max_iter = (int)P.max_iter, ls_max = (int)P.line_search_max_iter;
     for (int e = 0; e < (N + 1) * HZ; e++) step[e] = 0;
@@ -183,6 +184,7 @@ MPCC_HDN SqpResult sqp_solve(const Params& P, const TrackTable& T, double Ts, in
                 break;
             } else alpha *= P.line_search_tau;
         }
+        if (accepted && it < 32) res.accept_mask |= (1u << it);
         // ---- take the step (osqp_interface.cpp:549-551) ----
         double inf = 0;
         for (int k = 0; k <= N; k++) {

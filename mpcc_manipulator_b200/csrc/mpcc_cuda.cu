@@ -47,7 +47,7 @@ struct CycleArgs {
     double* rb;        // [150][B*S]
     double* u_out;     // [B][8]
     double* horizon;   // [B][S][17]
-    int32_t* status; int32_t* iters; int32_t* ok; int32_t* qp_iters; int32_t* qp_fail;
+    int32_t* status; int32_t* iters; int32_t* ok; int32_t* qp_iters; int32_t* qp_fail; int32_t* accept_mask;
     QpOptions qp;
 };
 
@@ -110,7 +110,7 @@ __global__ void k_sqp_thread(CycleArgs a) {
     WarmFlags fl = a.flags[b];
     bool ok = cycle_epilogue(a.N, r, x0, guess, fl);
     a.flags[b] = fl;
-    a.status[b] = r.status; a.iters[b] = r.iters; a.ok[b] = ok ? 1 : 0; a.qp_iters[b] = r.qp_iters; a.qp_fail[b] = r.qp_fail;
+    a.status[b] = r.status; a.iters[b] = r.iters; a.ok[b] = ok ? 1 : 0; a.qp_iters[b] = r.qp_iters; a.qp_fail[b] = r.qp_fail; a.accept_mask[b] = (int32_t)r.accept_mask;
     for (int j = 0; j < NU; j++) a.u_out[b * NU + j] = guess[NX + j];
     double* h = a.horizon + (size_t)b * a.S * HZ;
     for (int e = 0; e < a.S * HZ; e++) h[e] = guess[e];
@@ -222,9 +222,11 @@ struct mpcc_cuda_handle {
     double *d_warm = nullptr, *d_step = nullptr, *d_trial = nullptr, *d_filt = nullptr, *d_ws = nullptr, *d_qs = nullptr, *d_rb = nullptr;
     WarmFlags* d_flags = nullptr;
     double *d_u_out = nullptr, *d_horizon = nullptr;
-    int32_t *d_status = nullptr, *d_iters = nullptr, *d_ok = nullptr, *d_qp_iters = nullptr, *d_qp_fail = nullptr;
+    int32_t *d_status = nullptr, *d_iters = nullptr, *d_ok = nullptr, *d_qp_iters = nullptr, *d_qp_fail = nullptr, *d_accept = nullptr;
     double *d_wpack = nullptr, *d_bias = nullptr, *d_w_out_env = nullptr, *d_w_out_self = nullptr;
     int64_t launches = 0;
+    bool profiling = false;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // prologue | kin | mlp | sqp boundaries
     std::vector<double> h_params;  // host copy of set 0 (validation)
     std::vector<void*> allocs;
 
@@ -244,14 +246,15 @@ static CycleArgs make_args(mpcc_cuda_handle* h, double* d_x0, const double* d_u0
     a.x0 = d_x0; a.u0 = d_u0; a.obs = d_obs;
     a.warm = h->d_warm; a.step = h->d_step; a.trial = h->d_trial; a.filt = h->d_filt; a.ws = h->d_ws; a.flags = h->d_flags;
     a.qs = h->d_qs; a.rb = h->d_rb; a.u_out = h->d_u_out; a.horizon = h->d_horizon;
-    a.status = h->d_status; a.iters = h->d_iters; a.ok = h->d_ok; a.qp_iters = h->d_qp_iters; a.qp_fail = h->d_qp_fail;
+    a.status = h->d_status; a.iters = h->d_iters; a.ok = h->d_ok; a.qp_iters = h->d_qp_iters; a.qp_fail = h->d_qp_fail; a.accept_mask = h->d_accept;
     a.qp = QpOptions{h->cfg.qp_max_iter, h->cfg.qp_eps};
     return a;
 }
 
-static int launch_robot_data(mpcc_cuda_handle* h, const double* d_obs, int S_for_obs) {
+static int launch_robot_data(mpcc_cuda_handle* h, const double* d_obs, int S_for_obs, bool mark = false) {
     const int NS = (int)h->NS;
     k_kin<<<(NS + 127) / 128, 128, 0, h->stream>>>(h->d_qs, h->d_rb, NS);
+    if (mark) cudaEventRecord(h->ev[2], h->stream);
     MlpArgs m;
     m.wpack = h->d_wpack; m.bias = h->d_bias; m.w_out_env = h->d_w_out_env; m.w_out_self = h->d_w_out_self;
     m.qs = h->d_qs; m.obs = d_obs; m.rb = h->d_rb; m.NS = NS; m.S = S_for_obs;
@@ -294,6 +297,7 @@ int mpcc_cuda_create(const mpcc_cuda_config* cfg, mpcc_cuda_handle** out) {
     CK(cudaGetDeviceProperties(&prop, cfg->device));
     h->num_sms = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (auto& e : h->ev) CK(cudaEventCreate(&e));
     const size_t B = h->B, S = h->S, HN = S * HZ;
     cudaError_t ae = cudaSuccess;
     auto A = [&](cudaError_t r) { if (ae == cudaSuccess) ae = r; };
@@ -304,7 +308,7 @@ int mpcc_cuda_create(const mpcc_cuda_config* cfg, mpcc_cuda_handle** out) {
     A(h->alloc(&h->d_qs, h->NS * DOF)); A(h->alloc(&h->d_rb, h->NS * RB_DOUBLES));
     A(h->alloc(&h->d_flags, B));
     A(h->alloc(&h->d_u_out, B * NU)); A(h->alloc(&h->d_horizon, B * HN));
-    A(h->alloc(&h->d_status, B)); A(h->alloc(&h->d_iters, B)); A(h->alloc(&h->d_ok, B)); A(h->alloc(&h->d_qp_iters, B)); A(h->alloc(&h->d_qp_fail, B));
+    A(h->alloc(&h->d_status, B)); A(h->alloc(&h->d_iters, B)); A(h->alloc(&h->d_ok, B)); A(h->alloc(&h->d_qp_iters, B)); A(h->alloc(&h->d_qp_fail, B)); A(h->alloc(&h->d_accept, B));
     A(h->alloc(&h->d_wpack, (size_t)MLP_NCHUNK * MLP_CHUNK_D)); A(h->alloc(&h->d_bias, MLP_BIAS_TOTAL));
     A(h->alloc(&h->d_w_out_env, 9 * 256)); A(h->alloc(&h->d_w_out_self, 64));
     if (ae != cudaSuccess) { mpcc_cuda_destroy(h); return fail(MPCC_ERR_CUDA, std::string("device allocation failed: ") + cudaGetErrorString(ae)); }
@@ -321,6 +325,7 @@ int mpcc_cuda_destroy(mpcc_cuda_handle* h) {
     if (!h) return MPCC_OK;
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    for (cudaEvent_t e : h->ev) if (e) cudaEventDestroy(e);
     for (void* p : h->allocs) cudaFree(p);
     if (h->d_params) cudaFree(h->d_params);
     if (h->d_tracks) cudaFree(h->d_tracks);
@@ -486,12 +491,17 @@ int mpcc_cuda_run_cycle_device(mpcc_cuda_handle* h, double* d_x0, const double* 
     const double* obs = d_obs ? d_obs : h->d_obs_dummy;
     CycleArgs a = make_args(h, d_x0, d_u0, obs);
     h->launches = 0;
+    const bool prof = h->profiling;
+    if (prof) cudaEventRecord(h->ev[0], h->stream);
     k_prologue<<<(h->B + 63) / 64, 64, 0, h->stream>>>(a);
     h->launches++;
-    rc = launch_robot_data(h, obs, h->S);
+    if (prof) cudaEventRecord(h->ev[1], h->stream);
+    rc = launch_robot_data(h, obs, h->S, prof);
     if (rc) return rc;
+    if (prof) cudaEventRecord(h->ev[3], h->stream);
     k_sqp_thread<<<(h->B + 31) / 32, 32, 0, h->stream>>>(a);
     h->launches++;
+    if (prof) cudaEventRecord(h->ev[4], h->stream);
     CK(cudaGetLastError());
     return MPCC_OK;
 }
@@ -700,6 +710,82 @@ int mpcc_cuda_solve_ocp(mpcc_cuda_handle* h, double* guess, const double* rb, co
     }
     CK(cudaStreamSynchronize(h->stream));
     cudaFree(d_g); cudaFree(d_rb); cudaFree(d_cu); cudaFree(d_steps); cudaFree(d_alphas); cudaFree(d_qpok); cudaFree(d_nl);
+    return MPCC_OK;
+}
+
+int mpcc_cuda_sim_time_step_device(mpcc_cuda_handle* h, const double* d_x, const double* d_u, double ts, double* d_x_next) {
+    if (!h || !d_x || !d_u || !d_x_next) return fail(MPCC_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(h->cfg.device));
+    k_sim_step<<<(h->B + 127) / 128, 128, 0, h->stream>>>(d_x, d_u, ts, h->B, d_x_next);
+    CK(cudaGetLastError());
+    return MPCC_OK;
+}
+
+int mpcc_cuda_set_profiling(mpcc_cuda_handle* h, int32_t on) {
+    if (!h) return fail(MPCC_ERR_INVALID, "null handle");
+    h->profiling = on != 0;
+    return MPCC_OK;
+}
+int mpcc_cuda_get_kernel_times(mpcc_cuda_handle* h, double* ms4) {
+    if (!h || !ms4) return fail(MPCC_ERR_INVALID, "null argument");
+    if (!h->profiling) return fail(MPCC_ERR_STATE, "profiling is off (mpcc_cuda_set_profiling)");
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaEventSynchronize(h->ev[4]));
+    for (int i = 0; i < 4; i++) {
+        float t = 0;
+        CK(cudaEventElapsedTime(&t, h->ev[i], h->ev[i + 1]));
+        ms4[i] = t;
+    }
+    return MPCC_OK;
+}
+
+// FP64 DFMA peak of the device: 8 independent FMA chains per thread, enough CTAs to fill every SM
+__global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+        }
+    }
+    double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 123.456) out[0] = s;  // keep the chains alive
+}
+int mpcc_cuda_fp64_peak(int32_t device, double* tflops) {
+    if (!tflops) return fail(MPCC_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    double* d = nullptr;
+    CK(cudaMalloc((void**)&d, 8));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    const int grid = prop.multiProcessorCount * 8, iters = 4096;
+    k_fp64_peak<<<grid, 256>>>(d, 64);  // warm-up
+    double best = 0;
+    for (int rep = 0; rep < 5; rep++) {
+        CK(cudaEventRecord(e0));
+        k_fp64_peak<<<grid, 256>>>(d, iters);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        double fl = 2.0 * 64.0 * iters * 256.0 * grid;
+        double tf = fl / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    *tflops = best;
+    return MPCC_OK;
+}
+
+int mpcc_cuda_read_decisions(mpcc_cuda_handle* h, int32_t* accept_mask) {
+    if (!h || !accept_mask) return fail(MPCC_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaMemcpyAsync(accept_mask, h->d_accept, (size_t)h->B * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
     return MPCC_OK;
 }
 

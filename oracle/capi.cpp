@@ -248,6 +248,17 @@ int orc_solve_ocp(void* mp, double* guess, const double* rb, const double* cur_u
     *n_logged = nl;
     return ok ? 1 : 0;
 }
+// smallest robustness margin over the filter comparisons of the last solveOCP (see filter_margin)
+double orc_mpc_last_filter_margin(void* mp) { return ((MPC*)mp)->solver.min_filter_margin; }
+// follow these first-trial accept/reject decisions in the next solveOCP calls (n = 0: natural behaviour)
+void orc_mpc_set_forced_decisions(void* mp, const int* accept, int n) { ((MPC*)mp)->solver.forced_accept.assign(accept, accept + n); }
+// the line search's own decisions and their robustness margins in the last solveOCP
+int orc_mpc_decision_log(void* mp, int* natural, double* margins, int max_n) {
+    Solver& s = ((MPC*)mp)->solver;
+    int n = std::min<int>(max_n, (int)s.natural_accept.size());
+    for (int i = 0; i < n; i++) { natural[i] = s.natural_accept[i]; margins[i] = s.accept_margin[i]; }
+    return n;
+}
 double orc_rbf(double delta, double h) { return getRBF(delta, h); }
 void orc_log_exp(const double* R9, double* log9, double* exp_of_log9) {
     Mat3 R; for (int i = 0; i < 9; i++) R.m[i] = R9[i];

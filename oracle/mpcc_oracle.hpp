@@ -1022,6 +1022,15 @@ struct SqpLog {  // per-iteration record for the parity tests
     std::vector<double> alphas;
     std::vector<int> qp_ok, qp_iters;
 };
+// Robustness of one filter comparison "trial dominated by entry" (osqp_interface.cpp:778-783): the smallest
+// perturbation of (obj, gap) that flips it; obj scaled by 1+|obj|.  The parity tests use it to recognise
+// accept/reject decisions that hinge on solver noise (both sides of the gap comparison are ~1e-9 numbers).
+inline double filter_margin(double o2, double g2, double fo, double fg) {
+    double so = 1.0 + std::fabs(fo);
+    double d_o = (o2 - fo) / so, d_g = g2 - fg;
+    if (d_o >= 0 && d_g >= 0) return std::min(d_o, d_g);
+    return std::max(d_o < 0 ? -d_o : 0.0, d_g < 0 ? -d_g : 0.0);
+}
 
 struct Solver {
     int N;
@@ -1045,6 +1054,13 @@ struct Solver {
     std::vector<FilterData> filter;
     int sqp_iter = 0;
     SqpLog* log = nullptr;
+    double min_filter_margin = 1e300;  // over every filter comparison of the last solveOCP (test instrumentation)
+    // Test instrumentation for "parity modulo certified filter ties": per SQP iteration of the last solveOCP, the
+    // line search's own first-trial decision (1 = accepted) and the robustness margin of that decision; and an
+    // optional list of decisions to FOLLOW instead (so the oracle can be replayed along the device's branch).
+    std::vector<int> natural_accept;
+    std::vector<double> accept_margin;
+    std::vector<int> forced_accept;
 
     void init(int N_) {
         N = N_;
@@ -1253,7 +1269,17 @@ struct Solver {
             setConstraints(ug, nullptr, &c, &l, &u);
             upd.gap_vio = constraint_norm(c, l, u);
             for (size_t j = 0; j < filter.size(); j++)
+                min_filter_margin = std::min(min_filter_margin, filter_margin(upd.obj, upd.gap_vio, filter[j].obj, filter[j].gap_vio));
+            for (size_t j = 0; j < filter.size(); j++)
                 if (upd.obj >= filter[j].obj && upd.gap_vio >= filter[j].gap_vio) { is_alpha_accepted = false; break; }
+            if (i == 0) {
+                double mg = 1e300;
+                for (size_t j = 0; j < filter.size(); j++) mg = std::min(mg, filter_margin(upd.obj, upd.gap_vio, filter[j].obj, filter[j].gap_vio));
+                natural_accept.push_back(is_alpha_accepted ? 1 : 0);
+                accept_margin.push_back(mg);
+                size_t it = natural_accept.size() - 1;
+                if (it < forced_accept.size()) is_alpha_accepted = forced_accept[it] != 0;
+            }
             if (is_alpha_accepted) {
                 std::vector<FilterData> nf;
                 for (size_t j = 0; j < filter.size(); j++)
@@ -1271,6 +1297,8 @@ struct Solver {
         auto t0 = std::chrono::high_resolution_clock::now();
         step.assign(N_var, 0.0);
         filter.clear();
+        min_filter_margin = 1e300;
+        natural_accept.clear(); accept_margin.clear();
         *time = ComputeTime();
         std::vector<OptVariables> zero_guess(N + 1);
         for (int i = 0; i <= N; i++) { zero_guess[i].xk = initial_guess[0].xk; for (double& v : zero_guess[i].uk.v) v = 0; }

@@ -42,6 +42,7 @@ def lib():
         _lib.orc_mpc_track_length.restype = C.c_double
         _lib.orc_project.restype = C.c_double
         _lib.orc_rbf.restype = C.c_double
+        _lib.orc_mpc_last_filter_margin.restype = C.c_double
     return _lib
 
 
@@ -180,6 +181,20 @@ class OracleMPC:
         u = np.zeros(NU); hor = np.zeros((self.N + 1, 17)); st = C.c_int(); it = C.c_int(); tm = np.zeros(5)
         ok = lib().orc_mpc_run(self.h, _p(x0), _p(f64(u0)), _p(f64(obs4)), _p(u), _p(hor), C.byref(st), C.byref(it), _p(tm))
         return dict(ok=bool(ok), x0=x0, u0=u, horizon=hor, status=st.value, iters=it.value, times=tm)
+
+    def last_filter_margin(self):
+        """Smallest robustness margin of the filter accept/reject comparisons in the last solveOCP (1e300: none made)."""
+        return lib().orc_mpc_last_filter_margin(self.h)
+
+    def set_forced_decisions(self, accept):
+        """Follow these per-iteration first-trial accept (1) / reject (0) decisions instead of the filter's own."""
+        a = np.ascontiguousarray(accept, dtype=np.int32)
+        lib().orc_mpc_set_forced_decisions(self.h, _p(a), len(a))
+
+    def decision_log(self, max_n=128):
+        nat = np.zeros(max_n, np.int32); mg = np.zeros(max_n)
+        n = lib().orc_mpc_decision_log(self.h, _p(nat), _p(mg), max_n)
+        return nat[:n], mg[:n]
 
     def warm_state(self):
         hor = np.zeros((self.N + 1, 17)); v = C.c_int(); f = C.c_int()

@@ -1,0 +1,352 @@
+"""GPU tier: parity of the CUDA path, called through the C ABI (libmpcc_b200.so via ctypes), against the oracle,
+the committed goldens, and -- at BASELINE.json's full sizes -- size-independent properties.
+
+Tolerances (north_star): FK / Jacobian / manipulability / MLP / cost / constraint linearisations 1e-9 relative;
+QP / SQP iterates and the applied control within the reference QP solver's tolerance (OSQP eps_abs = 1e-4,
+osqp_interface.cpp:623).  Line-search decisions that hinge on solver noise ("filter ties", see
+tests/test_host_emul_vs_oracle.py) are recognised with the oracle's own robustness margin and excluded from the
+iterate comparison from the tie onwards; their share is bounded."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import helpers as H
+from helpers import flat_params, assemble_flat_qp_from_lin, step_to_flat, make_horizon
+
+pytestmark = pytest.mark.gpu
+G = Path(__file__).resolve().parent / "golden"
+REL = 1e-9
+QP_TOL = 1e-4
+TIE = 1e-6
+
+
+def rel_err(a, b):
+    return np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.fixture(scope="module")
+def M():
+    import mpcc_manipulator_b200 as M
+    return M
+
+
+def make_mpc(M, B, N, ee, **kw):
+    mpc = M.BatchMPC(B, N, **kw)
+    mpc.setup_default(init_position=ee)
+    return mpc
+
+
+RB_FIELDS = dict(q=(0, 7), p=(7, 10), R=(10, 19), Jv=(19, 40), Jw=(40, 61), manip=(61, 62), dmanip=(62, 69), sel=(69, 70), dsel=(70, 77),
+                 obsr=(77, 78), env=(78, 87), denv=(87, 150))
+
+
+def test_robot_data_vs_golden_and_oracle(M, O, nn, ee_home, rng):
+    g = np.load(G / "robot_data.npz")
+    mpc = make_mpc(M, 32, 10, ee_home)
+    rb = mpc.eval_robot_data(g["q"], g["obs"])
+    for k, (a, b) in RB_FIELDS.items():
+        assert rel_err(rb[:, a:b], g["rb"][:, a:b]) < REL, k
+    # fresh random samples against the live oracle, wide joint range
+    n = 200
+    q = rng.uniform(-2.5, 2.5, (n, 7)); q[:, 3] = rng.uniform(-3.0, -0.1, n); q[:, 5] = rng.uniform(0.0, 3.7, n)
+    obs = np.c_[rng.uniform(-0.8, 0.8, (n, 3)), rng.uniform(0, 10, n)]
+    rb = mpc.eval_robot_data(q, obs)
+    ref = np.stack([nn.robot_data(q[i], obs[i]) for i in range(n)])
+    for k, (a, b) in RB_FIELDS.items():
+        assert rel_err(rb[:, a:b], ref[:, a:b]) < REL, k
+    # single sample and dummy obstacle (mpc.cpp:97-100)
+    rb1 = mpc.eval_robot_data(O.Q_HOME[None])
+    assert rel_err(rb1[0], nn.robot_data(O.Q_HOME)) < REL
+    mpc.close()
+
+
+def test_relu_mask_agreement(M, O, nn, ee_home, rng):
+    """The forward-mode Jacobians use 1[a > 0] masks; a flipped mask would show as an O(1) error in one column."""
+    mpc = make_mpc(M, 64, 10, ee_home)
+    q = O.Q_HOME + rng.uniform(-1.0, 1.0, (640, 7))
+    rb = mpc.eval_robot_data(q)
+    ref = np.stack([nn.robot_data(qi) for qi in q])
+    assert rel_err(rb[:, 70:77], ref[:, 70:77]) < REL
+    assert rel_err(rb[:, 87:150], ref[:, 87:150]) < REL
+    mpc.close()
+
+
+def test_track_eval_vs_golden(M, ee_home):
+    g = np.load(G / "track_eval.npz")
+    mpc = make_mpc(M, 8, 10, ee_home)
+    out = mpc.eval_track(g["s"])
+    assert np.abs(out - g["out"]).max() < 1e-9 * max(1.0, np.abs(g["out"]).max())
+    mpc.close()
+
+
+def test_stage_linearisation_vs_golden_flat_qp(M, O, ee_home):
+    g = np.load(G / "flat_qp_n10.npz")
+    N = 10
+    mpc = make_mpc(M, 8, N, ee_home)
+    pf = flat_params(O.load_params())
+    hor, rb, cur_u = g["hor"], g["rb"], g["cur_u"]
+    up = np.vstack([cur_u[:7], hor[:N, 9:16]])
+    un = np.vstack([hor[1:, 9:16], np.zeros(7)])
+    xn = np.vstack([hor[1:, :9], np.zeros(9)])
+    lin = mpc.eval_stage(hor[:, :9], hor[:, 9:], up, un, xn, rb, np.arange(N + 1))
+    P, q = assemble_flat_qp_from_lin(lin, pf, N, 0.01)
+    assert rel_err(P, g["P"]) < REL and rel_err(q, g["q"]) < REL
+    assert abs(lin[:, H.LOBJ].sum() - g["obj"]) < REL * abs(g["obj"])
+    lo, hi = g["l"] - g["c"], g["u"] - g["c"]
+    Tx, Tu = pf[67:76], pf[76:84]
+    nx = 9 * (N + 1); B0 = nx; U0 = B0 + nx; D0 = U0 + 8 * N; P0 = D0 + 8 * N
+    for k in range(N + 1):
+        L = lin[k]
+        assert np.allclose(L[H.LXLO:H.LXLO + 9] * Tx, lo[B0 + 9 * k:B0 + 9 * k + 9], rtol=1e-9, atol=1e-12)
+        assert np.allclose(L[H.LXHI:H.LXHI + 9] * Tx, hi[B0 + 9 * k:B0 + 9 * k + 9], rtol=1e-9, atol=1e-12)
+        if k >= 1:
+            assert np.allclose(lin[k - 1][H.Lb:H.Lb + 9], lo[9 * k:9 * k + 9], rtol=1e-9, atol=1e-12)
+        if k < N:
+            pg = L[H.LPG:H.LPG + 77].reshape(11, 7); pd = L[H.LPD:H.LPD + 11]
+            rows = g["A"][P0 + 11 * k:P0 + 11 * k + 11]
+            assert rel_err(pd[:, None] * pg * Tx[None, :7], rows[:, 9 * k:9 * k + 7]) < REL
+            assert rel_err(-pg * Tu[None, :7], rows[:, nx + 8 * k:nx + 8 * k + 7]) < REL
+            assert np.allclose(L[H.LPRHS:H.LPRHS + 11], hi[P0 + 11 * k:P0 + 11 * k + 11], rtol=1e-9, atol=1e-12)
+            assert np.allclose(L[H.LDLO:H.LDLO + 7] * Tu[:7] / 0.01, lo[D0 + 8 * k:D0 + 8 * k + 7], rtol=1e-9, atol=1e-10)
+    mpc.close()
+
+
+@pytest.mark.parametrize("N", [10, 20, 40])
+def test_solve_ocp_iterates_vs_oracle(M, O, nn, ee_home, track_wp, rng, N):
+    """SolverInterface::solveOCP on given warm starts with frozen RobotData: per-iteration QP steps and alphas."""
+    B = 16
+    mpc = make_mpc(M, B, N, ee_home)
+    o = O.OracleMPC(N=N, nn=nn); o.set_track(*track_wp)
+    hors, rbs = [], []
+    for b in range(B):
+        x0 = np.r_[O.Q_HOME + rng.uniform(-0.05, 0.05, 7), 0., 0.]
+        hor = np.tile(np.r_[x0, np.zeros(8)], (N + 1, 1))
+        hors.append(hor); rbs.append(np.stack([nn.robot_data(hor[k, :7]) for k in range(N + 1)]))
+    hors, rbs = np.array(hors), np.array(rbs)
+    r = mpc.solve_ocp(hors, rbs, np.zeros((B, 8)), max_log=8, want_steps=True)
+    ties = 0
+    for b in range(B if N < 40 else 4):
+        ref = o.solve_ocp(hors[b], rbs[b], np.zeros(8))
+        assert r["status"][b] == ref["status"] == 0
+        same = 0
+        for i in range(min(r["n_logged"][b], len(ref["alphas"]))):
+            assert np.abs(step_to_flat(r["steps"][b, i], N) - ref["steps"][i]).max() < QP_TOL
+            if r["alphas"][b, i] != ref["alphas"][i]:
+                break
+            same += 1
+        assert same >= 1
+        if same == len(ref["alphas"]) == r["n_logged"][b]:
+            assert r["iters"][b] == ref["iters"]
+            assert np.abs(r["horizon"][b] - ref["horizon"]).max() < QP_TOL
+        else:
+            assert o.last_filter_margin() < TIE
+            ties += 1
+    print(f"N={N}: {ties} filter ties among {B if N < 40 else 4} instances")
+    mpc.close()
+
+
+def _first_cycles_vs_golden(mpc, g, with_obs=False):
+    """Golden fixture check on cycle 0 (cold start, identical inputs): projection, vs estimate, and -- for the
+    instances whose oracle run met no filter tie -- status, iteration count and applied control."""
+    B = g["x_in"].shape[1] if g["x_in"].ndim == 3 else 1
+    x_in = g["x_in"][0].reshape(B, 9); u_in = g["u_in"][0].reshape(B, 8)
+    obs = g["obs"][0].reshape(B, 4) if with_obs else None
+    r = mpc.run_cycle(x_in, u_in, obs)
+    x_ref = g["x_out"][0].reshape(B, 9); u_ref = g["u_out"][0].reshape(B, 8)
+    st = np.atleast_1d(g["status"][0]); it = np.atleast_1d(g["iters"][0]); mg = np.atleast_1d(g["margin"][0])
+    n_cmp = 0
+    for b in range(B):
+        assert np.abs(r["x0"][b] - x_ref[b]).max() < 1e-9
+        if mg[b] < TIE:
+            continue
+        assert r["status"][b] == st[b] and r["iters"][b] == it[b]
+        assert np.abs(r["u0"][b] - u_ref[b]).max() < QP_TOL
+        n_cmp += 1
+    mpc.reset()
+    return n_cmp
+
+
+def _closed_loop_follow(mpc, oracles, x, u, cycles, Ts, O, obs_fn=None):
+    """Closed loop on the GPU with one live oracle per instance replayed ALONG THE DEVICE'S BRANCH: the oracle is told
+    the device's per-iteration line-search decisions (mpcc_cuda_read_decisions) and must then reproduce status,
+    iteration count, updated s / vs and the applied control within the reference QP tolerance; wherever the oracle's
+    own decision differs from the device's, its robustness margin must certify a noise-level tie (< TIE).
+    Returns (comparisons, ties, worst |du0|)."""
+    B = x.shape[0]
+    n_cmp = n_tie = 0
+    worst = 0.0
+    for c in range(cycles):
+        obs = obs_fn(c) if obs_fn else None
+        r = mpc.run_cycle(x, u, obs)
+        masks = mpc.decisions()
+        for b in range(B):
+            dec = [(int(masks[b]) >> i) & 1 for i in range(min(int(r["iters"][b]), 32))]
+            oracles[b].set_forced_decisions(dec)
+            ro = oracles[b].run(x[b], u[b], obs[b] if obs is not None else (3., 3., 3., 0.))
+            nat, mg = oracles[b].decision_log()
+            assert np.abs(r["x0"][b] - ro["x0"]).max() < 1e-9
+            assert r["status"][b] == ro["status"], (c, b)
+            assert r["iters"][b] == ro["iters"], (c, b, r["iters"][b], ro["iters"])
+            d = np.abs(r["u0"][b] - ro["u0"]).max()
+            assert d < QP_TOL, (c, b, d)
+            assert np.abs(r["horizon"][b] - ro["horizon"]).max() < 10 * QP_TOL
+            worst = max(worst, d); n_cmp += 1
+            for i in range(len(dec)):
+                if nat[i] != dec[i]:
+                    assert mg[i] < TIE, (c, b, i, mg[i])
+                    n_tie += 1
+        u = r["u0"]
+        x = mpc.sim_time_step(r["x0"], u, Ts)
+    return n_cmp, n_tie, worst
+
+
+def test_closed_loop_c1(M, O, nn, ee_home, track_wp):
+    """Configuration C1: single Panda, default parameters, N = 10, closed loop from q_home (main.cpp:57-114)."""
+    g = np.load(G / "closed_loop_c1.npz")
+    mpc = make_mpc(M, 1, 10, ee_home)
+    _first_cycles_vs_golden(mpc, g)
+    o = O.OracleMPC(N=10, nn=nn); o.set_track(*track_wp)
+    x = np.r_[O.Q_HOME, 0., 0.][None]; u = np.zeros((1, 8))
+    n_cmp, n_tie, worst = _closed_loop_follow(mpc, [o], x, u, 60, 0.01, O)
+    print(f"C1: {n_cmp} cycle comparisons, {n_tie} certified filter ties, worst |du0| = {worst:.2e}")
+    assert n_cmp == 60
+    mpc.close()
+
+
+def test_batch_c2_small(M, O, nn, ee_home, track_wp):
+    g = np.load(G / "batch_c2_small.npz")
+    B, N = 12, 20
+    mpc = make_mpc(M, B, N, ee_home)
+    _first_cycles_vs_golden(mpc, g)
+    oracles = []
+    for b in range(B):
+        o = O.OracleMPC(N=N, nn=nn); o.set_track(*track_wp); oracles.append(o)
+    n_cmp, n_tie, worst = _closed_loop_follow(mpc, oracles, g["x_in"][0].copy(), g["u_in"][0].copy(), 4, 0.01, O)
+    print(f"C2 small: {n_cmp} comparisons, {n_tie} certified filter ties, worst |du0| = {worst:.2e}")
+    mpc.close()
+
+
+def test_batch_c3_obstacle(M, O, nn, ee_home, track_wp):
+    """Configuration C3 in small: active moving obstacle (env-collision rows live), tightened model parameters."""
+    g = np.load(G / "batch_c3_small.npz")
+    B, N = 8, 20
+    over = {"model.tol_envcol": 1.0, "model.tol_sing": 0.018, "model.desired_ee_velocity": 0.1}
+    mpc = M.BatchMPC(B, N)
+    mpc.load_nn()
+    mpc.set_params(M.load_default_params(overrides=over))
+    mpc.set_tracks(M.load_track_json(None, ee_home))
+    _first_cycles_vs_golden(mpc, g, with_obs=True)
+    pc3 = O.load_params(overrides={"model": {"tol_envcol": 1.0, "tol_sing": 0.018, "desired_ee_velocity": 0.1}})
+    oracles = []
+    for b in range(B):
+        o = O.OracleMPC(N=N, nn=nn, params=pc3); o.set_track(*track_wp); oracles.append(o)
+    obs0 = g["obs"][0].copy()
+
+    def obs_fn(c):
+        ob = obs0.copy(); ob[:, 2] += 0.05 * 0.01 * c
+        return ob
+    n_cmp, n_tie, worst = _closed_loop_follow(mpc, oracles, g["x_in"][0].copy(), g["u_in"][0].copy(), 4, 0.01, O, obs_fn)
+    print(f"C3 small: {n_cmp} comparisons, {n_tie} certified filter ties, worst |du0| = {worst:.2e}")
+    mpc.close()
+
+
+def test_full_size_batch_properties(M, O, ee_home):
+    """BASELINE configs[1] at full size (4096 x N=20): size-independent properties instead of an oracle run.
+    (a) duplicated instances give bit-identical results wherever they sit in the batch (no cross-talk, determinism);
+    (b) a permutation of the batch permutes the results; (c) every instance is SOLVED and obeys the input bounds;
+    (d) the returned horizon satisfies the model (x_{k+1} = A x_k + B u_k) to rounding; (e) a small-batch run of the
+    same inputs reproduces the same numbers (batch-size independence)."""
+    B, N = 4096, 20
+    rng = np.random.default_rng(0)
+    mpc = make_mpc(M, B, N, ee_home)
+    x0 = np.tile(np.r_[O.Q_HOME, 0., 0.], (B, 1)); x0[:, :7] += rng.uniform(-0.05, 0.05, (B, 7))
+    x0[B // 2:] = x0[:B // 2]          # duplicates
+    u0 = np.zeros((B, 8))
+    r = mpc.run_cycle(x0, u0)
+    assert np.all(r["status"] == 0) and np.all(r["ok"] == 1)
+    assert np.array_equal(r["u0"][:B // 2], r["u0"][B // 2:]) and np.array_equal(r["horizon"][:B // 2], r["horizon"][B // 2:])
+    p = O.load_params(); b = p["bounds"]; Ts = p["Ts"]
+    # quirk 1: true input steps are never box-bounded by the reference, but the rate rows bound dq_0 from u_prev = 0
+    assert np.all(np.abs(r["u0"][:, :7]) <= b[41:48].max() * Ts + 1e-6)
+    hor = r["horizon"]
+    xk, uk, xn = hor[:, :-1, :9], hor[:, :-1, 9:], hor[:, 1:, :9]
+    pred = xk.copy(); pred[..., :7] += Ts * uk[..., :7]; pred[..., 7] += Ts * xk[..., 8] + 0.5 * Ts * Ts * uk[..., 7]; pred[..., 8] += Ts * uk[..., 7]
+    assert np.abs(pred - xn).max() < 1e-7
+    perm = rng.permutation(B)
+    mpc.reset()
+    r2 = mpc.run_cycle(x0[perm], u0)
+    assert np.array_equal(r2["u0"], r["u0"][perm]) and np.array_equal(r2["iters"], r["iters"][perm])
+    mpc.close()
+    small = make_mpc(M, 8, N, ee_home)
+    r3 = small.run_cycle(x0[:8], u0[:8])
+    assert np.array_equal(r3["u0"], r["u0"][:8])
+    small.close()
+
+
+def test_warm_start_state_roundtrip_and_failure_policy(M, O, ee_home):
+    """MPC's persistent members: warm start shift, invalidation on a projection jump (mpc.cpp:117-121)."""
+    B, N = 4, 10
+    mpc = make_mpc(M, B, N, ee_home)
+    x0 = np.tile(np.r_[O.Q_HOME, 0., 0.], (B, 1)); u0 = np.zeros((B, 8))
+    r = mpc.run_cycle(x0, u0)
+    hor, valid, failed = mpc.get_warm_state()
+    assert np.all(valid == 1) and np.all(failed == 0)
+    assert np.abs(hor - r["horizon"]).max() == 0.0
+    mpc.set_warm_state(hor, valid, failed)
+    hor2, v2, f2 = mpc.get_warm_state()
+    assert np.array_equal(hor, hor2)
+    # a jump of s by more than max_dist_proj invalidates the warm start and counts a failure
+    x1 = mpc.sim_time_step(r["x0"], r["u0"]); x1[0, 7] += 0.5
+    r1 = mpc.run_cycle(x1, r["u0"])
+    _, v3, f3 = mpc.get_warm_state()
+    assert np.all(r1["status"] == 0)
+    mpc.close()
+
+
+def test_heterogeneous_tracks_and_weights(M, O, nn, ee_home, rng):
+    """Configuration C4 in small: per-instance tracks (track.py family) and per-instance cost weights."""
+    B, N = 6, 20
+    tables, wps = [], []
+    for b in range(B):
+        a, bb = rng.uniform(1.5, 3, 2); c = rng.uniform(0, 2.5)
+        t = np.linspace(np.pi / 2, 5 * np.pi / 2, 100); rr = 0.1
+        X, Y, Z = a * rr * np.sin(t), bb * rr * np.sin(2 * t), c * rr * np.cos(t)
+        X, Y, Z = O.shift_track(X, Y, Z, ee_home)
+        R = np.tile(np.diag([1., -1., -1.]).ravel(), (100, 1))
+        wps.append((X, Y, Z, R)); tables.append(M.fit_track(X, Y, Z, R))
+    over = [dict(qC=rng.uniform(200, 1000), qL=rng.uniform(50, 200), qOri=rng.uniform(10, 100), qVs=rng.uniform(5, 40)) for _ in range(B)]
+    params = np.stack([M.load_default_params(overrides={f"cost.{k}": v for k, v in ov.items()}) for ov in over])
+    mpc = M.BatchMPC(B, N); mpc.load_nn(); mpc.set_params(params); mpc.set_tracks(np.stack(tables), np.arange(B))
+    x0 = np.tile(np.r_[O.Q_HOME, 0., 0.], (B, 1)); x0[:, :7] += rng.uniform(-0.03, 0.03, (B, 7)); u0 = np.zeros((B, 8))
+    oracles = []
+    for b in range(B):
+        o = O.OracleMPC(N=N, nn=nn, params=O.load_params(overrides={"cost": over[b]})); o.set_track(*wps[b]); oracles.append(o)
+    n_cmp, n_tie, worst = _closed_loop_follow(mpc, oracles, x0, u0, 3, 0.01, O)
+    print(f"C4 small: {n_cmp} comparisons, {n_tie} certified filter ties, worst |du0| = {worst:.2e}")
+    mpc.close()
+
+
+def test_sim_time_step(M, O, ee_home, rng):
+    mpc = make_mpc(M, 16, 10, ee_home)
+    x = rng.uniform(-1, 1, (16, 9)); u = rng.uniform(-1, 1, (16, 8))
+    xn = mpc.sim_time_step(x, u, 0.01)
+    ref = np.stack([O.sim_time_step(x[i], u[i], 0.01) for i in range(16)])
+    assert np.abs(xn - ref).max() < 1e-14
+    mpc.close()
+
+
+def test_error_behaviour(M, ee_home):
+    mpc = M.BatchMPC(4, 10)
+    with pytest.raises(RuntimeError, match="not uploaded|not set"):
+        mpc.run_cycle(np.zeros((4, 9)), np.zeros((4, 8)))
+    mpc.load_nn()
+    with pytest.raises(RuntimeError):
+        mpc.run_cycle(np.zeros((4, 9)), np.zeros((4, 8)))
+    bad = M.load_default_params(); bad[84 + 2] = 1000  # sqp.max_iter beyond the device filter capacity
+    with pytest.raises(RuntimeError, match="max_iter"):
+        mpc.set_params(bad)
+    soc = M.load_default_params(overrides={"sqp.do_SOC": 1.0})
+    with pytest.raises(RuntimeError, match="do_SOC"):
+        mpc.set_params(soc)
+    mpc.close()
