@@ -7,6 +7,7 @@
 #include "dev_stage.cuh"
 #include "dev_qp.cuh"
 #include "dev_sqp.cuh"
+#include "sqp_warp.cuh"
 #include "mlp_kernel.cuh"
 #include "host/params_io.h"
 #include "host/track_fit.h"
@@ -25,7 +26,7 @@ static_assert(TRACK_DOUBLES == MPCC_TRACK_DOUBLES, "track layout");
 static_assert(sizeof(StageLin) == MPCC_STAGE_LIN_DOUBLES * sizeof(double), "stage lin layout");
 static_assert(RB_DOUBLES == MPCC_RB_DOUBLES, "robot data layout");
 
-constexpr int MAX_SQP_ITER = 128;
+constexpr int MAX_SQP_ITER = MAX_SQP_FILTER;
 constexpr int FILT_DOUBLES = 2 * (MAX_SQP_ITER + 2);
 
 // ------------------------------------------------------------------------------------------------
@@ -114,6 +115,71 @@ __global__ void k_sqp_thread(CycleArgs a) {
     for (int j = 0; j < NU; j++) a.u_out[b * NU + j] = guess[NX + j];
     double* h = a.horizon + (size_t)b * a.S * HZ;
     for (int e = 0; e < a.S * HZ; e++) h[e] = guess[e];
+}
+
+// SQP loop + epilogue, one WARP per instance (sqp_warp.cuh)
+constexpr int SQPW_WARPS = 2;  // warps (instances) per CTA
+__global__ void __launch_bounds__(SQPW_WARPS * 32) k_sqp_warp(CycleArgs a, double* wws, size_t ws_per, size_t sm_per) {
+    extern __shared__ __align__(16) double sqpw_smem[];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * SQPW_WARPS + wid;
+    if (b >= a.B) return;  // whole warps leave together
+    const Params& P = a.params[a.params_per_instance ? b : 0];
+    const TrackTable& T = a.tracks[a.track_id[b]];
+    const size_t B = (size_t)a.B, NS = B * a.S;
+    const int HN = a.S * HZ;
+    WarpSqp w{P, T, make_dyn(P, a.Ts), a.Ts, a.N, a.S, lane, a.qp};
+    w.carve(wws + (size_t)b * ws_per, sqpw_smem + (size_t)wid * sm_per);
+    if (lane < NX) w.SC[WSC_TXU + lane] = P.Tx[lane];
+    else if (lane < HZ) w.SC[WSC_TXU + lane] = P.Tu[lane - NX];
+    for (int e = lane; e < HN; e += 32) w.GUESS[e] = a.warm[(size_t)e * B + b];
+    __syncwarp();
+    double cur_u[NU], x0[NX];
+    for (int i = 0; i < NU; i++) cur_u[i] = a.u0[b * NU + i];
+    for (int i = 0; i < NX; i++) x0[i] = a.x0[b * NX + i];
+    SqpResult r = w.run(cur_u, a.rb + (size_t)b * a.S, NS, 1, nullptr);
+    // epilogue of runMPC_ (mpc.cpp:140-188)
+    WarmFlags fl = a.flags[b];
+    if (r.status == SOLVED) { fl.valid = 1; fl.failed = 0; }
+    else {
+        for (int e = lane; e < HN; e += 32) { const int rr = e % HZ; w.GUESS[e] = (rr < NX) ? x0[0] : 0.0; }
+        __syncwarp();
+        for (int k = lane; k < a.S; k += 32) for (int m = 0; m < NX; m++) w.GUESS[k * HZ + m] = x0[m];
+        fl.valid = 0; fl.failed++;
+    }
+    __syncwarp();
+    const bool ok = r.status == SOLVED || (r.status == MAX_ITER_EXCEEDED && fl.failed < 5);
+    double* h = a.horizon + (size_t)b * HN;
+    for (int e = lane; e < HN; e += 32) { const double v = w.GUESS[e]; a.warm[(size_t)e * B + b] = v; h[e] = v; }
+    if (lane < NU) a.u_out[b * NU + lane] = w.GUESS[NX + lane];
+    if (lane == 0) {
+        a.flags[b] = fl;
+        a.status[b] = r.status; a.iters[b] = r.iters; a.ok[b] = ok ? 1 : 0; a.qp_iters[b] = r.qp_iters; a.qp_fail[b] = r.qp_fail;
+        a.accept_mask[b] = (int32_t)r.accept_mask;
+    }
+}
+// solveOCP probe, one warp per instance: AoS guess / RobotData, optional iteration log
+__global__ void __launch_bounds__(SQPW_WARPS * 32) k_solve_ocp_warp(CycleArgs a, double* wws, size_t ws_per, size_t sm_per, double* guess, const double* rb,
+                                                                    const double* cur_u_all, int n, double* steps, double* alphas, int32_t* qp_ok, int max_log, int32_t* n_logged) {
+    extern __shared__ __align__(16) double sqpw_smem[];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * SQPW_WARPS + wid;
+    if (b >= n) return;
+    const Params& P = a.params[a.params_per_instance ? b : 0];
+    const TrackTable& T = a.tracks[a.track_id[b]];
+    const int HN = a.S * HZ;
+    WarpSqp w{P, T, make_dyn(P, a.Ts), a.Ts, a.N, a.S, lane, a.qp};
+    w.carve(wws + (size_t)b * ws_per, sqpw_smem + (size_t)wid * sm_per);
+    if (lane < NX) w.SC[WSC_TXU + lane] = P.Tx[lane];
+    else if (lane < HZ) w.SC[WSC_TXU + lane] = P.Tu[lane - NX];
+    for (int e = lane; e < HN; e += 32) w.GUESS[e] = guess[(size_t)b * HN + e];
+    __syncwarp();
+    double cur_u[NU];
+    for (int i = 0; i < NU; i++) cur_u[i] = cur_u_all[b * NU + i];
+    SqpLogRef lg{steps ? steps + (size_t)b * max_log * HN : nullptr, alphas + (size_t)b * max_log, qp_ok + (size_t)b * max_log, max_log, 0};
+    SqpResult r = w.run(cur_u, rb + (size_t)b * a.S * RB_DOUBLES, 1, RB_DOUBLES, max_log > 0 ? &lg : nullptr);
+    for (int e = lane; e < HN; e += 32) guess[(size_t)b * HN + e] = w.GUESS[e];
+    if (lane == 0) { a.status[b] = r.status; a.iters[b] = r.iters; n_logged[b] = lg.n; }
 }
 
 // ---- probe kernels ------------------------------------------------------------------------------
@@ -223,6 +289,7 @@ struct mpcc_cuda_handle {
     WarmFlags* d_flags = nullptr;
     double *d_u_out = nullptr, *d_horizon = nullptr;
     int32_t *d_status = nullptr, *d_iters = nullptr, *d_ok = nullptr, *d_qp_iters = nullptr, *d_qp_fail = nullptr, *d_accept = nullptr;
+    double* d_wws = nullptr; size_t wws_per = 0, wsm_per = 0;  // warp-kernel workspace (doubles per instance / per warp)
     double *d_wpack = nullptr, *d_bias = nullptr, *d_w_out_env = nullptr, *d_w_out_self = nullptr;
     int64_t launches = 0;
     bool profiling = false;
@@ -305,6 +372,8 @@ int mpcc_cuda_create(const mpcc_cuda_config* cfg, mpcc_cuda_handle** out) {
     A(h->alloc(&h->d_x0, B * NX)); A(h->alloc(&h->d_u0, B * NU)); A(h->alloc(&h->d_obs, B * 4)); A(h->alloc(&h->d_obs_dummy, B * 4));
     A(h->alloc(&h->d_warm, B * HN)); A(h->alloc(&h->d_step, B * HN)); A(h->alloc(&h->d_trial, B * HN));
     A(h->alloc(&h->d_filt, B * FILT_DOUBLES)); A(h->alloc(&h->d_ws, B * S * STAGE_WS));
+    h->wws_per = warp_ws_doubles(h->N); h->wsm_per = warp_smem_doubles(h->N);
+    A(h->alloc(&h->d_wws, B * h->wws_per));
     A(h->alloc(&h->d_qs, h->NS * DOF)); A(h->alloc(&h->d_rb, h->NS * RB_DOUBLES));
     A(h->alloc(&h->d_flags, B));
     A(h->alloc(&h->d_u_out, B * NU)); A(h->alloc(&h->d_horizon, B * HN));
@@ -316,6 +385,8 @@ int mpcc_cuda_create(const mpcc_cuda_config* cfg, mpcc_cuda_handle** out) {
     for (size_t b = 0; b < B; b++) { dummy[4 * b] = 3; dummy[4 * b + 1] = 3; dummy[4 * b + 2] = 3; dummy[4 * b + 3] = 0; }  // mpc.cpp:97-100
     CK(cudaMemcpyAsync(h->d_obs_dummy, dummy.data(), dummy.size() * 8, cudaMemcpyHostToDevice, h->stream));
     CK(cudaFuncSetAttribute(k_mlp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(k_sqp_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SQPW_WARPS * h->wsm_per * 8)));
+    CK(cudaFuncSetAttribute(k_solve_ocp_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SQPW_WARPS * h->wsm_per * 8)));
     CK(cudaStreamSynchronize(h->stream));
     *out = h;
     return MPCC_OK;
@@ -499,7 +570,8 @@ int mpcc_cuda_run_cycle_device(mpcc_cuda_handle* h, double* d_x0, const double* 
     rc = launch_robot_data(h, obs, h->S, prof);
     if (rc) return rc;
     if (prof) cudaEventRecord(h->ev[3], h->stream);
-    k_sqp_thread<<<(h->B + 31) / 32, 32, 0, h->stream>>>(a);
+    if (h->cfg.sqp_kernel == 1) k_sqp_thread<<<(h->B + 31) / 32, 32, 0, h->stream>>>(a);
+    else k_sqp_warp<<<(h->B + SQPW_WARPS - 1) / SQPW_WARPS, SQPW_WARPS * 32, SQPW_WARPS * h->wsm_per * 8, h->stream>>>(a, h->d_wws, h->wws_per, h->wsm_per);
     h->launches++;
     if (prof) cudaEventRecord(h->ev[4], h->stream);
     CK(cudaGetLastError());
@@ -698,7 +770,9 @@ int mpcc_cuda_solve_ocp(mpcc_cuda_handle* h, double* guess, const double* rb, co
     CK(cudaMemcpyAsync(d_cu, cur_u, (size_t)n * NU * 8, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemsetAsync(d_nl, 0, (size_t)n * 4, h->stream));
     CycleArgs a = make_args(h, h->d_x0, h->d_u0, h->d_obs_dummy);
-    k_solve_ocp<<<(n + 31) / 32, 32, 0, h->stream>>>(a, d_g, d_rb, d_cu, n, d_steps, d_alphas, d_qpok, max_log, d_nl);
+    if (h->cfg.sqp_kernel == 1) k_solve_ocp<<<(n + 31) / 32, 32, 0, h->stream>>>(a, d_g, d_rb, d_cu, n, d_steps, d_alphas, d_qpok, max_log, d_nl);
+    else k_solve_ocp_warp<<<(n + SQPW_WARPS - 1) / SQPW_WARPS, SQPW_WARPS * 32, SQPW_WARPS * h->wsm_per * 8, h->stream>>>(a, h->d_wws, h->wws_per, h->wsm_per, d_g, d_rb, d_cu, n,
+                                                                                                                        d_steps, d_alphas, d_qpok, max_log, d_nl);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(guess, d_g, n * HN * 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(status, h->d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));

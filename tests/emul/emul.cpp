@@ -63,6 +63,15 @@ int emu_solve_ocp(const double* params, const double* table, double Ts, int N, d
     return r.status == SOLVED;
 }
 
+// epilogue of runMPC_ (status policy, fallback horizon, warm-start flags); returns the reference's bool
+int emu_epilogue(int N, int status, int iters, const double* x0, double* guess, int* valid, int* failed) {
+    WarmFlags fl{*valid, *failed};
+    SqpResult r{status, iters, 0, 0, 0};
+    bool ok = cycle_epilogue(N, r, x0, WsRef{guess, 1}, fl);
+    *valid = fl.valid; *failed = fl.failed;
+    return ok ? 1 : 0;
+}
+
 // solve only the QP of the current linearisation; returns the normalised step in horizon layout
 int emu_solve_qp(const double* params, const double* table, double Ts, int N, const double* guess, const double* rb, const double* cur_u,
                  int qp_max_iter, double qp_eps, double* step_out, int* iters, double* res3) {

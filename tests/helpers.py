@@ -69,6 +69,21 @@ class Emul:
         k = nl.value
         return dict(ok=bool(ok), horizon=g, status=st.value, iters=it.value, qp_iters=qi.value, steps=steps[:k], alphas=al[:k], qp_ok=ok_[:k])
 
+    def epilogue(self, N, status, iters, x0, guess, valid, failed):
+        g = f64(guess).copy(); v, f = C.c_int(valid), C.c_int(failed)
+        ok = self.lib.emu_epilogue(N, int(status), int(iters), _p(f64(x0)), _p(g), C.byref(v), C.byref(f))
+        return bool(ok), g, v.value, f.value
+
+    def run_cycle(self, nn, params, table, Ts, N, x0, u0, state, obs=(3., 3., 3., 0.), qp_max_iter=60, qp_eps=1e-9):
+        """One whole control cycle with the product's host-compiled code; RobotData from the oracle's networks
+        (the GPU tier checks the CUDA RobotData against the same oracle at 1e-9).  state = [warm, valid, failed]."""
+        x0n, warm, v, f = self.prologue(params, table, Ts, N, x0, u0, state[0], state[1], state[2])
+        rb = np.stack([nn.robot_data(warm[k, :7], obs) for k in range(N + 1)])
+        r = self.solve_ocp(params, table, Ts, N, warm, rb, u0, qp_max_iter, qp_eps)
+        ok, g, v, f = self.epilogue(N, r["status"], r["iters"], x0n, r["horizon"], v, f)
+        state[0], state[1], state[2] = g, v, f
+        return dict(x0=x0n, u0=g[0, 9:].copy(), horizon=g, status=r["status"], iters=r["iters"], ok=ok, accept=[int(a == 1.0) for a in r["alphas"]], qp_ok=r["qp_ok"])
+
     def solve_qp(self, params, table, Ts, N, guess, rb, cur_u, qp_max_iter=60, qp_eps=1e-9):
         step = np.zeros((N + 1, HZ)); it = C.c_int(); res = np.zeros(3)
         ok = self.lib.emu_solve_qp(_p(params), _p(table), C.c_double(Ts), N, _p(f64(guess)), _p(f64(rb)), _p(f64(cur_u)), qp_max_iter, C.c_double(qp_eps),
