@@ -147,6 +147,10 @@ int mpcc_cuda_eval_track(mpcc_cuda_handle* h, const double* s, int32_t n, double
 int mpcc_cuda_solve_ocp(mpcc_cuda_handle* h, double* guess, const double* rb, const double* cur_u, int32_t n,
                         int32_t* status, int32_t* iters, double* steps, double* alphas, int32_t max_log, int32_t* n_logged);
 
+/* Per-instance ComputeTime of the last cycle's solveOCP (osqp_interface.h:71-79) in seconds, device global timer:
+ * seconds [B][4] = total, set_qp, solve_qp, get_alpha.  Filled by the warp-per-instance kernel. */
+int mpcc_cuda_read_compute_time(mpcc_cuda_handle* h, double* seconds);
+
 /* Line-search decisions of the last cycle, per instance: bit i = the filter accepted the first trial of SQP
  * iteration i (filterLineSearch, osqp_interface.cpp:759-808; i < 32).  Diagnostic used by the parity tests to
  * replay the oracle along the same branch when a decision hinges on solver noise. */

@@ -17,7 +17,7 @@ EXPORTS = [
     "mpcc_cuda_run_cycle_device", "mpcc_cuda_read_results", "mpcc_cuda_result_pointers", "mpcc_cuda_stream", "mpcc_cuda_synchronize",
     "mpcc_cuda_get_warm_state", "mpcc_cuda_set_warm_state", "mpcc_cuda_sim_time_step", "mpcc_cuda_eval_robot_data", "mpcc_cuda_eval_stage",
     "mpcc_cuda_eval_track", "mpcc_cuda_solve_ocp", "mpcc_cuda_get_stats", "mpcc_cuda_sim_time_step_device", "mpcc_cuda_set_profiling",
-    "mpcc_cuda_get_kernel_times", "mpcc_cuda_fp64_peak", "mpcc_cuda_read_decisions",
+    "mpcc_cuda_get_kernel_times", "mpcc_cuda_fp64_peak", "mpcc_cuda_read_decisions", "mpcc_cuda_read_compute_time",
 ]
 
 
@@ -221,6 +221,12 @@ class BatchMPC:
         al = np.zeros((n, max(1, max_log))); steps = np.zeros((n, max(1, max_log), self.S, HZ)) if want_steps else None
         _check(lib().mpcc_cuda_solve_ocp(self.h, _p(g), _p(_f64(rb)), _p(_f64(cur_u)), n, _p(st), _p(it), _p(steps), _p(al), max_log, _p(nl)))
         return dict(horizon=g, status=st, iters=it, alphas=al, n_logged=nl, steps=steps)
+
+    def compute_time(self):
+        """[B][4] seconds: total, set_qp, solve_qp, get_alpha of the last cycle's solveOCP (per instance)."""
+        t = np.zeros((self.B, 4))
+        _check(lib().mpcc_cuda_read_compute_time(self.h, _p(t)))
+        return t
 
     def decisions(self):
         m = np.zeros(self.B, np.int32)

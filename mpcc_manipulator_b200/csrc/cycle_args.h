@@ -1,0 +1,47 @@
+// Kernel argument block of one control cycle and the launchers of the SQP kernels (each kernel family lives in
+// its own translation unit so that the library builds in parallel).
+#pragma once
+#include "mpcc_types.h"
+#include "dev_sqp.cuh"
+#include <cuda_runtime.h>
+
+namespace mpcc {
+
+constexpr int MAX_SQP_ITER = 128;  // largest sqp.max_iter a handle accepts (filter capacity)
+constexpr int FILT_DOUBLES = 2 * (MAX_SQP_ITER + 2);
+
+struct CycleArgs {
+    int B, N, S;
+    double Ts;
+    const Params* params; int params_per_instance;
+    const TrackTable* tracks; const int32_t* track_id;
+    double* x0; const double* u0; const double* obs;  // [B][9], [B][8], [B][4] (AoS)
+    double* warm;      // [S*17][B]  (SoA) warm start == SQP iterate
+    double* step;      // [S*17][B]
+    double* trial;     // [S*17][B]
+    double* filt;      // [FILT_DOUBLES][B]
+    double* ws;        // [S*STAGE_WS][B]
+    WarmFlags* flags;  // [B]
+    double* qs;        // [7][B*S]
+    double* rb;        // [150][B*S]
+    double* u_out;     // [B][8]
+    double* horizon;   // [B][S][17]
+    int32_t* status; int32_t* iters; int32_t* ok; int32_t* qp_iters; int32_t* qp_fail; int32_t* accept_mask;
+    long long* sqp_ns;  // per-instance duration of the SQP loop (ComputeTime::total analogue)
+    QpOptions qp;
+};
+
+
+// one thread per instance (k_sqp_thread.cu)
+void launch_sqp_thread(const CycleArgs& a, cudaStream_t s);
+void launch_solve_ocp_thread(const CycleArgs& a, double* guess, const double* rb, const double* cur_u, int n, double* steps, double* alphas,
+                             int32_t* qp_ok, int max_log, int32_t* n_logged, cudaStream_t s);
+// one warp per instance (k_sqp_warp.cu)
+size_t sqp_warp_ws_doubles(int N);    // global workspace per instance
+size_t sqp_warp_smem_bytes(int N);    // dynamic shared memory per CTA
+cudaError_t configure_sqp_warp(int N);
+void launch_sqp_warp(const CycleArgs& a, double* wws, cudaStream_t s);
+void launch_solve_ocp_warp(const CycleArgs& a, double* wws, double* guess, const double* rb, const double* cur_u, int n, double* steps, double* alphas,
+                           int32_t* qp_ok, int max_log, int32_t* n_logged, cudaStream_t s);
+
+}  // namespace mpcc

@@ -1,0 +1,89 @@
+// Warp-per-instance SQP kernels (default): see sqp_warp.cuh.
+#include "cycle_args.h"
+#include "sqp_warp.cuh"
+
+namespace mpcc {
+
+// SQP loop + epilogue, one WARP per instance (sqp_warp.cuh)
+constexpr int SQPW_WARPS = 2;  // warps (instances) per CTA
+__global__ void __launch_bounds__(SQPW_WARPS * 32, 6) k_sqp_warp(CycleArgs a, double* wws, size_t ws_per, size_t sm_per) {
+    extern __shared__ __align__(16) double sqpw_smem[];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * SQPW_WARPS + wid;
+    if (b >= a.B) return;  // whole warps leave together
+    const Params& P = a.params[a.params_per_instance ? b : 0];
+    const TrackTable& T = a.tracks[a.track_id[b]];
+    const size_t B = (size_t)a.B, NS = B * a.S;
+    const int HN = a.S * HZ;
+    WarpSqp w{P, T, make_dyn(P, a.Ts), a.Ts, a.N, a.S, a.qp, Warp{lane}};
+    w.carve(wws + (size_t)b * ws_per, sqpw_smem + (size_t)wid * sm_per);
+    for (int e = lane; e < HN; e += 32) w.GUESS[e] = a.warm[(size_t)e * B + b];
+    __syncwarp();
+    double cur_u[NU], x0[NX];
+    for (int i = 0; i < NU; i++) cur_u[i] = a.u0[b * NU + i];
+    for (int i = 0; i < NX; i++) x0[i] = a.x0[b * NX + i];
+    long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    SqpResult r = w.run(cur_u, a.rb + (size_t)b * a.S, NS, 1, nullptr);
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    // epilogue of runMPC_ (mpc.cpp:140-188)
+    WarmFlags fl = a.flags[b];
+    if (r.status == SOLVED) { fl.valid = 1; fl.failed = 0; }
+    else {
+        for (int e = lane; e < HN; e += 32) { const int rr = e % HZ; w.GUESS[e] = (rr < NX) ? x0[0] : 0.0; }
+        __syncwarp();
+        for (int k = lane; k < a.S; k += 32) for (int m = 0; m < NX; m++) w.GUESS[k * HZ + m] = x0[m];
+        fl.valid = 0; fl.failed++;
+    }
+    __syncwarp();
+    const bool ok = r.status == SOLVED || (r.status == MAX_ITER_EXCEEDED && fl.failed < 5);
+    double* h = a.horizon + (size_t)b * HN;
+    for (int e = lane; e < HN; e += 32) { const double v = w.GUESS[e]; a.warm[(size_t)e * B + b] = v; h[e] = v; }
+    if (lane < NU) a.u_out[b * NU + lane] = w.GUESS[NX + lane];
+    if (lane == 0) {
+        a.flags[b] = fl;
+        a.status[b] = r.status; a.iters[b] = r.iters; a.ok[b] = ok ? 1 : 0; a.qp_iters[b] = r.qp_iters; a.qp_fail[b] = r.qp_fail;
+        a.accept_mask[b] = (int32_t)r.accept_mask;
+        a.sqp_ns[4 * b] = t1 - t0; a.sqp_ns[4 * b + 1] = (long long)w.tm_set_qp; a.sqp_ns[4 * b + 2] = (long long)w.tm_solve_qp; a.sqp_ns[4 * b + 3] = (long long)w.tm_get_alpha;
+    }
+}
+// solveOCP probe, one warp per instance: AoS guess / RobotData, optional iteration log
+__global__ void __launch_bounds__(SQPW_WARPS * 32, 6) k_solve_ocp_warp(CycleArgs a, double* wws, size_t ws_per, size_t sm_per, double* guess, const double* rb,
+                                                                    const double* cur_u_all, int n, double* steps, double* alphas, int32_t* qp_ok, int max_log, int32_t* n_logged) {
+    extern __shared__ __align__(16) double sqpw_smem[];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * SQPW_WARPS + wid;
+    if (b >= n) return;
+    const Params& P = a.params[a.params_per_instance ? b : 0];
+    const TrackTable& T = a.tracks[a.track_id[b]];
+    const int HN = a.S * HZ;
+    WarpSqp w{P, T, make_dyn(P, a.Ts), a.Ts, a.N, a.S, a.qp, Warp{lane}};
+    w.carve(wws + (size_t)b * ws_per, sqpw_smem + (size_t)wid * sm_per);
+    for (int e = lane; e < HN; e += 32) w.GUESS[e] = guess[(size_t)b * HN + e];
+    __syncwarp();
+    double cur_u[NU];
+    for (int i = 0; i < NU; i++) cur_u[i] = cur_u_all[b * NU + i];
+    SqpLogRef lg{steps ? steps + (size_t)b * max_log * HN : nullptr, alphas + (size_t)b * max_log, qp_ok + (size_t)b * max_log, max_log, 0};
+    SqpResult r = w.run(cur_u, rb + (size_t)b * a.S * RB_DOUBLES, 1, RB_DOUBLES, max_log > 0 ? &lg : nullptr);
+    for (int e = lane; e < HN; e += 32) guess[(size_t)b * HN + e] = w.GUESS[e];
+    if (lane == 0) { a.status[b] = r.status; a.iters[b] = r.iters; n_logged[b] = lg.n; }
+}
+
+
+size_t sqp_warp_ws_doubles(int N) { return warp_ws_doubles(N); }
+size_t sqp_warp_smem_bytes(int N) { return SQPW_WARPS * warp_smem_doubles(N) * sizeof(double); }
+cudaError_t configure_sqp_warp(int N) {
+    cudaError_t e = cudaFuncSetAttribute(k_sqp_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sqp_warp_smem_bytes(N));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_solve_ocp_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sqp_warp_smem_bytes(N));
+}
+void launch_sqp_warp(const CycleArgs& a, double* wws, cudaStream_t s) {
+    k_sqp_warp<<<(a.B + SQPW_WARPS - 1) / SQPW_WARPS, SQPW_WARPS * 32, sqp_warp_smem_bytes(a.N), s>>>(a, wws, warp_ws_doubles(a.N), warp_smem_doubles(a.N));
+}
+void launch_solve_ocp_warp(const CycleArgs& a, double* wws, double* guess, const double* rb, const double* cur_u, int n, double* steps, double* alphas,
+                           int32_t* qp_ok, int max_log, int32_t* n_logged, cudaStream_t s) {
+    k_solve_ocp_warp<<<(n + SQPW_WARPS - 1) / SQPW_WARPS, SQPW_WARPS * 32, sqp_warp_smem_bytes(a.N), s>>>(a, wws, warp_ws_doubles(a.N), warp_smem_doubles(a.N), guess, rb,
+                                                                                                         cur_u, n, steps, alphas, qp_ok, max_log, n_logged);
+}
+
+}  // namespace mpcc

@@ -7,7 +7,7 @@
 #include "dev_stage.cuh"
 #include "dev_qp.cuh"
 #include "dev_sqp.cuh"
-#include "sqp_warp.cuh"
+#include "cycle_args.h"
 #include "mlp_kernel.cuh"
 #include "host/params_io.h"
 #include "host/track_fit.h"
@@ -26,32 +26,10 @@ static_assert(TRACK_DOUBLES == MPCC_TRACK_DOUBLES, "track layout");
 static_assert(sizeof(StageLin) == MPCC_STAGE_LIN_DOUBLES * sizeof(double), "stage lin layout");
 static_assert(RB_DOUBLES == MPCC_RB_DOUBLES, "robot data layout");
 
-constexpr int MAX_SQP_ITER = MAX_SQP_FILTER;
-constexpr int FILT_DOUBLES = 2 * (MAX_SQP_ITER + 2);
 
 // ------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------
-struct CycleArgs {
-    int B, N, S;
-    double Ts;
-    const Params* params; int params_per_instance;
-    const TrackTable* tracks; const int32_t* track_id;
-    double* x0; const double* u0; const double* obs;  // [B][9], [B][8], [B][4] (AoS)
-    double* warm;      // [S*17][B]  (SoA) warm start == SQP iterate
-    double* step;      // [S*17][B]
-    double* trial;     // [S*17][B]
-    double* filt;      // [FILT_DOUBLES][B]
-    double* ws;        // [S*STAGE_WS][B]
-    WarmFlags* flags;  // [B]
-    double* qs;        // [7][B*S]
-    double* rb;        // [150][B*S]
-    double* u_out;     // [B][8]
-    double* horizon;   // [B][S][17]
-    int32_t* status; int32_t* iters; int32_t* ok; int32_t* qp_iters; int32_t* qp_fail; int32_t* accept_mask;
-    QpOptions qp;
-};
-
 // prologue of runMPC_ (mpc.cpp:104-124): one thread per instance
 __global__ void k_prologue(CycleArgs a) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -96,92 +74,6 @@ __global__ void k_kin(const double* __restrict__ qs, double* __restrict__ rb, in
     for (int j = 0; j < DOF; j++) rb[(size_t)(RB_DMANIP + j) * NS + n] = dm[j];
 }
 
-// SQP loop + epilogue (osqp_interface.cpp:398-590, mpc.cpp:140-188): one thread per instance
-__global__ void k_sqp_thread(CycleArgs a) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= a.B) return;
-    const Params& P = a.params[a.params_per_instance ? b : 0];
-    const TrackTable& T = a.tracks[a.track_id[b]];
-    const size_t B = (size_t)a.B, NS = B * a.S;
-    WsRef guess{a.warm + b, B}, step{a.step + b, B}, trial{a.trial + b, B}, filt{a.filt + b, B}, ws{a.ws + b, B};
-    double cur_u[NU], x0[NX];
-    for (int i = 0; i < NU; i++) cur_u[i] = a.u0[b * NU + i];
-    for (int i = 0; i < NX; i++) x0[i] = a.x0[b * NX + i];
-    SqpResult r = sqp_solve(P, T, a.Ts, a.N, guess, step, trial, filt, cur_u, a.rb + (size_t)b * a.S, NS, 1, ws, a.qp, nullptr);
-    WarmFlags fl = a.flags[b];
-    bool ok = cycle_epilogue(a.N, r, x0, guess, fl);
-    a.flags[b] = fl;
-    a.status[b] = r.status; a.iters[b] = r.iters; a.ok[b] = ok ? 1 : 0; a.qp_iters[b] = r.qp_iters; a.qp_fail[b] = r.qp_fail; a.accept_mask[b] = (int32_t)r.accept_mask;
-    for (int j = 0; j < NU; j++) a.u_out[b * NU + j] = guess[NX + j];
-    double* h = a.horizon + (size_t)b * a.S * HZ;
-    for (int e = 0; e < a.S * HZ; e++) h[e] = guess[e];
-}
-
-// SQP loop + epilogue, one WARP per instance (sqp_warp.cuh)
-constexpr int SQPW_WARPS = 2;  // warps (instances) per CTA
-__global__ void __launch_bounds__(SQPW_WARPS * 32) k_sqp_warp(CycleArgs a, double* wws, size_t ws_per, size_t sm_per) {
-    extern __shared__ __align__(16) double sqpw_smem[];
-    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.x * SQPW_WARPS + wid;
-    if (b >= a.B) return;  // whole warps leave together
-    const Params& P = a.params[a.params_per_instance ? b : 0];
-    const TrackTable& T = a.tracks[a.track_id[b]];
-    const size_t B = (size_t)a.B, NS = B * a.S;
-    const int HN = a.S * HZ;
-    WarpSqp w{P, T, make_dyn(P, a.Ts), a.Ts, a.N, a.S, lane, a.qp};
-    w.carve(wws + (size_t)b * ws_per, sqpw_smem + (size_t)wid * sm_per);
-    if (lane < NX) w.SC[WSC_TXU + lane] = P.Tx[lane];
-    else if (lane < HZ) w.SC[WSC_TXU + lane] = P.Tu[lane - NX];
-    for (int e = lane; e < HN; e += 32) w.GUESS[e] = a.warm[(size_t)e * B + b];
-    __syncwarp();
-    double cur_u[NU], x0[NX];
-    for (int i = 0; i < NU; i++) cur_u[i] = a.u0[b * NU + i];
-    for (int i = 0; i < NX; i++) x0[i] = a.x0[b * NX + i];
-    SqpResult r = w.run(cur_u, a.rb + (size_t)b * a.S, NS, 1, nullptr);
-    // epilogue of runMPC_ (mpc.cpp:140-188)
-    WarmFlags fl = a.flags[b];
-    if (r.status == SOLVED) { fl.valid = 1; fl.failed = 0; }
-    else {
-        for (int e = lane; e < HN; e += 32) { const int rr = e % HZ; w.GUESS[e] = (rr < NX) ? x0[0] : 0.0; }
-        __syncwarp();
-        for (int k = lane; k < a.S; k += 32) for (int m = 0; m < NX; m++) w.GUESS[k * HZ + m] = x0[m];
-        fl.valid = 0; fl.failed++;
-    }
-    __syncwarp();
-    const bool ok = r.status == SOLVED || (r.status == MAX_ITER_EXCEEDED && fl.failed < 5);
-    double* h = a.horizon + (size_t)b * HN;
-    for (int e = lane; e < HN; e += 32) { const double v = w.GUESS[e]; a.warm[(size_t)e * B + b] = v; h[e] = v; }
-    if (lane < NU) a.u_out[b * NU + lane] = w.GUESS[NX + lane];
-    if (lane == 0) {
-        a.flags[b] = fl;
-        a.status[b] = r.status; a.iters[b] = r.iters; a.ok[b] = ok ? 1 : 0; a.qp_iters[b] = r.qp_iters; a.qp_fail[b] = r.qp_fail;
-        a.accept_mask[b] = (int32_t)r.accept_mask;
-    }
-}
-// solveOCP probe, one warp per instance: AoS guess / RobotData, optional iteration log
-__global__ void __launch_bounds__(SQPW_WARPS * 32) k_solve_ocp_warp(CycleArgs a, double* wws, size_t ws_per, size_t sm_per, double* guess, const double* rb,
-                                                                    const double* cur_u_all, int n, double* steps, double* alphas, int32_t* qp_ok, int max_log, int32_t* n_logged) {
-    extern __shared__ __align__(16) double sqpw_smem[];
-    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.x * SQPW_WARPS + wid;
-    if (b >= n) return;
-    const Params& P = a.params[a.params_per_instance ? b : 0];
-    const TrackTable& T = a.tracks[a.track_id[b]];
-    const int HN = a.S * HZ;
-    WarpSqp w{P, T, make_dyn(P, a.Ts), a.Ts, a.N, a.S, lane, a.qp};
-    w.carve(wws + (size_t)b * ws_per, sqpw_smem + (size_t)wid * sm_per);
-    if (lane < NX) w.SC[WSC_TXU + lane] = P.Tx[lane];
-    else if (lane < HZ) w.SC[WSC_TXU + lane] = P.Tu[lane - NX];
-    for (int e = lane; e < HN; e += 32) w.GUESS[e] = guess[(size_t)b * HN + e];
-    __syncwarp();
-    double cur_u[NU];
-    for (int i = 0; i < NU; i++) cur_u[i] = cur_u_all[b * NU + i];
-    SqpLogRef lg{steps ? steps + (size_t)b * max_log * HN : nullptr, alphas + (size_t)b * max_log, qp_ok + (size_t)b * max_log, max_log, 0};
-    SqpResult r = w.run(cur_u, rb + (size_t)b * a.S * RB_DOUBLES, 1, RB_DOUBLES, max_log > 0 ? &lg : nullptr);
-    for (int e = lane; e < HN; e += 32) guess[(size_t)b * HN + e] = w.GUESS[e];
-    if (lane == 0) { a.status[b] = r.status; a.iters[b] = r.iters; n_logged[b] = lg.n; }
-}
-
 // ---- probe kernels ------------------------------------------------------------------------------
 __global__ void k_eval_stage(const Params* params, const TrackTable* tracks, double Ts, int N, const double* x, const double* u, const double* up,
                              const double* un, const double* xn, const double* rb, const int32_t* k, int n, double* out) {
@@ -202,22 +94,6 @@ __global__ void k_eval_track(const TrackTable* tracks, const double* s, int n, d
     double* o = out + (size_t)i * 21;
     for (int c = 0; c < 3; c++) { o[c] = tp.pos[c]; o[3 + c] = tp.dpos[c]; o[6 + c] = tp.ddpos[c]; }
     track_eval_rot(tracks[0], s[i], o + 9, o + 18);
-}
-// solveOCP on given warm starts and RobotData (both AoS), logging the SQP iterations
-__global__ void k_solve_ocp(CycleArgs a, double* guess, const double* rb, const double* cur_u, int n, double* steps, double* alphas,
-                            int32_t* qp_ok, int max_log, int32_t* n_logged) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= n) return;
-    const Params& P = a.params[a.params_per_instance ? b : 0];
-    const TrackTable& T = a.tracks[a.track_id[b]];
-    const size_t B = (size_t)a.B;
-    const int HN = a.S * HZ;
-    WsRef g{guess + (size_t)b * HN, 1}, step{a.step + b, B}, trial{a.trial + b, B}, filt{a.filt + b, B}, ws{a.ws + b, B};
-    SqpLogRef lg{steps ? steps + (size_t)b * max_log * HN : nullptr, alphas + (size_t)b * max_log, qp_ok + (size_t)b * max_log, max_log, 0};
-    SqpResult r = sqp_solve(P, T, a.Ts, a.N, g, step, trial, filt, cur_u + b * NU, rb + (size_t)b * a.S * RB_DOUBLES, 1, RB_DOUBLES, ws, a.qp,
-                            max_log > 0 ? &lg : nullptr);
-    a.status[b] = r.status; a.iters[b] = r.iters;
-    n_logged[b] = lg.n;
 }
 __global__ void k_transpose_rb_out(const double* rb_soa, int NS, int n, double* rb_aos) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -289,6 +165,7 @@ struct mpcc_cuda_handle {
     WarmFlags* d_flags = nullptr;
     double *d_u_out = nullptr, *d_horizon = nullptr;
     int32_t *d_status = nullptr, *d_iters = nullptr, *d_ok = nullptr, *d_qp_iters = nullptr, *d_qp_fail = nullptr, *d_accept = nullptr;
+    long long* d_sqp_ns = nullptr;
     double* d_wws = nullptr; size_t wws_per = 0, wsm_per = 0;  // warp-kernel workspace (doubles per instance / per warp)
     double *d_wpack = nullptr, *d_bias = nullptr, *d_w_out_env = nullptr, *d_w_out_self = nullptr;
     int64_t launches = 0;
@@ -313,7 +190,7 @@ static CycleArgs make_args(mpcc_cuda_handle* h, double* d_x0, const double* d_u0
     a.x0 = d_x0; a.u0 = d_u0; a.obs = d_obs;
     a.warm = h->d_warm; a.step = h->d_step; a.trial = h->d_trial; a.filt = h->d_filt; a.ws = h->d_ws; a.flags = h->d_flags;
     a.qs = h->d_qs; a.rb = h->d_rb; a.u_out = h->d_u_out; a.horizon = h->d_horizon;
-    a.status = h->d_status; a.iters = h->d_iters; a.ok = h->d_ok; a.qp_iters = h->d_qp_iters; a.qp_fail = h->d_qp_fail; a.accept_mask = h->d_accept;
+    a.status = h->d_status; a.iters = h->d_iters; a.ok = h->d_ok; a.qp_iters = h->d_qp_iters; a.qp_fail = h->d_qp_fail; a.accept_mask = h->d_accept; a.sqp_ns = h->d_sqp_ns;
     a.qp = QpOptions{h->cfg.qp_max_iter, h->cfg.qp_eps};
     return a;
 }
@@ -372,12 +249,12 @@ int mpcc_cuda_create(const mpcc_cuda_config* cfg, mpcc_cuda_handle** out) {
     A(h->alloc(&h->d_x0, B * NX)); A(h->alloc(&h->d_u0, B * NU)); A(h->alloc(&h->d_obs, B * 4)); A(h->alloc(&h->d_obs_dummy, B * 4));
     A(h->alloc(&h->d_warm, B * HN)); A(h->alloc(&h->d_step, B * HN)); A(h->alloc(&h->d_trial, B * HN));
     A(h->alloc(&h->d_filt, B * FILT_DOUBLES)); A(h->alloc(&h->d_ws, B * S * STAGE_WS));
-    h->wws_per = warp_ws_doubles(h->N); h->wsm_per = warp_smem_doubles(h->N);
+    h->wws_per = sqp_warp_ws_doubles(h->N);
     A(h->alloc(&h->d_wws, B * h->wws_per));
     A(h->alloc(&h->d_qs, h->NS * DOF)); A(h->alloc(&h->d_rb, h->NS * RB_DOUBLES));
     A(h->alloc(&h->d_flags, B));
     A(h->alloc(&h->d_u_out, B * NU)); A(h->alloc(&h->d_horizon, B * HN));
-    A(h->alloc(&h->d_status, B)); A(h->alloc(&h->d_iters, B)); A(h->alloc(&h->d_ok, B)); A(h->alloc(&h->d_qp_iters, B)); A(h->alloc(&h->d_qp_fail, B)); A(h->alloc(&h->d_accept, B));
+    A(h->alloc(&h->d_status, B)); A(h->alloc(&h->d_iters, B)); A(h->alloc(&h->d_ok, B)); A(h->alloc(&h->d_qp_iters, B)); A(h->alloc(&h->d_qp_fail, B)); A(h->alloc(&h->d_accept, B)); A(h->alloc(&h->d_sqp_ns, 4 * B));
     A(h->alloc(&h->d_wpack, (size_t)MLP_NCHUNK * MLP_CHUNK_D)); A(h->alloc(&h->d_bias, MLP_BIAS_TOTAL));
     A(h->alloc(&h->d_w_out_env, 9 * 256)); A(h->alloc(&h->d_w_out_self, 64));
     if (ae != cudaSuccess) { mpcc_cuda_destroy(h); return fail(MPCC_ERR_CUDA, std::string("device allocation failed: ") + cudaGetErrorString(ae)); }
@@ -385,8 +262,7 @@ int mpcc_cuda_create(const mpcc_cuda_config* cfg, mpcc_cuda_handle** out) {
     for (size_t b = 0; b < B; b++) { dummy[4 * b] = 3; dummy[4 * b + 1] = 3; dummy[4 * b + 2] = 3; dummy[4 * b + 3] = 0; }  // mpc.cpp:97-100
     CK(cudaMemcpyAsync(h->d_obs_dummy, dummy.data(), dummy.size() * 8, cudaMemcpyHostToDevice, h->stream));
     CK(cudaFuncSetAttribute(k_mlp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_SMEM_BYTES));
-    CK(cudaFuncSetAttribute(k_sqp_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SQPW_WARPS * h->wsm_per * 8)));
-    CK(cudaFuncSetAttribute(k_solve_ocp_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SQPW_WARPS * h->wsm_per * 8)));
+    CK(configure_sqp_warp(h->N));
     CK(cudaStreamSynchronize(h->stream));
     *out = h;
     return MPCC_OK;
@@ -570,8 +446,8 @@ int mpcc_cuda_run_cycle_device(mpcc_cuda_handle* h, double* d_x0, const double* 
     rc = launch_robot_data(h, obs, h->S, prof);
     if (rc) return rc;
     if (prof) cudaEventRecord(h->ev[3], h->stream);
-    if (h->cfg.sqp_kernel == 1) k_sqp_thread<<<(h->B + 31) / 32, 32, 0, h->stream>>>(a);
-    else k_sqp_warp<<<(h->B + SQPW_WARPS - 1) / SQPW_WARPS, SQPW_WARPS * 32, SQPW_WARPS * h->wsm_per * 8, h->stream>>>(a, h->d_wws, h->wws_per, h->wsm_per);
+    if (h->cfg.sqp_kernel == 1) launch_sqp_thread(a, h->stream);
+    else launch_sqp_warp(a, h->d_wws, h->stream);
     h->launches++;
     if (prof) cudaEventRecord(h->ev[4], h->stream);
     CK(cudaGetLastError());
@@ -770,9 +646,8 @@ int mpcc_cuda_solve_ocp(mpcc_cuda_handle* h, double* guess, const double* rb, co
     CK(cudaMemcpyAsync(d_cu, cur_u, (size_t)n * NU * 8, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemsetAsync(d_nl, 0, (size_t)n * 4, h->stream));
     CycleArgs a = make_args(h, h->d_x0, h->d_u0, h->d_obs_dummy);
-    if (h->cfg.sqp_kernel == 1) k_solve_ocp<<<(n + 31) / 32, 32, 0, h->stream>>>(a, d_g, d_rb, d_cu, n, d_steps, d_alphas, d_qpok, max_log, d_nl);
-    else k_solve_ocp_warp<<<(n + SQPW_WARPS - 1) / SQPW_WARPS, SQPW_WARPS * 32, SQPW_WARPS * h->wsm_per * 8, h->stream>>>(a, h->d_wws, h->wws_per, h->wsm_per, d_g, d_rb, d_cu, n,
-                                                                                                                        d_steps, d_alphas, d_qpok, max_log, d_nl);
+    if (h->cfg.sqp_kernel == 1) launch_solve_ocp_thread(a, d_g, d_rb, d_cu, n, d_steps, d_alphas, d_qpok, max_log, d_nl, h->stream);
+    else launch_solve_ocp_warp(a, h->d_wws, d_g, d_rb, d_cu, n, d_steps, d_alphas, d_qpok, max_log, d_nl, h->stream);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(guess, d_g, n * HN * 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(status, h->d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
@@ -852,6 +727,16 @@ int mpcc_cuda_fp64_peak(int32_t device, double* tflops) {
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
     *tflops = best;
+    return MPCC_OK;
+}
+
+int mpcc_cuda_read_compute_time(mpcc_cuda_handle* h, double* seconds) {
+    if (!h || !seconds) return fail(MPCC_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(h->cfg.device));
+    std::vector<long long> ns((size_t)4 * h->B);
+    CK(cudaMemcpyAsync(ns.data(), h->d_sqp_ns, ns.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (size_t i = 0; i < ns.size(); i++) seconds[i] = 1e-9 * (double)ns[i];
     return MPCC_OK;
 }
 

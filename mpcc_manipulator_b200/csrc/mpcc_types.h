@@ -5,10 +5,10 @@
 
 #if defined(__CUDACC__)
 #define MPCC_HD __host__ __device__ __forceinline__
-#define MPCC_HDN __host__ __device__
+#define MPCC_HDN inline __host__ __device__
 #else
 #define MPCC_HD inline
-#define MPCC_HDN
+#define MPCC_HDN inline
 #endif
 
 namespace mpcc {

@@ -1,709 +1,843 @@
 // Warp-cooperative SQP loop: ONE WARP PER MPCC INSTANCE.
 //
-// Same algorithm as the one-thread-per-instance formulation in dev_sqp.cuh / dev_qp.cuh (which stays as the
-// host-compilable statement of the method and as the device kernel selected by sqp_kernel = 1):
-//   reference SQP loop          cpp/src/Interfaces/osqp_interface.cpp:398-590
-//   filter line search          :759-808
+// Same algorithm as the one-thread-per-instance formulation in dev_sqp.cuh / dev_qp.cuh:
+//   reference SQP loop           cpp/src/Interfaces/osqp_interface.cpp:398-590
+//   filter line search           :759-808
 //   QP (replaces OSQP, :592-656) Mehrotra predictor-corrector interior point; every Newton system solved by a
-//                               Riccati recursion on the state augmented with the previous joint-velocity step.
-// Work distribution inside the warp:
-//   * stage linearisation / trial evaluation: lane = stage (stage_eval is independent per stage);
-//   * every per-constraint and per-variable pass of the interior-point iteration: flat index over
-//     (stage, item), 32 items per round, warp-shuffle reductions for norms / step lengths;
-//   * the Riccati factorisation and the two triangular sweeps are sequential in the stage; inside a stage all
-//     32 lanes work on the 8x8 / 8x16 / 16x16 blocks held in this warp's shared-memory scratch.
-// Memory: the iterate, the current QP point and the Newton step live in shared memory; the per-stage QP blocks,
-// the per-constraint interior-point vectors and the Riccati factors live in a per-instance CONTIGUOUS global
-// workspace (every warp access is a run of consecutive doubles: full 128-byte lines).
+//                                Riccati recursion on the state augmented with the previous joint-velocity step.
 //
-// The dynamics multipliers are not iterated: the dual residual is evaluated with the costates obtained from the
-// state-stationarity recursion  p_N = g_N,  p_k = g_k + A' p_{k+1}  (g = gradient of the Lagrangian in xi with the
+// The code is written as a sequence of PHASES: inside a phase every lane works on its own items and only reads
+// data written in earlier phases; phases are separated by a warp barrier.  On the device a phase is one call
+// of its body with lane = threadIdx.x & 31 (reductions by warp shuffles); compiled for the host (tests/emul) a
+// phase is a loop over the 32 lanes, forwards or backwards, which is how the CPU-only test tier exercises this
+// exact code (and checks that no phase depends on the lane order).
+//
+// Work distribution:
+//   * stage linearisation / trial evaluation: lane = stage (stage_eval is independent per stage);
+//   * per-constraint and per-variable passes of the interior-point iteration: flat index over (stage, item),
+//     one loop per constraint type (box / rate / polytopic) so that a round does not diverge;
+//   * Riccati factorisation and the two vector sweeps: sequential in the stage; inside a stage the 32 lanes work
+//     on the 8x8 / 8x16 / 16x16 / 14x14 blocks in this warp's shared-memory scratch with register blocking;
+//     the factor is stored as L^-1 and Lam = L^-1 Mnx so that both sweeps are pure mat-vecs.
+// Memory: the iterate, the QP point and the Newton step live in shared memory; the per-stage QP blocks, the
+// per-constraint interior-point vectors and the Riccati factors live in a per-instance CONTIGUOUS global
+// workspace (every warp access is a run of consecutive doubles).
+//
+// The dynamics multipliers are not iterated: the dual residual is evaluated with the costates of the
+// xi-stationarity recursion  p_N = g_N,  p_k = g_k + A' p_{k+1}  (g = gradient of the Lagrangian in xi with the
 // current inequality multipliers; p = -y of dev_qp.cuh), which zeroes the xi-residual by construction; the
-// termination test is then on the nu-stationarity residual g_nu,k + B' p_{k+1}, the primal residual and the
-// complementarity gap, with the same thresholds.
+// termination test is on the nu-stationarity residual g_nu,k + B' p_{k+1}, the primal residual and the
+// complementarity gap, with the thresholds of dev_qp.cuh.
 #pragma once
 #include "dev_sqp.cuh"
 
-#if defined(__CUDACC__)
 namespace mpcc {
 
-constexpr int MAX_SQP_FILTER = 128;  // largest sqp.max_iter a handle accepts (filter capacity)
-constexpr int WF_L = 0, WF_INV = 36, WF_LAM = 44, WF_SIZE = 172;  // per-stage factor record: L (packed lower), 1/diag, Lam (8 x 16)
-constexpr int WSC_PM = 0, WSC_MNX = 256, WSC_MNN = 384, WSC_FF = 448, WSC_GS = 520, WSC_WG = 674, WSC_VEC = 688, WSC_TXU = 752, WSC_SIZE = 772;
+// ---- the 32-lane execution abstraction -----------------------------------------------------------------------
+struct Warp {
+#if defined(__CUDA_ARCH__)
+    int lane;
+    template <class F> __device__ __forceinline__ void each(F f) const { f(lane); __syncwarp(); }
+    template <class F> __device__ __forceinline__ double rmax(F f) const {
+        double v = f(lane);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+        __syncwarp();
+        return v;
+    }
+    template <class F> __device__ __forceinline__ double rmin(F f) const {
+        double v = f(lane);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+        __syncwarp();
+        return v;
+    }
+    template <class F> __device__ __forceinline__ double rsum(F f) const {
+        double v = f(lane);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        __syncwarp();
+        return v;
+    }
+    template <class F> __device__ __forceinline__ bool any(F f) const {
+        bool r = __any_sync(0xffffffffu, f(lane));
+        __syncwarp();
+        return r;
+    }
+#else
+    bool reverse = false;
+    template <class F> void each(F f) const {
+        if (!reverse) for (int l = 0; l < 32; l++) f(l);
+        else for (int l = 31; l >= 0; l--) f(l);
+    }
+    template <class F> double rmax(F f) const { double v = -INFINITY; each([&](int l) { v = fmax(v, f(l)); }); return v; }
+    template <class F> double rmin(F f) const { double v = INFINITY; each([&](int l) { v = fmin(v, f(l)); }); return v; }
+    template <class F> double rsum(F f) const { double v = 0; each([&](int l) { v += f(l); }); return v; }
+    template <class F> bool any(F f) const { bool v = false; each([&](int l) { v = f(l) || v; }); return v; }
+#endif
+};
 
-// doubles of global workspace per instance
-__host__ __device__ inline size_t warp_ws_doubles(int N) {
+#if defined(__CUDA_ARCH__)
+#define MPCC_RSQRT(x) rsqrt(x)
+#else
+#define MPCC_RSQRT(x) (1.0 / sqrt(x))
+#endif
+
+// ---- layouts -------------------------------------------------------------------------------------------------
+// per-stage QP record written by the linearisation (polytopic rows live in the cycle-constant record)
+constexpr int WL_Q = 0, WL_q = 81, WL_RD = 90, WL_r = 98, WL_b = 106, WL_XLO = 115, WL_XHI = 124, WL_DLO = 133, WL_DHI = 140, WL_PRHS = 147, WL_SIZE = 158;
+constexpr int WC_SIZE = NPOLY * 14;   // cycle constants per stage: 11 normalised polytopic rows [ax(7) | au(7)]
+constexpr int WF_X = 0, WF_LAM = 64, WF_SIZE = 192;  // factor record: L^-1 (8 x 8, lower), Lam (8 x 16)
+// shared-memory scratch of one warp (doubles)
+constexpr int SC_P = 0, SC_PM = 256, SC_MNN = 512, SC_MNX = 576, SC_X = 704, SC_LAM = 768, SC_U = 896, SC_GS = 1092, SC_WP = 1246, SC_FF = 1258,
+              SC_VEC = 1330, SC_TXU = 1426, SC_RED = 1444, SC_SIZE = 1508;
+constexpr int V_P = 0, V_MN = 16, V_MX = 24, V_KAP = 40, V_D0 = 48, V_D1 = 64, V_RHS = 80, V_DN = 88;  // inside SC_VEC (96)
+constexpr int MAX_SQP_FILTER = 128;
+
+MPCC_HD size_t warp_ws_doubles(int N) {
     const size_t S = N + 1;
-    return S * (LIN_SIZE + 7 * NINEQ + HZ /*G*/ + 8 /*KAP*/ + WF_SIZE + HZ /*persistent step*/) + 2 * (MAX_SQP_FILTER + 2);
+    return S * (WL_SIZE + WC_SIZE + 7 * NINEQ + HZ /*G*/ + 8 /*KAP*/ + WF_SIZE + 2 * HZ /*persistent step, iterate*/) + 2 * (MAX_SQP_FILTER + 2);
 }
-// doubles of shared memory per warp
-__host__ __device__ inline size_t warp_smem_doubles(int N) { return (size_t)3 * (N + 1) * HZ + WSC_SIZE; }
+MPCC_HD size_t warp_smem_doubles(int N) { return (size_t)2 * (N + 1) * HZ + SC_SIZE; }
 
-__device__ __forceinline__ double wmax(double v) {
+// isPosdef / isNan of one packed-lower 9 x 9 Hessian block, fully unrolled (static indices: registers).
+// pd is cleared at the first non-positive pivot unless that pivot is NaN (NaN is reported through `nan`).
+MPCC_HD void block9_pd_nan(const double* Qp, bool& pd, bool& nan) {
+    double A[45];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
-__device__ __forceinline__ double wmin(double v) {
+    for (int e = 0; e < 45; e++) { A[e] = Qp[e]; if (A[e] != A[e]) nan = true; }
+    bool stop = false;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
-__device__ __forceinline__ double wsum(double v) {
+    for (int j = 0; j < 9; j++) {
+        double d = A[sym9(j, j)];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
+        for (int t = 0; t < 9; t++) if (t < j) d -= A[sym9(j, t)] * A[sym9(j, t)];
+        if (!stop && !(d > 0.0)) { stop = true; if (d == d) pd = false; }
+        const double sd = sqrt(d);
+#pragma unroll
+        for (int i = 0; i < 9; i++)
+            if (i > j) {
+                double v = A[sym9(i, j)];
+#pragma unroll
+                for (int t = 0; t < 9; t++) if (t < j) v -= A[sym9(i, t)] * A[sym9(j, t)];
+                A[sym9(i, j)] = v / sd;
+            }
+    }
 }
-__device__ __forceinline__ bool wany(bool p) { return __any_sync(0xffffffffu, p); }
 
 struct WarpSqp {
     const Params& P;
     const TrackTable& T;
     DynConst dyn;
     double Ts;
-    int N, S, lane;
+    int N, S;
     QpOptions opt;
-    // global, per instance
-    double *LIN, *IT, *ILAM, *IRP, *IW, *IV, *IDT, *IDLAM, *G, *KAP, *FACT, *SSTEP, *FILT;
-    // shared, per warp
-    double *GUESS, *VAR, *STEP, *SC;
+    Warp W;
+    // per-instance global workspace
+    double *LIN, *CST, *IT, *ILAM, *IRP, *IW, *IV, *IDT, *IDLAM, *G, *KAP, *FACT, *SSTEP, *GUESS, *FILT;
+    // per-warp shared memory
+    double *VAR, *STEP, *SC;
+    int OR_, OP_;  // offsets of the rate / polytopic sub-arrays inside the per-constraint vectors
+    // the reference's ComputeTime phases (osqp_interface.h:71-79) for this instance, in ns: set_qp, solve_qp, get_alpha
+    double tm_set_qp = 0, tm_solve_qp = 0, tm_get_alpha = 0;
+    MPCC_HD static double now_ns() {
+#if defined(__CUDA_ARCH__)
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        return (double)t;
+#else
+        return 0.0;
+#endif
+    }
 
-    __device__ void carve(double* gws, double* sm) {
+    MPCC_HD void carve(double* gws, double* sm) {
         const size_t S_ = S;
-        LIN = gws; gws += S_ * LIN_SIZE;
+        LIN = gws; gws += S_ * WL_SIZE;
+        CST = gws; gws += S_ * WC_SIZE;
         IT = gws; gws += S_ * NINEQ; ILAM = gws; gws += S_ * NINEQ; IRP = gws; gws += S_ * NINEQ; IW = gws; gws += S_ * NINEQ;
         IV = gws; gws += S_ * NINEQ; IDT = gws; gws += S_ * NINEQ; IDLAM = gws; gws += S_ * NINEQ;
-        G = gws; gws += S_ * HZ; KAP = gws; gws += S_ * 8; FACT = gws; gws += S_ * WF_SIZE; SSTEP = gws; gws += S_ * HZ; FILT = gws;
-        GUESS = sm; VAR = sm + S_ * HZ; STEP = sm + 2 * S_ * HZ; SC = sm + 3 * S_ * HZ;
+        G = gws; gws += S_ * HZ; KAP = gws; gws += S_ * 8; FACT = gws; gws += S_ * WF_SIZE; SSTEP = gws; gws += S_ * HZ; GUESS = gws; gws += S_ * HZ; FILT = gws;
+        VAR = sm; STEP = sm + S_ * HZ; SC = sm + 2 * S_ * HZ;
+        OR_ = 18 * S; OP_ = 32 * S;
     }
-    __device__ __forceinline__ double Tx(int m) const { return SC[WSC_TXU + m]; }
-    __device__ __forceinline__ double Tu(int j) const { return SC[WSC_TXU + 9 + j]; }
-    __device__ __forceinline__ static bool present(int N_, int k, int c) { return (c < NBOX) ? (k >= 1) : (k < N_); }
+    MPCC_HD void init_scratch() const {
+        W.each([&](int lane) {
+            if (lane < NX) SC[SC_TXU + lane] = P.Tx[lane];
+            else if (lane < HZ) SC[SC_TXU + lane] = P.Tu[lane - NX];
+        });
+    }
+    MPCC_HD double Tx(int m) const { return SC[SC_TXU + m]; }
+    MPCC_HD double Tu(int j) const { return SC[SC_TXU + NX + j]; }
 
-    // G z for constraint c of stage k on a [S][17] vector pair (xi | nu) held in shared memory
-    __device__ double gz(const double* Z, int k, int c) const {
+    // G z of one constraint on a [S][17] (xi | nu) vector in shared memory
+    MPCC_HD double gz_box(const double* Z, int k, int c) const { return (c < 9) ? -Z[k * HZ + c] : Z[k * HZ + c - 9]; }
+    MPCC_HD double gz_rate(const double* Z, int k, int c) const {
+        const int j = (c < 7) ? c : c - 7;
+        double d = Z[k * HZ + NX + j];
+        if (k >= 1) d -= Z[(k - 1) * HZ + NX + j];
+        return (c < 7) ? -d : d;
+    }
+    MPCC_HD double gz_poly(const double* Z, int k, int j) const {
+        const double* row = CST + ((size_t)k * NPOLY + j) * 14;
         const double* z = Z + k * HZ;
-        if (c < 9) return -z[c];
-        if (c < 18) return z[c - 9];
-        if (c < 32) {
-            const int j = (c < 25) ? c - 18 : c - 25;
-            double d = z[NX + j];
-            if (k >= 1) d -= z[NX + j - HZ];
-            return (c < 25) ? -d : d;
-        }
-        const int j = c - 32;
-        const double* L = LIN + (size_t)k * LIN_SIZE;
-        const double pd = L[LIN_PD + j];
-        const double* pg = L + LIN_PG + j * DOF;
         double s = 0;
 #pragma unroll
-        for (int m = 0; m < DOF; m++) {
-            const double g = pg[m];
-            s += (pd * g * Tx(m)) * z[m] + (-g * Tu(m)) * z[NX + m];
-        }
+        for (int m = 0; m < DOF; m++) s += row[m] * z[m] + row[7 + m] * z[NX + m];
         return s;
     }
-    __device__ __forceinline__ double hval(int k, int c) const {
-        const double* L = LIN + (size_t)k * LIN_SIZE;
-        if (c < 9) return -L[LIN_XLO + c];
-        if (c < 18) return L[LIN_XHI + c - 9];
-        if (c < 25) return -L[LIN_DLO + c - 18];
-        if (c < 32) return L[LIN_DHI + c - 25];
-        return L[LIN_PRHS + c - 32];
+    MPCC_HD double h_box(int k, int c) const { const double* L = LIN + (size_t)k * WL_SIZE; return (c < 9) ? -L[WL_XLO + c] : L[WL_XHI + c - 9]; }
+    MPCC_HD double h_rate(int k, int c) const { const double* L = LIN + (size_t)k * WL_SIZE; return (c < 7) ? -L[WL_DLO + c] : L[WL_DHI + c - 7]; }
+    MPCC_HD double h_poly(int k, int j) const { return LIN[(size_t)k * WL_SIZE + WL_PRHS + j]; }
+
+    // f(i, gz, h) for every PRESENT constraint (i = index into the per-constraint vectors), on vector Z
+    template <class F>
+    MPCC_HD void for_present(int lane, const double* Z, bool need_h, F f) const {
+        for (int i = 18 + lane; i < 18 * S; i += 32) { const int k = i / 18, c = i - k * 18; f(i, gz_box(Z, k, c), need_h ? h_box(k, c) : 0.0); }
+        for (int i = lane; i < 14 * N; i += 32) { const int k = i / 14, c = i - k * 14; f(OR_ + i, gz_rate(Z, k, c), need_h ? h_rate(k, c) : 0.0); }
+        for (int i = lane; i < NPOLY * N; i += 32) { const int k = i / NPOLY, j = i - k * NPOLY; f(OP_ + i, gz_poly(Z, k, j), need_h ? h_poly(k, j) : 0.0); }
     }
 
-    // ---- gradient of the step QP: g = H z + f + G' mu.  Writes g(mu = IV) to G (global); optionally also
-    //      g(mu = ILAM) to dst0 (shared) for the dual residual.
-    __device__ void gradient(double* dst0) const {
-        const int tot = S * HZ;
-        for (int o = lane; o < tot; o += 32) {
-            const int k = o / HZ, r = o - k * HZ;
-            const double* L = LIN + (size_t)k * LIN_SIZE;
-            const double* z = VAR + k * HZ;
-            const double* mv = IV + (size_t)k * NINEQ;
-            const double* ml = ILAM + (size_t)k * NINEQ;
-            double base = 0, sv = 0, sl = 0;
-            if (r < NX) {
-                base = L[LIN_q + r];
+    // ---- gradient of the step QP: G <- H z + f + G'(IV); dst0 (shared) <- same with multipliers ILAM ----
+    MPCC_HD void gradient(double* dst0) const {
+        W.each([&](int lane) {
+            for (int o = lane; o < NX * S; o += 32) {
+                const int k = o / NX, r = o - k * NX;
+                const double* L = LIN + (size_t)k * WL_SIZE;
+                const double* z = VAR + k * HZ;
+                double base = L[WL_q + r];
 #pragma unroll
-                for (int c = 0; c < NX; c++) base += L[LIN_Q + ((r >= c) ? sym9(r, c) : sym9(c, r))] * z[c];
-                sv = mv[9 + r] - mv[r];
-                if (dst0) sl = ml[9 + r] - ml[r];
+                for (int c = 0; c < NX; c++) base += L[WL_Q + r * 9 + c] * z[c];
+                double sv = IV[k * 18 + 9 + r] - IV[k * 18 + r];
+                double sl = dst0 ? ILAM[k * 18 + 9 + r] - ILAM[k * 18 + r] : 0.0;
                 if (k < N && r < DOF) {
-                    const double tx = Tx(r);
+                    const double* col = CST + (size_t)k * WC_SIZE + r;
 #pragma unroll
                     for (int j = 0; j < NPOLY; j++) {
-                        const double a = L[LIN_PD + j] * L[LIN_PG + j * DOF + r] * tx;
-                        sv += mv[32 + j] * a;
-                        if (dst0) sl += ml[32 + j] * a;
+                        const double a = col[j * 14];
+                        sv += IV[OP_ + k * NPOLY + j] * a;
+                        if (dst0) sl += ILAM[OP_ + k * NPOLY + j] * a;
                     }
                 }
-            } else if (k < N) {
-                const int j = r - NX;
-                base = L[LIN_RD + j] * z[r] + L[LIN_r + j];
+                G[k * HZ + r] = base + sv;
+                if (dst0) dst0[k * HZ + r] = base + sl;
+            }
+            for (int o = lane; o < NU * N; o += 32) {
+                const int k = o / NU, j = o - k * NU;
+                const double* L = LIN + (size_t)k * WL_SIZE;
+                const double* z = VAR + k * HZ + NX;
+                double base = L[WL_RD + j] * z[j] + L[WL_r + j];
+                double sv = 0, sl = 0;
                 if (j < DOF) {
-                    if (k >= 1) base += dyn.cpl[j] * z[r - HZ];
-                    if (k <= N - 2) base += dyn.cpl[j] * z[r + HZ];
-                    sv = mv[25 + j] - mv[18 + j];
-                    if (dst0) sl = ml[25 + j] - ml[18 + j];
-                    if (k + 1 <= N - 1) {
-                        sv -= mv[NINEQ + 25 + j] - mv[NINEQ + 18 + j];
-                        if (dst0) sl -= ml[NINEQ + 25 + j] - ml[NINEQ + 18 + j];
+                    if (k >= 1) base += dyn.cpl[j] * z[j - HZ];
+                    if (k <= N - 2) base += dyn.cpl[j] * z[j + HZ];
+                    const int ir = OR_ + k * 14;
+                    sv = IV[ir + 7 + j] - IV[ir + j];
+                    if (dst0) sl = ILAM[ir + 7 + j] - ILAM[ir + j];
+                    if (k + 1 < N) {
+                        sv -= IV[ir + 14 + 7 + j] - IV[ir + 14 + j];
+                        if (dst0) sl -= ILAM[ir + 14 + 7 + j] - ILAM[ir + 14 + j];
                     }
-                    const double tu = Tu(j);
+                    const double* col = CST + (size_t)k * WC_SIZE + 7 + j;
 #pragma unroll
                     for (int jj = 0; jj < NPOLY; jj++) {
-                        const double a = -L[LIN_PG + jj * DOF + j] * tu;
-                        sv += mv[32 + jj] * a;
-                        if (dst0) sl += ml[32 + jj] * a;
+                        const double a = col[jj * 14];
+                        sv += IV[OP_ + k * NPOLY + jj] * a;
+                        if (dst0) sl += ILAM[OP_ + k * NPOLY + jj] * a;
                     }
                 }
+                G[k * HZ + NX + j] = base + sv;
+                if (dst0) dst0[k * HZ + NX + j] = base + sl;
             }
-            G[o] = base + sv;
-            if (dst0) dst0[o] = base + sl;
-        }
-        __syncwarp();
+        });
     }
 
     // ---- Riccati factorisation; false if some M_nunu is not positive definite ----
-    __device__ bool factor() const {
-        double* Pm = SC + WSC_PM;    // 16 x 16 cost-to-go of stage k+1: rows/cols 0..8 = xi, 9..15 = previous dq step
-        double* Mnx = SC + WSC_MNX;  // 8 x 16
-        double* Mnn = SC + WSC_MNN;  // 8 x 8
-        double* FF = SC + WSC_FF;    // 8 x 9
-        double* GS = SC + WSC_GS;    // 11 x 14 polytopic rows (ax | au) of the current stage
-        double* WG = SC + WSC_WG;    // 11 barrier weights of the polytopic rows
+    MPCC_HD bool factor() const {
+        double* Pc = SC + SC_P;      // 16 x 16 cost-to-go of stage k+1 (rows/cols 0..8 xi, 9..15 previous dq step)
+        double* PM = SC + SC_PM;     // [Mxx 0; 0 Mww] of stage k
+        double* Mnn = SC + SC_MNN;   // 8 x 8
+        double* Mnx = SC + SC_MNX;   // 8 x 16
+        double* X = SC + SC_X;       // L^-1
+        double* Lam = SC + SC_LAM;   // L^-1 Mnx
+        double* U = SC + SC_U;       // 14 x 14 polytopic barrier Hessian  sum_p w_p g_p g_p'
+        double* Lc = SC + SC_U;      // Cholesky factor (U is dead by then)
+        double* INV = SC + SC_U + 64;
+        double* GS = SC + SC_GS;
+        double* WP = SC + SC_WP;
+        double* FF = SC + SC_FF;
         // terminal stage: P_N = Q_N + box W
-        {
-            const double* L = LIN + (size_t)N * LIN_SIZE;
-            const double* w = IW + (size_t)N * NINEQ;
+        W.each([&](int lane) {
+            const double* L = LIN + (size_t)N * WL_SIZE;
             for (int e = lane; e < 256; e += 32) {
                 const int r = e >> 4, c = e & 15;
                 double v = 0;
                 if (r < 9 && c < 9) {
-                    v = L[LIN_Q + ((r >= c) ? sym9(r, c) : sym9(c, r))];
-                    if (r == c) v += w[r] + w[9 + r];
+                    v = L[WL_Q + r * 9 + c];
+                    if (r == c) v += IW[N * 18 + r] + IW[N * 18 + 9 + r];
                 }
-                Pm[e] = v;
+                Pc[e] = v;
             }
-        }
-        __syncwarp();
+        });
         bool ok = true;
         for (int k = N - 1; k >= 0; k--) {
-            const double* L = LIN + (size_t)k * LIN_SIZE;
-            const double* w = IW + (size_t)k * NINEQ;
-            // stage the polytopic rows and their weights
-            for (int e = lane; e < NPOLY * 14; e += 32) {
-                const int j = e / 14, a = e - j * 14;
-                const double g = L[LIN_PG + j * DOF + (a < 7 ? a : a - 7)];
-                GS[e] = (a < 7) ? L[LIN_PD + j] * g * Tx(a) : -g * Tu(a - 7);
-            }
-            if (lane < NPOLY) WG[lane] = w[32 + lane];
-            // FF = B'Pxx + E'Pwx  (8 x 9)
-            for (int e = lane; e < 72; e += 32) {
-                const int i = e / 9, c = e - i * 9;
-                FF[e] = (i < 7) ? dyn.bq[i] * Pm[i * 16 + c] + Pm[(9 + i) * 16 + c] : dyn.bs * Pm[7 * 16 + c] + dyn.bv * Pm[8 * 16 + c];
-            }
-            __syncwarp();
-            // Mnn (8 x 8)
-            for (int e = lane; e < 64; e += 32) {
-                const int i = e >> 3, j = e & 7;
-                double v;
-                if (j < 7) {
-                    v = dyn.bq[j] * FF[i * 9 + j];
-                    if (i < 7) v += dyn.bq[i] * Pm[(9 + j) * 16 + i] + Pm[(9 + i) * 16 + 9 + j];
-                    else v += dyn.bs * Pm[(9 + j) * 16 + 7] + dyn.bv * Pm[(9 + j) * 16 + 8];
-                } else {
-                    v = dyn.bs * FF[i * 9 + 7] + dyn.bv * FF[i * 9 + 8];
+            const double* L = LIN + (size_t)k * WL_SIZE;
+            const double* wB = IW + k * 18;
+            const double* wR = IW + OR_ + k * 14;
+            const double* wP = IW + OP_ + k * NPOLY;
+            // F1: stage the polytopic rows and their barrier weights, FF = B'Pxx + E'Pwx (8 x 9)
+            W.each([&](int lane) {
+                const double* row = CST + (size_t)k * WC_SIZE;
+                for (int e = lane; e < WC_SIZE; e += 32) GS[e] = row[e];
+                if (lane < NPOLY) WP[lane] = wP[lane];
+                for (int e = lane; e < 72; e += 32) {
+                    const int i = e / 9, c = e - i * 9;
+                    FF[e] = (i < 7) ? dyn.bq[i] * Pc[i * 16 + c] + Pc[(9 + i) * 16 + c] : dyn.bs * Pc[7 * 16 + c] + dyn.bv * Pc[8 * 16 + c];
                 }
-                if (i == j) { v += L[LIN_RD + j]; if (j < 7) v += w[18 + j] + w[25 + j]; }
+            });
+            // F2: U = sum_p (w_p g_p) g_p'  in 2 x 2 register blocks
+            W.each([&](int lane) {
+                for (int blk = lane; blk < 49; blk += 32) {
+                    const int bi = blk / 7, bj = blk - bi * 7;
+                    double a00 = 0, a01 = 0, a10 = 0, a11 = 0;
 #pragma unroll
-                for (int p = 0; p < NPOLY; p++) if (i < 7 && j < 7) v += WG[p] * GS[p * 14 + 7 + i] * GS[p * 14 + 7 + j];
-                Mnn[e] = v;
-            }
-            // Mnx (8 x 16) = [FF A + poly | (cpl - wr) diag]
-            for (int e = lane; e < 128; e += 32) {
-                const int i = e >> 4, c = e & 15;
-                double v = 0;
-                if (c < 9) {
-                    v = FF[i * 9 + c];
-                    if (c == 8) v += dyn.asv * FF[i * 9 + 7];
-                    if (i < 7 && c < 7) {
-#pragma unroll
-                        for (int p = 0; p < NPOLY; p++) v += WG[p] * GS[p * 14 + 7 + i] * GS[p * 14 + c];
+                    for (int p = 0; p < NPOLY; p++) {
+                        const double wp = WP[p];
+                        const double w0 = wp * GS[p * 14 + 2 * bi], w1 = wp * GS[p * 14 + 2 * bi + 1];
+                        const double g0 = GS[p * 14 + 2 * bj], g1 = GS[p * 14 + 2 * bj + 1];
+                        a00 += w0 * g0; a01 += w0 * g1; a10 += w1 * g0; a11 += w1 * g1;
                     }
-                } else if (c - 9 == i && k >= 1) {
-                    v = dyn.cpl[i] - (w[18 + i] + w[25 + i]);
+                    U[(2 * bi) * 14 + 2 * bj] = a00; U[(2 * bi) * 14 + 2 * bj + 1] = a01;
+                    U[(2 * bi + 1) * 14 + 2 * bj] = a10; U[(2 * bi + 1) * 14 + 2 * bj + 1] = a11;
                 }
-                Mnx[e] = v;
-            }
-            __syncwarp();  // everybody has read P_{k+1}; overwrite it with [Mxx 0; 0 Mww]
-            {
-                double nv[8];
-#pragma unroll
-                for (int t = 0; t < 8; t++) {
-                    const int e = lane + 32 * t, r = e >> 4, c = e & 15;
+            });
+            // F3: Mnn (8 x 8), Mnx (8 x 16) and [Mxx 0; 0 Mww] (16 x 16)
+            W.each([&](int lane) {
+                for (int e = lane; e < 64; e += 32) {
+                    const int i = e >> 3, j = e & 7;
+                    double v;
+                    if (j < 7) {
+                        v = dyn.bq[j] * FF[i * 9 + j];
+                        if (i < 7) v += dyn.bq[i] * Pc[(9 + j) * 16 + i] + Pc[(9 + i) * 16 + 9 + j] + U[(7 + i) * 14 + 7 + j];
+                        else v += dyn.bs * Pc[(9 + j) * 16 + 7] + dyn.bv * Pc[(9 + j) * 16 + 8];
+                    } else {
+                        v = dyn.bs * FF[i * 9 + 7] + dyn.bv * FF[i * 9 + 8];
+                    }
+                    if (i == j) { v += L[WL_RD + j]; if (j < 7) v += wR[j] + wR[7 + j]; }
+                    Mnn[e] = v;
+                }
+                for (int e = lane; e < 128; e += 32) {
+                    const int i = e >> 4, c = e & 15;
+                    double v = 0;
+                    if (c < 9) {
+                        v = FF[i * 9 + c];
+                        if (c == 8) v += dyn.asv * FF[i * 9 + 7];
+                        if (i < 7 && c < 7) v += U[(7 + i) * 14 + c];
+                    } else if (c - 9 == i && k >= 1) {
+                        v = dyn.cpl[i] - (wR[i] + wR[7 + i]);
+                    }
+                    Mnx[e] = v;
+                }
+                for (int e = lane; e < 256; e += 32) {
+                    const int r = e >> 4, c = e & 15;
                     double v = 0;
                     if (r < 9 && c < 9) {
-                        v = Pm[e];
-                        if (c == 8) v += dyn.asv * Pm[r * 16 + 7];
-                        if (r == 8) v += dyn.asv * (Pm[7 * 16 + c] + ((c == 8) ? dyn.asv * Pm[7 * 16 + 7] : 0.0));
-                        v += L[LIN_Q + ((r >= c) ? sym9(r, c) : sym9(c, r))];
-                        if (r == c && k >= 1) v += w[r] + w[9 + r];
-                        if (r < 7 && c < 7) {
-#pragma unroll
-                            for (int p = 0; p < NPOLY; p++) v += WG[p] * GS[p * 14 + r] * GS[p * 14 + c];
-                        }
-                    } else if (r == c && k >= 1) {
-                        v = w[18 + (r - 9)] + w[25 + (r - 9)];
+                        v = Pc[e];
+                        if (c == 8) v += dyn.asv * Pc[r * 16 + 7];
+                        if (r == 8) v += dyn.asv * (Pc[7 * 16 + c] + ((c == 8) ? dyn.asv * Pc[7 * 16 + 7] : 0.0));
+                        v += L[WL_Q + r * 9 + c];
+                        if (r == c && k >= 1) v += wB[r] + wB[9 + r];
+                        if (r < 7 && c < 7) v += U[r * 14 + c];
+                    } else if (r == c && r >= 9 && k >= 1) {
+                        v = wR[r - 9] + wR[7 + r - 9];
                     }
-                    nv[t] = v;
+                    PM[e] = v;
                 }
-                __syncwarp();
-#pragma unroll
-                for (int t = 0; t < 8; t++) Pm[lane + 32 * t] = nv[t];
-            }
-            // Cholesky Mnn = L L' in place (lower triangle), right-looking; 1/L_jj kept in registers
-            double inv_d[8];
+            });
+            // F4: Cholesky Mnn = Lc Lc' column by column (lane = row); 1 / Lc_jj kept in INV
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                __syncwarp();
-                const double d = Mnn[j * 8 + j];
-                if (!(d > 0.0)) ok = false;
-                const double inv = rsqrt(d);
-                inv_d[j] = inv;
-                // trailing update of the lower triangle below/right of j; reads column j (not written here)
+                W.each([&](int lane) {
+                    if (lane >= j && lane < 8) {
+                        const int i = lane;
+                        double djj = Mnn[j * 8 + j], s = Mnn[i * 8 + j];
 #pragma unroll
-                for (int rnd = 0; rnd < 2; rnd++) {
-                    const int ee = lane + 32 * rnd, ii = ee >> 3, cc = ee & 7;
-                    if (ii > j && cc > j && cc <= ii) Mnn[ee] -= (Mnn[ii * 8 + j] * inv) * (Mnn[cc * 8 + j] * inv);
+                        for (int t = 0; t < 8; t++)
+                            if (t < j) { const double ljt = Lc[j * 8 + t]; djj -= ljt * ljt; s -= Lc[i * 8 + t] * ljt; }
+                        const double inv = MPCC_RSQRT(djj);
+                        if (i == j) { Lc[j * 8 + j] = djj * inv; INV[j] = (djj > 0.0) ? inv : -1.0; }
+                        else Lc[i * 8 + j] = s * inv;
+                    }
+                });
+            }
+            if (W.any([&](int lane) { return lane < 8 && !(INV[lane] > 0.0 && INV[lane] < 1e150); })) { ok = false; break; }
+            // F5: [Lam | X] = Lc^-1 [Mnx | I] by forward substitution, one column per lane (16 + 8 columns)
+            W.each([&](int lane) {
+                if (lane < 24) {
+                    const int c = lane;
+                    double col[8];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        double s = (c < 16) ? Mnx[i * 16 + (c & 15)] : ((i == c - 16) ? 1.0 : 0.0);
+#pragma unroll
+                        for (int t = 0; t < 8; t++) if (t < i) s -= Lc[i * 8 + t] * col[t];
+                        col[i] = s * INV[i];
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; i++) { if (c < 16) Lam[i * 16 + c] = col[i]; else X[i * 8 + c - 16] = col[i]; }
                 }
-                __syncwarp();
-                if (lane > j && lane < 8) Mnn[lane * 8 + j] *= inv;
-                if (lane == j) Mnn[j * 8 + j] = d * inv;
-            }
-            __syncwarp();
-            // Lam = L^-1 Mnx (8 x 16): one column per lane (lanes 0..15)
-            if (lane < 16) {
-                double col[8];
+            });
+            // F6: P_k = [Mxx 0; 0 Mww] - Lam' Lam  in 4 x 2 register blocks; F7: store the factor record
+            W.each([&](int lane) {
+                const int r0 = 4 * (lane >> 3), c0 = 2 * (lane & 7);
+                double acc[4][2];
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    double s = Mnx[i * 16 + lane];
+                for (int a = 0; a < 4; a++) { acc[a][0] = PM[(r0 + a) * 16 + c0]; acc[a][1] = PM[(r0 + a) * 16 + c0 + 1]; }
 #pragma unroll
-                    for (int t = 0; t < i; t++) s -= Mnn[i * 8 + t] * col[t];
-                    col[i] = s * inv_d[i];
+                for (int t = 0; t < 8; t++) {
+                    const double l0 = Lam[t * 16 + c0], l1 = Lam[t * 16 + c0 + 1];
+#pragma unroll
+                    for (int a = 0; a < 4; a++) { const double lr = Lam[t * 16 + r0 + a]; acc[a][0] -= lr * l0; acc[a][1] -= lr * l1; }
                 }
 #pragma unroll
-                for (int i = 0; i < 8; i++) Mnx[i * 16 + lane] = col[i];
-            }
-            __syncwarp();
-            // P_k = [Mxx 0; 0 Mww] - Lam' Lam
-#pragma unroll
-            for (int t = 0; t < 8; t++) {
-                const int e = lane + 32 * t, r = e >> 4, c = e & 15;
-                double s = Pm[e];
-#pragma unroll
-                for (int q = 0; q < 8; q++) s -= Mnx[q * 16 + r] * Mnx[q * 16 + c];
-                Pm[e] = s;
-            }
-            // store the factor of this stage
-            double* F = FACT + (size_t)k * WF_SIZE;
-            for (int e = lane; e < 36; e += 32) {
-                int i = 0;
-                while ((i + 1) * (i + 2) / 2 <= e) i++;
-                const int j = e - i * (i + 1) / 2;
-                F[WF_L + e] = Mnn[i * 8 + j];
-            }
-            if (lane < 8) {
-                double v = inv_d[0];
-#pragma unroll
-                for (int j = 1; j < 8; j++) if (lane == j) v = inv_d[j];
-                F[WF_INV + lane] = v;
-            }
-            for (int e = lane; e < 128; e += 32) F[WF_LAM + e] = Mnx[e];
-            __syncwarp();
+                for (int a = 0; a < 4; a++) { Pc[(r0 + a) * 16 + c0] = acc[a][0]; Pc[(r0 + a) * 16 + c0 + 1] = acc[a][1]; }
+                double* F = FACT + (size_t)k * WF_SIZE;
+                for (int e = lane; e < WF_SIZE; e += 32) F[e] = X[e];  // X and Lam are contiguous in the scratch
+            });
         }
-        return !wany(!ok);
+        return ok;
     }
 
     // ---- Riccati vector sweeps: Newton step for the gradient in G -> STEP (shared), KAP (global) ----
-    __device__ void solve_step() const {
-        double* FS = SC + WSC_PM;    // staged factor record of the current stage (172 doubles)
-        double* pv = SC + WSC_VEC;   // p = [px(9); pw(7)]
-        double* mn = SC + WSC_VEC + 16;
-        double* dv = SC + WSC_VEC + 32;  // forward: d = [dxi(9); dw(7)]
-        if (lane < 16) pv[lane] = (lane < 9) ? G[(size_t)N * HZ + lane] : 0.0;
-        __syncwarp();
+    MPCC_HD void solve_step() const {
+        double* FS[2] = {SC + SC_P, SC + SC_PM};  // staged factor records, double buffered (the P blocks are dead here)
+        double* V = SC + SC_VEC;
+        W.each([&](int lane) {
+            if (lane < 16) V[V_P + lane] = (lane < 9) ? G[(size_t)N * HZ + lane] : 0.0;
+            const double* F = FACT + (size_t)(N - 1) * WF_SIZE;
+            double* dst = FS[(N - 1) & 1];
+            for (int e = lane; e < WF_SIZE; e += 32) dst[e] = F[e];
+        });
         for (int k = N - 1; k >= 0; k--) {
-            const double* F = FACT + (size_t)k * WF_SIZE;
-            for (int e = lane; e < WF_SIZE; e += 32) FS[e] = F[e];
-            const double* g = G + (size_t)k * HZ;
-            if (lane < 8) {
-                const int i = lane;
-                mn[i] = (i < 7) ? g[NX + i] + dyn.bq[i] * pv[i] + pv[9 + i] : g[NX + 7] + dyn.bs * pv[7] + dyn.bv * pv[8];
-            }
-            double mx = 0;
-            if (lane < 9) { mx = g[lane] + pv[lane]; if (lane == 8) mx += dyn.asv * pv[7]; }
-            __syncwarp();
-            // kappa = L^-1 mn (every lane, redundantly)
-            double kap[8];
-            {
-                int q = 0;
+            const double* Fs = FS[k & 1];
+            W.each([&](int lane) {
+                double pre[6];
+                if (k > 0) {
+                    const double* F = FACT + (size_t)(k - 1) * WF_SIZE;
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    double s = mn[i];
-#pragma unroll
-                    for (int t = 0; t < i; t++) s -= FS[WF_L + q++] * kap[t];
-                    q++;
-                    kap[i] = s * FS[WF_INV + i];
+                    for (int t = 0; t < 6; t++) pre[t] = F[lane + 32 * t];
                 }
-            }
-            if (lane < 16) {
+                const double* g = G + (size_t)k * HZ;
+                const double* p = V + V_P;
+                if (lane < 8) V[V_MN + lane] = (lane < 7) ? g[NX + lane] + dyn.bq[lane] * p[lane] + p[9 + lane] : g[NX + 7] + dyn.bs * p[7] + dyn.bv * p[8];
+                if (lane < 16) {
+                    double mx = 0;
+                    if (lane < 9) { mx = g[lane] + p[lane]; if (lane == 8) mx += dyn.asv * p[7]; }
+                    V[V_MX + lane] = mx;
+                }
+                if (k > 0) {
+                    double* dst = FS[(k - 1) & 1];
 #pragma unroll
-                for (int t = 0; t < 8; t++) mx -= FS[WF_LAM + 16 * t + lane] * kap[t];
-            }
-            __syncwarp();
-            if (lane < 16) pv[lane] = mx;
-            if (lane < 8) {
-                double v = kap[0];
+                    for (int t = 0; t < 6; t++) dst[lane + 32 * t] = pre[t];
+                }
+            });
+            W.each([&](int lane) {
+                if (lane < 8) {
+                    double s = 0;
 #pragma unroll
-                for (int i = 1; i < 8; i++) if (lane == i) v = kap[i];
-                KAP[(size_t)k * 8 + lane] = v;
-            }
-            __syncwarp();
+                    for (int t = 0; t < 8; t++) s += Fs[WF_X + lane * 8 + t] * V[V_MN + t];  // X is lower triangular with explicit zeros
+                    V[V_KAP + lane] = s;
+                    KAP[(size_t)k * 8 + lane] = s;
+                }
+            });
+            W.each([&](int lane) {
+                if (lane < 16) {
+                    double mx = V[V_MX + lane];
+#pragma unroll
+                    for (int t = 0; t < 8; t++) mx -= Fs[WF_LAM + 16 * t + lane] * V[V_KAP + t];
+                    V[V_P + lane] = mx;
+                }
+            });
         }
         // forward
-        if (lane < 16) dv[lane] = 0.0;
-        if (lane < NX) STEP[lane] = 0.0;
-        __syncwarp();
+        W.each([&](int lane) {
+            if (lane < 16) V[V_D0 + lane] = 0.0;
+            if (lane < NX) STEP[lane] = 0.0;
+            const double* F = FACT;
+            double* dst = FS[0];
+            for (int e = lane; e < WF_SIZE; e += 32) dst[e] = F[e];
+        });
         for (int k = 0; k < N; k++) {
-            const double* F = FACT + (size_t)k * WF_SIZE;
-            for (int e = lane; e < WF_SIZE; e += 32) FS[e] = F[e];
-            __syncwarp();
-            if (lane < 8) {
-                double s = KAP[(size_t)k * 8 + lane];
+            const double* Fs = FS[k & 1];
+            const double* d = V + ((k & 1) ? V_D1 : V_D0);
+            double* dn_ = V + ((k & 1) ? V_D0 : V_D1);
+            W.each([&](int lane) {
+                double pre[6];
+                if (k + 1 < N) {
+                    const double* F = FACT + (size_t)(k + 1) * WF_SIZE;
 #pragma unroll
-                for (int c = 0; c < 16; c++) s += FS[WF_LAM + 16 * lane + c] * dv[c];
-                mn[lane] = -s;
-            }
-            __syncwarp();
-            // dn = L^-T rhs (every lane, redundantly)
-            double dn[8];
+                    for (int t = 0; t < 6; t++) pre[t] = F[lane + 32 * t];
+                }
+                if (lane < 8) {
+                    double s = KAP[(size_t)k * 8 + lane];
 #pragma unroll
-            for (int i = 7; i >= 0; i--) {
-                double s = mn[i];
+                    for (int c = 0; c < 16; c++) s += Fs[WF_LAM + 16 * lane + c] * d[c];
+                    V[V_RHS + lane] = -s;
+                }
+                if (k + 1 < N) {
+                    double* dst = FS[(k + 1) & 1];
 #pragma unroll
-                for (int t = i + 1; t < 8; t++) s -= FS[WF_L + t * (t + 1) / 2 + i] * dn[t];
-                dn[i] = s * FS[WF_INV + i];
-            }
-            double nx = 0;
-            double dsel = dn[0];  // dn[lane], selected with compile-time indices to keep dn in registers
+                    for (int t = 0; t < 6; t++) dst[lane + 32 * t] = pre[t];
+                }
+            });
+            W.each([&](int lane) {
+                if (lane < 8) {
+                    double s = 0;
 #pragma unroll
-            for (int i = 1; i < 8; i++) if (lane == i) dsel = dn[i];
-            if (lane < 7) nx = dv[lane] + dyn.bq[lane] * dsel;
-            else if (lane == 7) nx = dv[7] + dyn.asv * dv[8] + dyn.bs * dn[7];
-            else if (lane == 8) nx = dv[8] + dyn.bv * dn[7];
-            __syncwarp();
-            if (lane < 8) STEP[k * HZ + NX + lane] = dsel;
-            if (lane < 9) { dv[lane] = nx; STEP[(k + 1) * HZ + lane] = nx; }
-            else if (lane < 16) {
-                double v = dn[0];
-#pragma unroll
-                for (int i = 1; i < 7; i++) if (lane - 9 == i) v = dn[i];
-                dv[lane] = v;
-            }
-            __syncwarp();
+                    for (int t = 0; t < 8; t++) s += Fs[WF_X + t * 8 + lane] * V[V_RHS + t];
+                    V[V_DN + lane] = s;
+                    STEP[k * HZ + NX + lane] = s;
+                }
+            });
+            W.each([&](int lane) {
+                if (lane < 16) {
+                    double nx;
+                    if (lane < 7) nx = d[lane] + dyn.bq[lane] * V[V_DN + lane];
+                    else if (lane == 7) nx = d[7] + dyn.asv * d[8] + dyn.bs * V[V_DN + 7];
+                    else if (lane == 8) nx = d[8] + dyn.bv * V[V_DN + 7];
+                    else nx = V[V_DN + lane - 9];
+                    dn_[lane] = nx;
+                    if (lane < NX) STEP[(k + 1) * HZ + lane] = nx;
+                }
+            });
         }
-        if (lane < NU) STEP[N * HZ + NX + lane] = 0.0;
-        __syncwarp();
+        W.each([&](int lane) { if (lane < NU) STEP[N * HZ + NX + lane] = 0.0; });
     }
 
     // slack / multiplier steps from the primal step; largest step keeping t, lam > 0
-    __device__ double ineq_steps() const {
-        double a = 1.0;
-        const int tot = S * NINEQ;
-        for (int i = lane; i < tot; i += 32) {
-            const int k = i / NINEQ, c = i - k * NINEQ;
-            if (!present(N, k, c)) continue;
-            const double g = gz(STEP, k, c);
-            const double dt = -IRP[i] - g;
-            const double dl = -ILAM[i] + IV[i] + IW[i] * g;
-            IDT[i] = dt; IDLAM[i] = dl;
-            if (dt < 0) a = fmin(a, -IT[i] / dt);
-            if (dl < 0) a = fmin(a, -ILAM[i] / dl);
-        }
-        __syncwarp();
-        return wmin(a);
+    MPCC_HD double ineq_steps() const {
+        return W.rmin([&](int lane) {
+            double a = 1.0;
+            for_present(lane, STEP, false, [&](int i, double g, double) {
+                const double dt = -IRP[i] - g;
+                const double dl = -ILAM[i] + IV[i] + IW[i] * g;
+                IDT[i] = dt; IDLAM[i] = dl;
+                if (dt < 0) a = fmin(a, -IT[i] / dt);
+                if (dl < 0) a = fmin(a, -ILAM[i] / dl);
+            });
+            return a;
+        });
     }
 
-    // ---- interior-point loop; on success VAR holds the step (xi exact rollout of nu) ----
-    __device__ QpStats solve() const {
+    // ---- interior-point loop; on success VAR holds the step (xi = exact rollout of nu) ----
+    MPCC_HD QpStats solve() const {
         QpStats st;
         st.ok = 0; st.iters = 0; st.res_dual = 0; st.res_prim = 0; st.gap = 0;
         const int tot = S * NINEQ;
+        double* RED = SC + SC_RED;
         // feasibility of the boxes (stage 0: xi_0 = 0 must lie inside; others: lo <= hi)
-        {
-            bool bad = false;
-            for (int o = lane; o < S * NX; o += 32) {
-                const int k = o / NX, m = o - k * NX;
-                const double* L = LIN + (size_t)k * LIN_SIZE;
-                if (k == 0) { if (L[LIN_XLO + m] > 1e-9 || L[LIN_XHI + m] < -1e-9) bad = true; }
-                else if (L[LIN_XLO + m] > L[LIN_XHI + m]) bad = true;
+        if (W.any([&](int lane) {
+                bool bad = false;
+                for (int o = lane; o < S * NX; o += 32) {
+                    const int k = o / NX, m = o - k * NX;
+                    const double* L = LIN + (size_t)k * WL_SIZE;
+                    if (k == 0) { if (L[WL_XLO + m] > 1e-9 || L[WL_XHI + m] < -1e-9) bad = true; }
+                    else if (L[WL_XLO + m] > L[WL_XHI + m]) bad = true;
+                }
+                return bad;
+            })) return st;
+        // initial point: nu = 0, xi = rollout of the defects (lane = state component), t = max(h - Gz, 1), lam = 1
+        const double qn = W.rmax([&](int lane) {
+            double q = 0;
+            for (int o = lane; o < S * HZ; o += 32) {
+                const int k = o / HZ, r = o - k * HZ;
+                const double* L = LIN + (size_t)k * WL_SIZE;
+                if (r < NX) q = fmax(q, fabs(L[WL_q + r]));
+                else { VAR[o] = 0.0; G[o] = 0.0; if (k < N) q = fmax(q, fabs(L[WL_r + r - NX])); }
             }
-            if (wany(bad)) return st;
-        }
-        // initial point: nu = 0, xi = rollout of the defects, t = max(h - Gz, 1), lam = 1
-        double qn = 0;
-        {
-            double x = 0;
-            for (int k = 0; k <= N; k++) {
-                const double* L = LIN + (size_t)k * LIN_SIZE;
-                if (lane < NX) { VAR[k * HZ + lane] = x; qn = fmax(qn, fabs(L[LIN_q + lane])); }
-                else if (lane < HZ) { VAR[k * HZ + lane] = 0.0; if (k < N) qn = fmax(qn, fabs(L[LIN_r + lane - NX])); }
-                const double x8 = __shfl_sync(0xffffffffu, x, 8);
-                if (k < N && lane < NX) { x += L[LIN_b + lane]; if (lane == 7) x += dyn.asv * x8; }
+            if (lane < NX && lane != 7) {
+                double x = 0;
+                for (int k = 0; k <= N; k++) { VAR[k * HZ + lane] = x; if (k < N) x += LIN[(size_t)k * WL_SIZE + WL_b + lane]; }
             }
-            qn = wmax(qn);
-        }
-        __syncwarp();
-        for (int i = lane; i < tot; i += 32) {
-            const int k = i / NINEQ, c = i - k * NINEQ;
-            if (!present(N, k, c)) { IT[i] = 1; ILAM[i] = 0; IW[i] = 0; IV[i] = 0; IRP[i] = 0; continue; }
-            IT[i] = fmax(hval(k, c) - gz(VAR, k, c), 1.0);
-            ILAM[i] = 1.0;
-        }
-        __syncwarp();
+            return q;
+        });
+        W.each([&](int lane) {
+            if (lane == 7) {
+                double x = 0;
+                for (int k = 0; k <= N; k++) { VAR[k * HZ + 7] = x; if (k < N) x += dyn.asv * VAR[k * HZ + 8] + LIN[(size_t)k * WL_SIZE + WL_b + 7]; }
+            }
+            for (int i = lane; i < tot; i += 32) { IT[i] = 1.0; ILAM[i] = 0.0; IW[i] = 0.0; IV[i] = 0.0; IRP[i] = 0.0; IDT[i] = 0.0; IDLAM[i] = 0.0; }
+        });
+        W.each([&](int lane) {
+            for_present(lane, VAR, true, [&](int i, double g, double h) { IT[i] = fmax(h - g, 1.0); ILAM[i] = 1.0; });
+        });
         const double m_tot = 43.0 * N;
         for (int it = 0; it < opt.max_iter; it++) {
             // residuals, barrier weights, predictor v = lam rp / t
-            double mu = 0, nrp = 0;
-            for (int i = lane; i < tot; i += 32) {
-                const int k = i / NINEQ, c = i - k * NINEQ;
-                if (!present(N, k, c)) continue;
-                const double t = IT[i], lam = ILAM[i];
-                const double rp = gz(VAR, k, c) + t - hval(k, c);
-                IRP[i] = rp;
-                nrp = fmax(nrp, fabs(rp));
-                mu += t * lam;
-                const double w = lam / t;
-                IW[i] = w;
-                IV[i] = w * rp;
-            }
-            __syncwarp();
-            mu = wsum(mu) / m_tot;
-            nrp = wmax(nrp);
+            const double nrp = W.rmax([&](int lane) {
+                double nr = 0, mu_p = 0;
+                for_present(lane, VAR, true, [&](int i, double g, double h) {
+                    const double t = IT[i], lam = ILAM[i];
+                    const double rp = g + t - h;
+                    IRP[i] = rp;
+                    nr = fmax(nr, fabs(rp));
+                    mu_p += t * lam;
+                    const double w = lam / t;
+                    IW[i] = w;
+                    IV[i] = w * rp;
+                });
+                RED[lane] = mu_p;
+                return nr;
+            });
+            const double mu = W.rsum([&](int lane) { return RED[lane]; }) / m_tot;
             gradient(STEP);  // G <- predictor gradient; STEP <- Lagrangian gradient (scratch until the step is computed)
-            // costates by the xi-stationarity recursion and the nu-stationarity residual
-            double nrd = 0;
-            {
-                double y = 0;  // lane m < 9 holds y_{k}[m]
-                for (int k = N; k >= 1; k--) {
-                    const double y7 = __shfl_sync(0xffffffffu, y, 7);
-                    if (lane < NX) { y += STEP[k * HZ + lane]; if (lane == 8) y += dyn.asv * y7; }
-                    const double y8 = __shfl_sync(0xffffffffu, y, 8);
-                    if (lane < 7) nrd = fmax(nrd, fabs(STEP[(k - 1) * HZ + NX + lane] + dyn.bq[lane] * y));
-                    else if (lane == 7) nrd = fmax(nrd, fabs(STEP[(k - 1) * HZ + NX + 7] + dyn.bs * y + dyn.bv * y8));
+            // costates: in-place suffix recursion p_k = g_k + A' p_{k+1} on the xi part of STEP
+            W.each([&](int lane) {
+                if (lane < 8) for (int k = N - 1; k >= 1; k--) STEP[k * HZ + lane] += STEP[(k + 1) * HZ + lane];
+            });
+            W.each([&](int lane) {
+                if (lane == 8) for (int k = N - 1; k >= 1; k--) STEP[k * HZ + 8] += STEP[(k + 1) * HZ + 8] + dyn.asv * STEP[(k + 1) * HZ + 7];
+            });
+            const double nrd = W.rmax([&](int lane) {
+                double nr = 0;
+                for (int o = lane; o < NU * N; o += 32) {
+                    const int k = o / NU, j = o - k * NU;
+                    const double* pn = STEP + (k + 1) * HZ;
+                    const double btp = (j < 7) ? dyn.bq[j] * pn[j] : dyn.bs * pn[7] + dyn.bv * pn[8];
+                    nr = fmax(nr, fabs(STEP[k * HZ + NX + j] + btp));
                 }
-                nrd = wmax(nrd);
-            }
-            __syncwarp();
+                return nr;
+            });
             st.iters = it; st.res_dual = nrd; st.res_prim = nrp; st.gap = mu;
             if (nrd <= opt.eps * (1.0 + qn) && nrp <= opt.eps && mu <= opt.eps) { st.ok = 1; break; }
             if (!(nrd == nrd) || !(mu == mu)) break;
             if (!factor()) break;
             solve_step();
             const double a_aff = ineq_steps();
-            double mu_aff = 0;
-            for (int i = lane; i < tot; i += 32) {
-                const int k = i / NINEQ, c = i - k * NINEQ;
-                if (!present(N, k, c)) continue;
-                mu_aff += (IT[i] + a_aff * IDT[i]) * (ILAM[i] + a_aff * IDLAM[i]);
-            }
-            mu_aff = wsum(mu_aff) / m_tot;
+            const double mu_aff = W.rsum([&](int lane) {
+                double s = 0;
+                for (int i = lane; i < tot; i += 32) s += (IT[i] + a_aff * IDT[i]) * (ILAM[i] + a_aff * IDLAM[i]);  // absent: (1)(0)
+                return s;
+            }) / m_tot;
             const double sigma = (mu > 0) ? (mu_aff / mu) * (mu_aff / mu) * (mu_aff / mu) : 0.0;
             // corrector: v = (lam rp + sigma mu - dt_a dlam_a) / t
-            for (int i = lane; i < tot; i += 32) {
-                const int k = i / NINEQ, c = i - k * NINEQ;
-                if (!present(N, k, c)) continue;
-                IV[i] = (ILAM[i] * IRP[i] + sigma * mu - IDT[i] * IDLAM[i]) / IT[i];
-            }
-            __syncwarp();
+            W.each([&](int lane) {
+                const double sm = sigma * mu;
+                for (int i = 18 + lane; i < 18 * S; i += 32) IV[i] = (ILAM[i] * IRP[i] + sm - IDT[i] * IDLAM[i]) / IT[i];
+                for (int i = OR_ + lane; i < OR_ + 14 * N; i += 32) IV[i] = (ILAM[i] * IRP[i] + sm - IDT[i] * IDLAM[i]) / IT[i];
+                for (int i = OP_ + lane; i < OP_ + NPOLY * N; i += 32) IV[i] = (ILAM[i] * IRP[i] + sm - IDT[i] * IDLAM[i]) / IT[i];
+            });
             gradient(nullptr);
             solve_step();
             const double a = fmin(1.0, 0.995 * ineq_steps());
-            for (int o = lane; o < S * HZ; o += 32) VAR[o] += a * STEP[o];
-            for (int i = lane; i < tot; i += 32) {
-                const int k = i / NINEQ, c = i - k * NINEQ;
-                if (!present(N, k, c)) continue;
-                IT[i] += a * IDT[i];
-                ILAM[i] += a * IDLAM[i];
-            }
-            __syncwarp();
+            W.each([&](int lane) {
+                for (int o = lane; o < S * HZ; o += 32) VAR[o] += a * STEP[o];
+                for (int i = lane; i < tot; i += 32) { IT[i] += a * IDT[i]; ILAM[i] += a * IDLAM[i]; }  // absent: dt = dl = 0
+            });
             st.iters = it + 1;
         }
         if (st.ok) {
             // make the equalities exact: xi = rollout(nu)
-            double x = 0;
-            for (int k = 0; k <= N; k++) {
-                const double* L = LIN + (size_t)k * LIN_SIZE;
-                if (lane < NX) VAR[k * HZ + lane] = x;
-                const double x8 = __shfl_sync(0xffffffffu, x, 8);
-                if (k < N && lane < NX) {
-                    const double nu7 = VAR[k * HZ + NX + 7];
-                    if (lane < 7) x = x + dyn.bq[lane] * VAR[k * HZ + NX + lane] + L[LIN_b + lane];
-                    else if (lane == 7) x = x + dyn.asv * x8 + dyn.bs * nu7 + L[LIN_b + 7];
-                    else x = x + dyn.bv * nu7 + L[LIN_b + 8];
+            W.each([&](int lane) {
+                if (lane < NX && lane != 7) {
+                    double x = 0;
+                    for (int k = 0; k <= N; k++) {
+                        VAR[k * HZ + lane] = x;
+                        if (k < N) {
+                            const double b = LIN[(size_t)k * WL_SIZE + WL_b + lane];
+                            x = (lane < 7) ? x + dyn.bq[lane] * VAR[k * HZ + NX + lane] + b : x + dyn.bv * VAR[k * HZ + NX + 7] + b;
+                        }
+                    }
                 }
-            }
-            __syncwarp();
+            });
+            W.each([&](int lane) {
+                if (lane == 7) {
+                    double x = 0;
+                    for (int k = 0; k <= N; k++) {
+                        VAR[k * HZ + 7] = x;
+                        if (k < N) x = x + dyn.asv * VAR[k * HZ + 8] + dyn.bs * VAR[k * HZ + NX + 7] + LIN[(size_t)k * WL_SIZE + WL_b + 7];
+                    }
+                }
+            });
         }
         return st;
     }
 
-    // ---- horizon evaluation, lane = stage.  FULL: fill LIN; else objective / violation of guess + alpha T step ----
+    // ---- horizon evaluation at guess + alpha T step, lane = stage.
+    //      FULL: fill LIN (and, if write_cst, the polytopic rows), test the Hessian blocks (notpd / nan);
+    //      else only the objective and the l1 constraint violation ----
     template <bool FULL>
-    __device__ void eval_horizon(const double* cur_u, const double* rb, size_t rb_stride, size_t rb_stage, double alpha, double& obj, double& gap) const {
-        double o_acc = 0, g_acc = 0;
-        for (int k = lane; k <= N; k += 32) {
-            double x[NX], u[NU], up[DOF], un[DOF], xn[NX];
-            auto gx = [&](int kk, int e) -> double {
-                double v = GUESS[kk * HZ + e];
-                if (!FULL) {
-                    if (e < NX) v += alpha * (Tx(e) * SSTEP[kk * HZ + e]);
-                    else v = (kk < N) ? v + alpha * (Tu(e - NX) * SSTEP[kk * HZ + e]) : 0.0;
+    MPCC_HD void eval_horizon(const double* cur_u, const double* rb, size_t rb_stride, size_t rb_stage, double alpha, bool write_cst, double& obj, double& gap,
+                              bool* notpd, bool* nan) const {
+        double* RED = SC + SC_RED;
+        obj = W.rsum([&](int lane) {
+            double o_acc = 0, g_acc = 0;
+            bool pd_l = true, nan_l = false;
+            for (int k = lane; k <= N; k += 32) {
+                double x[NX], u[NU], up[DOF], un[DOF], xn[NX];
+                auto gx = [&](int kk, int e) -> double {
+                    double v = GUESS[kk * HZ + e];
+                    if (alpha != 0.0) {
+                        if (e < NX) v += alpha * (Tx(e) * SSTEP[kk * HZ + e]);
+                        else v = (kk < N) ? v + alpha * (Tu(e - NX) * SSTEP[kk * HZ + e]) : 0.0;
+                    }
+                    return v;
+                };
+                for (int e = 0; e < NX; e++) x[e] = gx(k, e);
+                for (int e = 0; e < NU; e++) u[e] = gx(k, NX + e);
+                for (int j = 0; j < DOF; j++) {
+                    up[j] = (k == 0) ? cur_u[j] : gx(k - 1, NX + j);
+                    un[j] = (k < N) ? gx(k + 1, NX + j) : 0.0;
                 }
-                return v;
-            };
-#pragma unroll
-            for (int e = 0; e < NX; e++) x[e] = gx(k, e);
-#pragma unroll
-            for (int e = 0; e < NU; e++) u[e] = gx(k, NX + e);
-#pragma unroll
-            for (int j = 0; j < DOF; j++) {
-                up[j] = (k == 0) ? cur_u[j] : gx(k - 1, NX + j);
-                un[j] = (k < N) ? gx(k + 1, NX + j) : 0.0;
+                for (int e = 0; e < NX; e++) xn[e] = (k < N) ? gx(k + 1, e) : 0.0;
+                StageLin sl;
+                RbView rv{rb + (size_t)k * rb_stage, rb_stride};
+                stage_eval<FULL>(P, T, Ts, N, k, x, u, up, un, xn, rv, sl);
+                o_acc += sl.obj; g_acc += sl.gap;
+                if (FULL) {
+                    block9_pd_nan(sl.Q, pd_l, nan_l);
+                    if (k < N) for (int j = 0; j < NU; j++) if (sl.Rd[j] != sl.Rd[j]) nan_l = true;
+                    double* L = LIN + (size_t)k * WL_SIZE;
+                    for (int r = 0; r < 9; r++) for (int c = 0; c < 9; c++) L[WL_Q + r * 9 + c] = sl.Q[(r >= c) ? sym9(r, c) : sym9(c, r)];
+                    for (int m = 0; m < NX; m++) { L[WL_q + m] = sl.q[m]; L[WL_b + m] = sl.b[m]; L[WL_XLO + m] = sl.xlo[m]; L[WL_XHI + m] = sl.xhi[m]; }
+                    for (int j = 0; j < NU; j++) { L[WL_RD + j] = sl.Rd[j]; L[WL_r + j] = sl.r[j]; }
+                    for (int j = 0; j < DOF; j++) { L[WL_DLO + j] = sl.dlo[j]; L[WL_DHI + j] = sl.dhi[j]; }
+                    for (int j = 0; j < NPOLY; j++) L[WL_PRHS + j] = sl.prhs[j];
+                    if (write_cst && k < N) {
+                        // the polytopic rows depend only on the (frozen) RobotData: constant over the cycle
+                        double* C = CST + (size_t)k * WC_SIZE;
+                        for (int j = 0; j < NPOLY; j++)
+                            for (int m = 0; m < DOF; m++) {
+                                const double g = sl.pg[j * DOF + m];
+                                C[j * 14 + m] = sl.pd[j] * g * Tx(m);
+                                C[j * 14 + 7 + m] = -g * Tu(m);
+                            }
+                    }
+                }
             }
-#pragma unroll
-            for (int e = 0; e < NX; e++) xn[e] = (k < N) ? gx(k + 1, e) : 0.0;
-            StageLin sl;
-            RbView rv{rb + (size_t)k * rb_stage, rb_stride};
-            stage_eval<FULL>(P, T, Ts, N, k, x, u, up, un, xn, rv, sl);
-            o_acc += sl.obj; g_acc += sl.gap;
-            if (FULL) {
-                double* L = LIN + (size_t)k * LIN_SIZE;
-                const double* src = (const double*)&sl;
-                for (int e = 0; e < LIN_SIZE; e++) L[e] = src[e];
+            if (FULL && lane < NU) {
+                // input block of the Hessian: per joint a tridiagonal (Rd, cpl) chain over the stages, dVs diagonal.
+                // Rd depends on the parameters only (dev_stage.cuh): same expression, no loads.
+                const int j = lane;
+                const double tu = P.Tu[j];
+                double d = 0;
+                for (int k = 0; k < N; k++) {
+                    const double kap = (k == 0 || k == N - 1) ? 2.0 : 4.0;
+                    const double rd = (j < 7) ? tu * ((2.0 * P.r_dq + 1e-6) + kap * P.r_ddq_solver) * tu : tu * (2.0 * P.r_dVs + 1e-6) * tu;
+                    d = (k == 0 || j == 7) ? rd : rd - dyn.cpl[j] * dyn.cpl[j] / d;
+                    if (d <= 0.0) { pd_l = false; break; }
+                }
             }
+            RED[32 + lane] = g_acc;
+            RED[lane] = (pd_l ? 0.0 : 1.0) + (nan_l ? 2.0 : 0.0);
+            return o_acc;
+        });
+        gap = W.rsum([&](int lane) { return RED[32 + lane]; });
+        if (FULL) {
+            *notpd = W.any([&](int lane) { const int f = (int)RED[lane]; return (f & 1) != 0; });
+            *nan = W.any([&](int lane) { const int f = (int)RED[lane]; return (f & 2) != 0; });
         }
-        __syncwarp();
-        obj = wsum(o_acc); gap = wsum(g_acc);
     }
 
     // ---- the SQP loop (solveOCP) ----
-    __device__ SqpResult run(const double* cur_u, const double* rb, size_t rb_stride, size_t rb_stage, SqpLogRef* log) {
+    MPCC_HD SqpResult run(const double* cur_u, const double* rb, size_t rb_stride, size_t rb_stage, SqpLogRef* log) {
         SqpResult res;
         res.status = SOLVED; res.iters = 0; res.qp_fail = 0; res.qp_iters = 0; res.accept_mask = 0;
         const int max_iter = (int)P.max_iter, ls_max = (int)P.line_search_max_iter;
         const int HN = S * HZ;
-        for (int e = lane; e < HN; e += 32) SSTEP[e] = 0.0;
-        __syncwarp();
+        init_scratch();
+        W.each([&](int lane) { for (int e = lane; e < HN; e += 32) SSTEP[e] = 0.0; });
         int n_filt = 0, it = 0;
         bool done = false;
+        bool have_lin = false, lin_notpd = false, lin_nan = false;  // LIN already holds the linearisation of GUESS
+        double inf_step = 0.0;                                       // inf-norm of the persistent step
         for (it = 0; it < max_iter; it++) {
-            double obj, gap;
-            eval_horizon<true>(cur_u, rb, rb_stride, rb_stage, 0.0, obj, gap);
+            const double t_a = now_ns();
+            if (!have_lin) {
+                double obj, gap;
+                eval_horizon<true>(cur_u, rb, rb_stride, rb_stage, 0.0, it == 0, obj, gap, &lin_notpd, &lin_nan);
+            }
+            have_lin = false;
             // mis-indexed input-bound rows (osqp_interface.cpp:273) intersected into the state boxes
-            for (int c = lane; c < NU * N; c += 32) {
-                const int k = c / NX, m = c - k * NX, i = c / NU, kk = c - i * NU;
-                const double uv = GUESS[i * HZ + NX + kk];
-                const double lo = (P.lu[kk] - uv) / Tu(kk), hi = (P.uu[kk] - uv) / Tu(kk);
-                double* L = LIN + (size_t)k * LIN_SIZE;
-                L[LIN_XLO + m] = fmax(L[LIN_XLO + m], lo);
-                L[LIN_XHI + m] = fmin(L[LIN_XHI + m], hi);
-            }
-            __syncwarp();
-            // isPosdef / isNan on the block structure of the Hessian (osqp_interface.cpp:454-473)
-            {
-                bool pd = true, nan = false;
-                for (int k = lane; k <= N; k += 32) {
-                    const double* L = LIN + (size_t)k * LIN_SIZE;
-                    double A[81];
-                    for (int r = 0; r < 9; r++) for (int c = 0; c <= r; c++) { A[9 * r + c] = L[LIN_Q + sym9(r, c)]; if (A[9 * r + c] != A[9 * r + c]) nan = true; }
-                    for (int j = 0; j < 9 && pd; j++) {
-                        double d = A[10 * j];
-                        for (int t = 0; t < j; t++) d -= A[9 * j + t] * A[9 * j + t];
-                        if (d <= 0.0) { pd = false; break; }
-                        d = sqrt(d);
-                        A[10 * j] = d;
-                        for (int i = j + 1; i < 9; i++) {
-                            double s = A[9 * i + j];
-                            for (int t = 0; t < j; t++) s -= A[9 * i + t] * A[9 * j + t];
-                            A[9 * i + j] = s / d;
-                        }
-                    }
+            W.each([&](int lane) {
+                for (int c = lane; c < NU * N; c += 32) {
+                    const int k = c / NX, m = c - k * NX, i = c / NU, kk = c - i * NU;
+                    const double uv = GUESS[i * HZ + NX + kk];
+                    const double lo = (P.lu[kk] - uv) / Tu(kk), hi = (P.uu[kk] - uv) / Tu(kk);
+                    double* L = LIN + (size_t)k * WL_SIZE;
+                    L[WL_XLO + m] = fmax(L[WL_XLO + m], lo);
+                    L[WL_XHI + m] = fmin(L[WL_XHI + m], hi);
                 }
-                if (lane < NU) {
-                    const int j = lane;
-                    double d = 0;
-                    for (int k = 0; k < N; k++) {
-                        const double rd = LIN[(size_t)k * LIN_SIZE + LIN_RD + j];
-                        if (rd != rd) nan = true;
-                        d = (k == 0 || j == 7) ? rd : rd - dyn.cpl[j] * dyn.cpl[j] / d;
-                        if (d <= 0.0) { pd = false; break; }
-                    }
-                }
-                pd = !wany(!pd); nan = wany(nan);
-                if (!pd) { res.status = NON_PD_HESSIAN; done = true; break; }
-                if (nan) { res.status = NAN_HESSIAN; done = true; break; }
-            }
+            });
+            // isPosdef / isNan on the block structure of the Hessian (osqp_interface.cpp:454-473), tested while linearising
+            if (lin_notpd) { res.status = NON_PD_HESSIAN; done = true; break; }
+            if (lin_nan) { res.status = NAN_HESSIAN; done = true; break; }
+            const double t_b = now_ns();
             QpStats qs = solve();
             res.qp_iters += qs.iters;
             if (qs.ok) {
-                for (int e = lane; e < HN; e += 32) { const int k = e / HZ, r = e - k * HZ; SSTEP[e] = (r < NX || k < N) ? VAR[e] : 0.0; }
+                inf_step = W.rmax([&](int lane) {
+                    double m = 0;
+                    for (int e = lane; e < HN; e += 32) { const int k = e / HZ, r = e - k * HZ; const double v = (r < NX || k < N) ? VAR[e] : 0.0; SSTEP[e] = v; m = fmax(m, fabs(v)); }
+                    return m;
+                });
             } else {
                 res.qp_fail++;  // step keeps its previous value (osqp_interface.cpp:479-505)
             }
-            __syncwarp();
+            const double t_c = now_ns();
+            tm_set_qp += t_b - t_a; tm_solve_qp += t_c - t_b;
             // ---- filterLineSearch (osqp_interface.cpp:759-808) ----
             double alpha = 1.0;
             bool accepted = true;  // never reset inside the loop (:767)
             for (int i = 0; i < ls_max; i++) {
-                if (accepted) {  // once a trial is rejected no later trial can be accepted: their evaluation is dead work
+                if (accepted) {  // once a trial is rejected no later trial can be accepted: evaluating them is dead work
                     double o2, g2;
-                    eval_horizon<false>(cur_u, rb, rb_stride, rb_stage, alpha, o2, g2);
-                    bool dom = false;
-                    for (int j = lane; j < n_filt; j += 32) if (o2 >= FILT[2 * j] && g2 >= FILT[2 * j + 1]) dom = true;
-                    if (wany(dom)) accepted = false;
+                    // If this trial is accepted and the loop goes on (alpha |step| >= eps_prim), the next iteration linearises
+                    // exactly at this point: evaluate it in full right away instead of values now and everything later.
+                    const bool spec = (i == 0) && (inf_step >= P.eps_prim) && (it + 1 < max_iter);
+                    bool sp_notpd = false, sp_nan = false;
+                    if (spec) eval_horizon<true>(cur_u, rb, rb_stride, rb_stage, alpha, false, o2, g2, &sp_notpd, &sp_nan);
+                    else eval_horizon<false>(cur_u, rb, rb_stride, rb_stage, alpha, false, o2, g2, nullptr, nullptr);
+                    if (W.any([&](int lane) {
+                            bool dom = false;
+                            for (int j = lane; j < n_filt; j += 32) if (o2 >= FILT[2 * j] && g2 >= FILT[2 * j + 1]) dom = true;
+                            return dom;
+                        })) accepted = false;
                     if (accepted) {
-                        if (lane == 0) {
-                            int w = 0;
-                            for (int j = 0; j < n_filt; j++)
-                                if (o2 > FILT[2 * j] || g2 > FILT[2 * j + 1]) { FILT[2 * w] = FILT[2 * j]; FILT[2 * w + 1] = FILT[2 * j + 1]; w++; }
-                            FILT[2 * w] = o2; FILT[2 * w + 1] = g2;
-                            n_filt = w + 1;
+                        // prune the entries the new point dominates, append it (sequential: order matters)
+                        int w = 0;
+                        for (int j = 0; j < n_filt; j++) {
+                            const double fo = FILT[2 * j], fg = FILT[2 * j + 1];
+                            if (o2 > fo || g2 > fg) {
+                                if (w != j) W.each([&](int lane) { if (lane == 0) { FILT[2 * w] = fo; FILT[2 * w + 1] = fg; } });
+                                w++;
+                            }
                         }
-                        n_filt = __shfl_sync(0xffffffffu, n_filt, 0);
-                        __syncwarp();
+                        W.each([&](int lane) { if (lane == 0) { FILT[2 * w] = o2; FILT[2 * w + 1] = g2; } });
+                        n_filt = w + 1;
+                        if (spec) { have_lin = true; lin_notpd = sp_notpd; lin_nan = sp_nan; }
                         break;
                     }
                 }
                 alpha *= P.line_search_tau;
             }
+            tm_get_alpha += now_ns() - t_c;
             if (accepted && it < 32) res.accept_mask |= (1u << it);
             // ---- take the step (osqp_interface.cpp:549-551) ----
-            double inf = 0;
-            for (int e = lane; e < HN; e += 32) {
-                const int k = e / HZ, r = e - k * HZ;
-                const double s = SSTEP[e];
-                if (r < NX) { GUESS[e] += alpha * (Tx(r) * s); inf = fmax(inf, fabs(s)); }
-                else if (k < N) { GUESS[e] += alpha * (Tu(r - NX) * s); inf = fmax(inf, fabs(s)); }
-                else GUESS[e] = 0.0;
-            }
-            __syncwarp();
-            inf = wmax(inf);
+            W.each([&](int lane) {
+                for (int e = lane; e < HN; e += 32) {
+                    const int k = e / HZ, r = e - k * HZ;
+                    const double s = SSTEP[e];
+                    if (r < NX) GUESS[e] += alpha * (Tx(r) * s);
+                    else if (k < N) GUESS[e] += alpha * (Tu(r - NX) * s);
+                    else GUESS[e] = 0.0;
+                }
+            });
+            const double inf = inf_step;
             if (log && log->n < log->max_log) {
-                if (log->steps) for (int e = lane; e < HN; e += 32) log->steps[(size_t)log->n * HN + e] = SSTEP[e];
-                if (lane == 0) { log->alphas[log->n] = alpha; log->qp_ok[log->n] = qs.ok; }
+                W.each([&](int lane) {
+                    if (log->steps) for (int e = lane; e < HN; e += 32) log->steps[(size_t)log->n * HN + e] = SSTEP[e];
+                    if (lane == 0) { log->alphas[log->n] = alpha; log->qp_ok[log->n] = qs.ok; }
+                });
                 log->n++;
             }
             if (alpha * inf < P.eps_prim) { res.status = SOLVED; res.iters = it + 1; done = true; break; }
@@ -715,4 +849,3 @@ struct WarpSqp {
 };
 
 }  // namespace mpcc
-#endif  // __CUDACC__

@@ -2,6 +2,7 @@
 // so the CPU-only test tier can exercise the exact code the CUDA kernels inline (there is no GPU in
 // the build container).  This object is never part of libmpcc_b200.so and is not a fallback path.
 #include "../../mpcc_manipulator_b200/csrc/dev_sqp.cuh"
+#include "../../mpcc_manipulator_b200/csrc/sqp_warp.cuh"
 #include "../../mpcc_manipulator_b200/csrc/host/track_fit.h"
 #include <cstring>
 #include <vector>
@@ -70,6 +71,51 @@ int emu_epilogue(int N, int status, int iters, const double* x0, double* guess, 
     bool ok = cycle_epilogue(N, r, x0, WsRef{guess, 1}, fl);
     *valid = fl.valid; *failed = fl.failed;
     return ok ? 1 : 0;
+}
+
+// The warp-per-instance formulation (sqp_warp.cuh) executed phase by phase on the host; reverse = lane order.
+int emu_warp_solve_ocp(const double* params, const double* table, double Ts, int N, double* guess, const double* rb, const double* cur_u,
+                       int qp_max_iter, double qp_eps, int reverse, int* status, int* iters, int* qp_iters, double* steps, double* alphas, int* qp_ok,
+                       int max_log, int* n_logged, unsigned* accept_mask) {
+    const Params& P = *(const Params*)params;
+    const int S = N + 1, HN = S * HZ;
+    std::vector<double> gws(warp_ws_doubles(N)), sm(warp_smem_doubles(N));
+    Warp wp; wp.reverse = reverse != 0;
+    WarpSqp w{P, *(const TrackTable*)table, make_dyn(P, Ts), Ts, N, S, QpOptions{qp_max_iter, qp_eps}, wp};
+    w.carve(gws.data(), sm.data());
+    for (int e = 0; e < HN; e++) w.GUESS[e] = guess[e];
+    SqpLogRef lg{steps, alphas, qp_ok, max_log, 0};
+    SqpResult r = w.run(cur_u, rb, 1, RB_DOUBLES, max_log > 0 ? &lg : nullptr);
+    for (int e = 0; e < HN; e++) guess[e] = w.GUESS[e];
+    *status = r.status; *iters = r.iters; *qp_iters = r.qp_iters; *n_logged = lg.n; *accept_mask = r.accept_mask;
+    return r.status == SOLVED;
+}
+// one QP of the warp formulation at the linearisation of `guess`
+int emu_warp_solve_qp(const double* params, const double* table, double Ts, int N, const double* guess, const double* rb, const double* cur_u,
+                      int qp_max_iter, double qp_eps, int reverse, double* step_out, int* iters, double* res3) {
+    const Params& P = *(const Params*)params;
+    const int S = N + 1, HN = S * HZ;
+    std::vector<double> gws(warp_ws_doubles(N)), sm(warp_smem_doubles(N));
+    Warp wp; wp.reverse = reverse != 0;
+    WarpSqp w{P, *(const TrackTable*)table, make_dyn(P, Ts), Ts, N, S, QpOptions{qp_max_iter, qp_eps}, wp};
+    w.carve(gws.data(), sm.data());
+    for (int e = 0; e < HN; e++) w.GUESS[e] = guess[e];
+    w.init_scratch();
+    double obj, gap;
+    bool f1, f2;
+    w.eval_horizon<true>(cur_u, rb, 1, RB_DOUBLES, 0.0, true, obj, gap, &f1, &f2);
+    for (int c = 0; c < NU * N; c++) {
+        const int k = c / NX, m = c % NX, i = c / NU, kk = c % NU;
+        const double uv = guess[i * HZ + NX + kk];
+        double* L = w.LIN + (size_t)k * WL_SIZE;
+        L[WL_XLO + m] = fmax(L[WL_XLO + m], (P.lu[kk] - uv) / P.Tu[kk]);
+        L[WL_XHI + m] = fmin(L[WL_XHI + m], (P.uu[kk] - uv) / P.Tu[kk]);
+    }
+    QpStats qs = w.solve();
+    for (int e = 0; e < HN; e++) step_out[e] = w.VAR[e];
+    for (int j = 0; j < NU; j++) step_out[N * HZ + NX + j] = 0.0;
+    *iters = qs.iters; res3[0] = qs.res_dual; res3[1] = qs.res_prim; res3[2] = qs.gap;
+    return qs.ok;
 }
 
 // solve only the QP of the current linearisation; returns the normalised step in horizon layout

@@ -269,3 +269,46 @@ def test_prologue_vs_oracle_cycles(O, nn, emu, track_wp, setup, rng):
     assert v2 == 1
     assert np.allclose(we[0, :9], xe) and np.allclose(we[1:N - 1], warm[2:N]) and np.allclose(we[N - 1], we[N - 2])
     assert np.allclose(we[N, :9], O.rk4(we[N - 1, :9], we[N - 1, 9:], Ts)) or we[N, 7] == o.track_length
+
+
+# ---- the warp-per-instance formulation (csrc/sqp_warp.cuh), executed phase by phase on the host ----------------
+@pytest.mark.parametrize("N", [10, 20, 40])
+def test_warp_qp_matches_thread_formulation_and_lane_order(O, nn, emu, track_wp, setup, rng, N):
+    """Same interior-point iteration, different work distribution: steps agree to rounding, and the result does not
+    depend on the order in which the 32 lanes of a phase are executed (no intra-phase data dependence)."""
+    p, pf, table = setup
+    Ts = p["Ts"]
+    for trial in range(3):
+        obs = None if trial == 0 else (0.48, 0.218, 0.521, 5.0)
+        hor, rb, cur_u = _stage_inputs(O, nn, rng, N, Ts, obs)
+        ok1, s1, it1, r1 = emu.solve_qp(pf, table, Ts, N, hor, rb, cur_u)
+        ok2, s2, it2, r2 = emu.warp_solve_qp(pf, table, Ts, N, hor, rb, cur_u)
+        ok3, s3, it3, r3 = emu.warp_solve_qp(pf, table, Ts, N, hor, rb, cur_u, reverse=True)
+        assert ok1 == ok2 == ok3
+        if ok1:
+            assert abs(it1 - it2) <= 1 and it2 == it3
+            assert np.abs(s1 - s2).max() < 1e-7 and np.abs(s2 - s3).max() < 1e-9
+
+
+@pytest.mark.parametrize("N", [10, 20])
+def test_warp_sqp_loop_vs_oracle(O, nn, emu, track_wp, setup, rng, N):
+    p, pf, table = setup
+    Ts = p["Ts"]
+    o = O.OracleMPC(N=N, nn=nn)
+    o.set_track(*track_wp)
+    for trial in range(6):
+        q0 = O.Q_HOME + rng.uniform(-0.05, 0.05, 7)
+        hor = np.tile(np.r_[q0, 0.0, 0.0, np.zeros(8)], (N + 1, 1))
+        rb = np.stack([nn.robot_data(hor[k, :7]) for k in range(N + 1)])
+        cur_u = np.zeros(8)
+        a = emu.warp_solve_ocp(pf, table, Ts, N, hor, rb, cur_u, reverse=bool(trial % 2))
+        o.set_forced_decisions([int(x == 1.0) for x in a["alphas"]])
+        b = o.solve_ocp(hor, rb, cur_u)
+        nat, mg = o.decision_log()
+        o.set_forced_decisions([])
+        assert a["status"] == b["status"] == 0 and a["iters"] == b["iters"]
+        assert np.allclose(a["alphas"], b["alphas"])
+        for i in range(len(b["steps"])):
+            assert np.abs(step_to_flat(a["steps"][i], N) - b["steps"][i]).max() < 1e-4
+            assert nat[i] == int(a["alphas"][i] == 1.0) or mg[i] < 1e-6
+        assert a["accept_mask"] == sum(int(x == 1.0) << i for i, x in enumerate(a["alphas"]))
