@@ -35,6 +35,10 @@ UNIT = "solves/s"
 # algorithmic FLOPs: minimal MAC counts of both networks with 7 forward-mode tangent columns
 MLP_FLOP_PER_STAGE = 2.0 * 1746688
 KIN_FLOP_PER_STAGE = 2.0 * 9000
+# SQP kernel, per interior-point iteration and stage: Riccati factorisation 4.2 k MAC (polytopic rank-11
+# update 1155, L^-1 Mnx 576, cost-to-go update 2048, blocks / Cholesky ~400), two sweeps 2 x 384, two gradients ~500,
+# three constraint passes ~500
+QP_FLOP_PER_STAGE_ITER = 2.0 * 6000
 NOMINAL_FP64_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12
 
 
@@ -246,11 +250,9 @@ def run_ours(args):
         st_out = torch.as_tensor(DevPtr(p_st, (B,), "<i4"), device=f"cuda:{local}")
         it_out = torch.as_tensor(DevPtr(p_it, (B,), "<i4"), device=f"cuda:{local}")
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")  # > 126 MB L2
-        if world > 1:
-            g_u = torch.empty((world * B, 8), dtype=torch.float64, device=f"cuda:{local}")
-            g_st = torch.empty((world * B, 2), dtype=torch.int32, device=f"cuda:{local}")
-            st_pack = torch.empty((B, 2), dtype=torch.int32, device=f"cuda:{local}")
     launches = {"n": 0}
+    gathered = {}
+    from mpcc_manipulator_b200.sharding import gather_results
 
     def step():
         """device-resident closed-loop step: cycle -> (gather) -> plant"""
@@ -259,10 +261,8 @@ def run_ours(args):
         launches["n"] += 4
         with torch.cuda.stream(stream):
             if world > 1:
-                # the path's only collective: gather the applied controls and per-instance status/iterations
-                st_pack[:, 0] = st_out; st_pack[:, 1] = it_out
-                dist.all_gather_into_tensor(g_u, u_out)
-                dist.all_gather_into_tensor(g_st, st_pack)
+                # the path's only collective: gather the applied controls and per-instance status / iterations (NCCL)
+                gathered["u0"], gathered["status"], gathered["iters"] = gather_results(u_out, st_out, it_out, world * B, dist)
             u.copy_(u_out)
         mpc.sim_time_step_device(x.data_ptr(), u.data_ptr(), xn.data_ptr())
         launches["n"] += 1
@@ -352,16 +352,32 @@ def run_ours(args):
     out = None
     if rank == 0:
         km = ktimes.mean(axis=0)
-        names = ["k_prologue", "k_kin", "k_mlp", "k_sqp"]
+        names = ["k_prologue", "k_kin", "k_mlp", "k_sqp_warp"]
         dom = int(np.argmax(km))
         peak = M.fp64_peak(local)
+        peak_src = ("FP64 FMA microbenchmark measured in this run (mpcc_cuda_fp64_peak); MEASURED_PEAKS.json holds no FP64 figure; "
+                    "nominal 148 SM x 64 FMA/clk x 1.965 GHz = %.1f" % NOMINAL_FP64_TFLOPS)
+        traffic = {}
+        try:
+            traffic = json.loads((ROOT / "profiles" / "dram_traffic.json").read_text())
+        except Exception:
+            pass
         mlp_flop = B * S * MLP_FLOP_PER_STAGE
+        qp_iters_step = float(stats_acc.get("qp_iters", 0))
+        sqp_flop = qp_iters_step * N * QP_FLOP_PER_STAGE_ITER
         kernels = {n: round(float(t), 4) for n, t in zip(names, km)}
-        roof = {"bound": "fp64", "kernel": "k_mlp", "achieved": mlp_flop / (km[2] * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
-                "frac": mlp_flop / (km[2] * 1e-3) / 1e12 / peak, "traffic": None,
-                "peak_source": "FP64 FMA microbenchmark measured in this run (mpcc_cuda_fp64_peak); MEASURED_PEAKS.json holds no FP64 figure; nominal 148 SM x 64 FMA/clk x 1.965 GHz = %.1f" % NOMINAL_FP64_TFLOPS,
-                "algorithmic_flops_per_launch": mlp_flop, "kernel_ms": float(km[2]), "dominant_kernel": names[dom],
-                "kernel_share_of_step": {n: round(float(t / step_ms.mean()), 4) for n, t in zip(names, km)}}
+        share = {n: round(float(t / step_ms.mean()), 4) for n, t in zip(names, km)}
+
+        def roof_of(kernel, flop, ms, note):
+            ach = flop / (ms * 1e-3) / 1e12
+            return {"bound": "fp64", "kernel": kernel, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                    "traffic": traffic.get(kernel), "algorithmic_flops_per_launch": flop, "kernel_ms": float(ms), "peak_source": peak_src, "note": note}
+        roof_mlp = roof_of("k_mlp", mlp_flop, km[2], "dense fp64 contraction (both networks + 7 forward-mode tangents); tcgen05 has no f64 kind, the DFMA pipe is the roof")
+        roof_sqp = roof_of("k_sqp_warp", sqp_flop, km[3], "interior-point / Riccati SQP loop: dependent small factorisations, latency- and DRAM-latency-bound "
+                           "(FLOP model x measured interior-point iterations of the last step); its DRAM traffic is in `traffic`")
+        roof = dict(roof_sqp if dom == 3 else roof_mlp)
+        roof["dominant_kernel"] = names[dom]
+        roof["kernel_share_of_step"] = share
         hbm_peak = None
         try:
             hbm_peak = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"]
@@ -370,6 +386,8 @@ def run_ours(args):
         alg_bytes = B * ((9 + 8 + 4) * 8 + 2 * (17 * N + 9) * 8 + 64 + 16)
         roof["hbm"] = {"algorithmic_bytes_per_step": alg_bytes, "achieved_gbs": alg_bytes / (step_ms.mean() * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                        "note": "arithmetic intensity ~1e4 FLOP/B: HBM fraction is tiny by construction (SURVEY 8d)"}
+        if traffic.get(names[dom]) and hbm_peak:
+            roof["hbm"]["dominant_kernel_dram_gbs"] = traffic[names[dom]] / (km[dom] * 1e-3) / 1e9
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                "config": {"workload": "C2 (BASELINE configs[1]): 4096 Panda instances per GPU, q0 = q_home + U(-0.05,0.05) seeded, default track.json, N=20, closed loop",
@@ -377,7 +395,7 @@ def run_ours(args):
                "latency_ms": {"p50": float(np.percentile(step_ms, 50)), "p99": float(np.percentile(step_ms, 99)), "max": float(step_ms.max())},
                "clocks": clocks, "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                                          "api": "mpcc_cuda_run_cycle (host buffers, pinned)"},
-               "gpu_launches": launches["n"], "kernels_ms": kernels, "roofline": roof,
+               "gpu_launches": launches["n"], "kernels_ms": kernels, "roofline": roof, "roofline_mlp": roof_mlp, "roofline_sqp": roof_sqp,
                "last_step_stats": stats_acc, "wall_s_timed_region": t_wall}
     mpc.close()
     if world > 1:

@@ -1,0 +1,41 @@
+"""The reference-shaped C++ host API (include/mpcc/mpcc.hpp) compiles with the host compiler alone and, on a GPU box,
+drives the closed loop of the reference's main.cpp through mpcc::MPC::runMPC."""
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def build_example():
+    subprocess.check_call(["make", "-s", "-C", str(ROOT / "examples")])
+    return ROOT / "examples" / "closed_loop"
+
+
+def test_cpp_api_compiles_and_fails_loudly_without_gpu():
+    exe = build_example()
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    r = subprocess.run([str(exe), str(ROOT / "mpcc_manipulator_b200/assets/params"), str(ROOT / "mpcc_manipulator_b200/assets/nn"), "2"], capture_output=True, text=True)
+    assert r.returncode == 1 and "CUDA" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_closed_loop_matches_golden():
+    exe = build_example()
+    r = subprocess.run([str(exe), str(ROOT / "mpcc_manipulator_b200/assets/params"), str(ROOT / "mpcc_manipulator_b200/assets/nn"), "31", "10"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    g = np.load(ROOT / "tests" / "golden" / "closed_loop_c1.npz")
+    m = re.search(r"track length ([0-9.]+), EE \(([-0-9.]+) ([-0-9.]+) ([-0-9.]+)\)", r.stdout)
+    assert abs(float(m.group(2)) - 0.5545) < 1e-4 and abs(float(m.group(4)) - 0.5211) < 1e-4
+    rows = re.findall(r"cycle\s+(\d+)\s+s ([-0-9.]+)\s+vs ([-0-9.]+)\s+iters (\d+)", r.stdout)
+    assert len(rows) >= 4
+    for c, s, vs, it in rows:
+        c = int(c)
+        # state after the plant step of cycle c == golden input of cycle c + 1 (same closed loop, oracle side); filter ties
+        # make later cycles branch-dependent, so only the progress along the path is compared loosely there
+        assert abs(float(s) - g["x_in"][c + 1][7]) < (1e-4 if c == 0 else 5e-3), (c, s)

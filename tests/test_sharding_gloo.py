@@ -1,0 +1,61 @@
+"""CPU tier: the multi-GPU host logic (batch sharding + gather of results / counters) with world_size 2 and 3 on the
+gloo backend.  No data-path collective exists on this path: instances are independent."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from mpcc_manipulator_b200.sharding import shard_range, shard_sizes, gather_results, reduce_counters
+
+
+def test_shard_ranges_cover_batch():
+    for total in (1, 7, 64, 4096, 65536, 65537):
+        for world in (1, 2, 3, 4, 8):
+            blocks = [shard_range(total, r, world) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == total
+            for a, b in zip(blocks[:-1], blocks[1:]):
+                assert a[1] == b[0]
+            sizes = shard_sizes(total, world)
+            assert sum(sizes) == total and max(sizes) - min(sizes) <= 1
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _worker(rank, world, port, total, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = shard_range(total, rank, world)
+    idx = torch.arange(lo, hi)
+    u0 = (idx[:, None] * 10 + torch.arange(8)[None]).to(torch.float64)       # stands for the controls of this shard
+    status = (idx % 3).to(torch.int32); iters = (idx % 5 + 1).to(torch.int32)
+    gu, gs, gi = gather_results(u0, status, iters, total, dist)
+    solved, failed, mx = reduce_counters(int((status == 0).sum()), int((status != 0).sum()), int(iters.max()), dist)
+    if rank == 0:
+        out.put((gu.numpy(), gs.numpy(), gi.numpy(), solved, failed, mx))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,total", [(2, 64), (3, 50)])
+def test_gather_gloo(world, total):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, total, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    gu, gs, gi, solved, failed, mx = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    idx = np.arange(total)
+    assert np.array_equal(gu, idx[:, None] * 10.0 + np.arange(8)[None])
+    assert np.array_equal(gs, idx % 3) and np.array_equal(gi, idx % 5 + 1)
+    assert solved == int((idx % 3 == 0).sum()) and failed == total - solved and mx == 5
