@@ -258,7 +258,7 @@ def run_ours(args):
         """device-resident closed-loop step: cycle -> (gather) -> plant"""
         nonlocal x, xn
         mpc.run_cycle_device(x.data_ptr(), u.data_ptr())
-        launches["n"] += 4
+        launches["n"] += 5
         with torch.cuda.stream(stream):
             if world > 1:
                 # the path's only collective: gather the applied controls and per-instance status / iterations (NCCL)

@@ -151,6 +151,9 @@ int mpcc_cuda_solve_ocp(mpcc_cuda_handle* h, double* guess, const double* rb, co
  * seconds [B][4] = total, set_qp, solve_qp, get_alpha.  Filled by the warp-per-instance kernel. */
 int mpcc_cuda_read_compute_time(mpcc_cuda_handle* h, double* seconds);
 
+/* Per-instance QP counters of the last cycle: interior-point iterations summed over the cycle's QPs, failed QPs. */
+int mpcc_cuda_read_qp_counters(mpcc_cuda_handle* h, int32_t* qp_iters, int32_t* qp_fail);
+
 /* Line-search decisions of the last cycle, per instance: bit i = the filter accepted the first trial of SQP
  * iteration i (filterLineSearch, osqp_interface.cpp:759-808; i < 32).  Diagnostic used by the parity tests to
  * replay the oracle along the same branch when a decision hinges on solver noise. */

@@ -17,7 +17,7 @@ EXPORTS = [
     "mpcc_cuda_run_cycle_device", "mpcc_cuda_read_results", "mpcc_cuda_result_pointers", "mpcc_cuda_stream", "mpcc_cuda_synchronize",
     "mpcc_cuda_get_warm_state", "mpcc_cuda_set_warm_state", "mpcc_cuda_sim_time_step", "mpcc_cuda_eval_robot_data", "mpcc_cuda_eval_stage",
     "mpcc_cuda_eval_track", "mpcc_cuda_solve_ocp", "mpcc_cuda_get_stats", "mpcc_cuda_sim_time_step_device", "mpcc_cuda_set_profiling",
-    "mpcc_cuda_get_kernel_times", "mpcc_cuda_fp64_peak", "mpcc_cuda_read_decisions", "mpcc_cuda_read_compute_time",
+    "mpcc_cuda_get_kernel_times", "mpcc_cuda_fp64_peak", "mpcc_cuda_read_decisions", "mpcc_cuda_read_qp_counters", "mpcc_cuda_read_compute_time",
 ]
 
 
@@ -227,6 +227,11 @@ class BatchMPC:
         t = np.zeros((self.B, 4))
         _check(lib().mpcc_cuda_read_compute_time(self.h, _p(t)))
         return t
+
+    def qp_counters(self):
+        a = np.zeros(self.B, np.int32); b = np.zeros(self.B, np.int32)
+        _check(lib().mpcc_cuda_read_qp_counters(self.h, _p(a), _p(b)))
+        return a, b
 
     def decisions(self):
         m = np.zeros(self.B, np.int32)

@@ -28,6 +28,8 @@ struct CycleArgs {
     double* horizon;   // [B][S][17]
     int32_t* status; int32_t* iters; int32_t* ok; int32_t* qp_iters; int32_t* qp_fail; int32_t* accept_mask;
     long long* sqp_ns;  // per-instance duration of the SQP loop (ComputeTime::total analogue)
+    int32_t* hist;      // per-instance history of SQP iteration counts (4 cycles, one byte each): scheduling hint only
+    int32_t* order;     // launch order of the instances (longest expected first)
     QpOptions qp;
 };
 

@@ -4,13 +4,33 @@
 
 namespace mpcc {
 
+// Launch order: instances that took many SQP iterations in one of the last four cycles go first, so that the long
+// tail of the batch starts at time zero (longest-processing-time-first; affects scheduling only, never results).
+__global__ void k_order(const int32_t* __restrict__ hist, int32_t* __restrict__ order, int B) {
+    __shared__ int cnt[16], base[16];
+    if (threadIdx.x < 16) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    auto key = [&](int b) {
+        const unsigned h = (unsigned)hist[b];
+        unsigned m = h & 255u;
+        m = max(m, (h >> 8) & 255u); m = max(m, (h >> 16) & 255u); m = max(m, (h >> 24) & 255u);
+        return 15 - (int)min(m, 15u);  // bucket 0 = longest
+    };
+    for (int b = threadIdx.x; b < B; b += blockDim.x) atomicAdd(&cnt[key(b)], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) { int s = 0; for (int i = 0; i < 16; i++) { base[i] = s; s += cnt[i]; } }
+    __syncthreads();
+    for (int b = threadIdx.x; b < B; b += blockDim.x) order[atomicAdd(&base[key(b)], 1)] = b;
+}
+
 // SQP loop + epilogue, one WARP per instance (sqp_warp.cuh)
 constexpr int SQPW_WARPS = 2;  // warps (instances) per CTA
-__global__ void __launch_bounds__(SQPW_WARPS * 32, 6) k_sqp_warp(CycleArgs a, double* wws, size_t ws_per, size_t sm_per) {
+__global__ void __launch_bounds__(SQPW_WARPS * 32, 5) k_sqp_warp(CycleArgs a, double* wws, size_t ws_per, size_t sm_per) {
     extern __shared__ __align__(16) double sqpw_smem[];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.x * SQPW_WARPS + wid;
-    if (b >= a.B) return;  // whole warps leave together
+    const int slot = blockIdx.x * SQPW_WARPS + wid;
+    if (slot >= a.B) return;  // whole warps leave together
+    const int b = a.order[slot];
     const Params& P = a.params[a.params_per_instance ? b : 0];
     const TrackTable& T = a.tracks[a.track_id[b]];
     const size_t B = (size_t)a.B, NS = B * a.S;
@@ -44,11 +64,12 @@ __global__ void __launch_bounds__(SQPW_WARPS * 32, 6) k_sqp_warp(CycleArgs a, do
         a.flags[b] = fl;
         a.status[b] = r.status; a.iters[b] = r.iters; a.ok[b] = ok ? 1 : 0; a.qp_iters[b] = r.qp_iters; a.qp_fail[b] = r.qp_fail;
         a.accept_mask[b] = (int32_t)r.accept_mask;
+        a.hist[b] = (int32_t)(((unsigned)a.hist[b] << 8) | (unsigned)min(r.iters, 255));
         a.sqp_ns[4 * b] = t1 - t0; a.sqp_ns[4 * b + 1] = (long long)w.tm_set_qp; a.sqp_ns[4 * b + 2] = (long long)w.tm_solve_qp; a.sqp_ns[4 * b + 3] = (long long)w.tm_get_alpha;
     }
 }
 // solveOCP probe, one warp per instance: AoS guess / RobotData, optional iteration log
-__global__ void __launch_bounds__(SQPW_WARPS * 32, 6) k_solve_ocp_warp(CycleArgs a, double* wws, size_t ws_per, size_t sm_per, double* guess, const double* rb,
+__global__ void __launch_bounds__(SQPW_WARPS * 32, 5) k_solve_ocp_warp(CycleArgs a, double* wws, size_t ws_per, size_t sm_per, double* guess, const double* rb,
                                                                     const double* cur_u_all, int n, double* steps, double* alphas, int32_t* qp_ok, int max_log, int32_t* n_logged) {
     extern __shared__ __align__(16) double sqpw_smem[];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -78,6 +99,7 @@ cudaError_t configure_sqp_warp(int N) {
     return cudaFuncSetAttribute(k_solve_ocp_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sqp_warp_smem_bytes(N));
 }
 void launch_sqp_warp(const CycleArgs& a, double* wws, cudaStream_t s) {
+    k_order<<<1, 1024, 0, s>>>(a.hist, a.order, a.B);
     k_sqp_warp<<<(a.B + SQPW_WARPS - 1) / SQPW_WARPS, SQPW_WARPS * 32, sqp_warp_smem_bytes(a.N), s>>>(a, wws, warp_ws_doubles(a.N), warp_smem_doubles(a.N));
 }
 void launch_solve_ocp_warp(const CycleArgs& a, double* wws, double* guess, const double* rb, const double* cur_u, int n, double* steps, double* alphas,

@@ -166,6 +166,7 @@ struct mpcc_cuda_handle {
     double *d_u_out = nullptr, *d_horizon = nullptr;
     int32_t *d_status = nullptr, *d_iters = nullptr, *d_ok = nullptr, *d_qp_iters = nullptr, *d_qp_fail = nullptr, *d_accept = nullptr;
     long long* d_sqp_ns = nullptr;
+    int32_t *d_hist = nullptr, *d_order = nullptr;
     double* d_wws = nullptr; size_t wws_per = 0, wsm_per = 0;  // warp-kernel workspace (doubles per instance / per warp)
     double *d_wpack = nullptr, *d_bias = nullptr, *d_w_out_env = nullptr, *d_w_out_self = nullptr;
     int64_t launches = 0;
@@ -190,7 +191,7 @@ static CycleArgs make_args(mpcc_cuda_handle* h, double* d_x0, const double* d_u0
     a.x0 = d_x0; a.u0 = d_u0; a.obs = d_obs;
     a.warm = h->d_warm; a.step = h->d_step; a.trial = h->d_trial; a.filt = h->d_filt; a.ws = h->d_ws; a.flags = h->d_flags;
     a.qs = h->d_qs; a.rb = h->d_rb; a.u_out = h->d_u_out; a.horizon = h->d_horizon;
-    a.status = h->d_status; a.iters = h->d_iters; a.ok = h->d_ok; a.qp_iters = h->d_qp_iters; a.qp_fail = h->d_qp_fail; a.accept_mask = h->d_accept; a.sqp_ns = h->d_sqp_ns;
+    a.status = h->d_status; a.iters = h->d_iters; a.ok = h->d_ok; a.qp_iters = h->d_qp_iters; a.qp_fail = h->d_qp_fail; a.accept_mask = h->d_accept; a.sqp_ns = h->d_sqp_ns; a.hist = h->d_hist; a.order = h->d_order;
     a.qp = QpOptions{h->cfg.qp_max_iter, h->cfg.qp_eps};
     return a;
 }
@@ -254,7 +255,7 @@ int mpcc_cuda_create(const mpcc_cuda_config* cfg, mpcc_cuda_handle** out) {
     A(h->alloc(&h->d_qs, h->NS * DOF)); A(h->alloc(&h->d_rb, h->NS * RB_DOUBLES));
     A(h->alloc(&h->d_flags, B));
     A(h->alloc(&h->d_u_out, B * NU)); A(h->alloc(&h->d_horizon, B * HN));
-    A(h->alloc(&h->d_status, B)); A(h->alloc(&h->d_iters, B)); A(h->alloc(&h->d_ok, B)); A(h->alloc(&h->d_qp_iters, B)); A(h->alloc(&h->d_qp_fail, B)); A(h->alloc(&h->d_accept, B)); A(h->alloc(&h->d_sqp_ns, 4 * B));
+    A(h->alloc(&h->d_status, B)); A(h->alloc(&h->d_iters, B)); A(h->alloc(&h->d_ok, B)); A(h->alloc(&h->d_qp_iters, B)); A(h->alloc(&h->d_qp_fail, B)); A(h->alloc(&h->d_accept, B)); A(h->alloc(&h->d_sqp_ns, 4 * B)); A(h->alloc(&h->d_hist, B)); A(h->alloc(&h->d_order, B));
     A(h->alloc(&h->d_wpack, (size_t)MLP_NCHUNK * MLP_CHUNK_D)); A(h->alloc(&h->d_bias, MLP_BIAS_TOTAL));
     A(h->alloc(&h->d_w_out_env, 9 * 256)); A(h->alloc(&h->d_w_out_self, 64));
     if (ae != cudaSuccess) { mpcc_cuda_destroy(h); return fail(MPCC_ERR_CUDA, std::string("device allocation failed: ") + cudaGetErrorString(ae)); }
@@ -447,7 +448,7 @@ int mpcc_cuda_run_cycle_device(mpcc_cuda_handle* h, double* d_x0, const double* 
     if (rc) return rc;
     if (prof) cudaEventRecord(h->ev[3], h->stream);
     if (h->cfg.sqp_kernel == 1) launch_sqp_thread(a, h->stream);
-    else launch_sqp_warp(a, h->d_wws, h->stream);
+    else { launch_sqp_warp(a, h->d_wws, h->stream); h->launches++; }  // + the launch-order kernel
     h->launches++;
     if (prof) cudaEventRecord(h->ev[4], h->stream);
     CK(cudaGetLastError());
@@ -737,6 +738,15 @@ int mpcc_cuda_read_compute_time(mpcc_cuda_handle* h, double* seconds) {
     CK(cudaMemcpyAsync(ns.data(), h->d_sqp_ns, ns.size() * 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     for (size_t i = 0; i < ns.size(); i++) seconds[i] = 1e-9 * (double)ns[i];
+    return MPCC_OK;
+}
+
+int mpcc_cuda_read_qp_counters(mpcc_cuda_handle* h, int32_t* qp_iters, int32_t* qp_fail) {
+    if (!h || !qp_iters || !qp_fail) return fail(MPCC_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaMemcpyAsync(qp_iters, h->d_qp_iters, (size_t)h->B * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(qp_fail, h->d_qp_fail, (size_t)h->B * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
     return MPCC_OK;
 }
 

@@ -83,14 +83,39 @@ struct Warp {
 #define MPCC_RSQRT(x) (1.0 / sqrt(x))
 #endif
 
+// 8-byte asynchronous global -> shared copy (LDGSTS): the data does not pass through registers, so a lane can keep
+// many copies in flight; groups complete in commit order.  Host build: plain copies.
+MPCC_HD void async_copy8(double* smem_dst, const double* gsrc) {
+#if defined(__CUDA_ARCH__)
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
+#else
+    *smem_dst = *gsrc;
+#endif
+}
+MPCC_HD void async_commit() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+#endif
+}
+template <int PENDING>
+MPCC_HD void async_wait() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(PENDING) : "memory");
+#endif
+}
+
 // ---- layouts -------------------------------------------------------------------------------------------------
 // per-stage QP record written by the linearisation (polytopic rows live in the cycle-constant record)
 constexpr int WL_Q = 0, WL_q = 81, WL_RD = 90, WL_r = 98, WL_b = 106, WL_XLO = 115, WL_XHI = 124, WL_DLO = 133, WL_DHI = 140, WL_PRHS = 147, WL_SIZE = 158;
 constexpr int WC_SIZE = NPOLY * 14;   // cycle constants per stage: 11 normalised polytopic rows [ax(7) | au(7)]
 constexpr int WF_X = 0, WF_LAM = 64, WF_SIZE = 192;  // factor record: L^-1 (8 x 8, lower), Lam (8 x 16)
 // shared-memory scratch of one warp (doubles)
-constexpr int SC_P = 0, SC_PM = 256, SC_MNN = 512, SC_MNX = 576, SC_X = 704, SC_LAM = 768, SC_U = 896, SC_GS = 1092, SC_WP = 1246, SC_FF = 1258,
-              SC_VEC = 1330, SC_TXU = 1426, SC_RED = 1444, SC_SIZE = 1508;
+constexpr int SC_P = 0, SC_PM = 256, SC_MNN = 512, SC_MNX = 576, SC_X = 704, SC_LAM = 768, SC_U = 896, SC_STG = 1092, SC_FF = 1668,
+              SC_VEC = 1740, SC_TXU = 1836, SC_RED = 1854, SC_SIZE = 1918;
+// staged inputs of one stage of the factorisation (two slots, filled by asynchronous copies one stage ahead):
+// polytopic rows, their barrier weights, Q, Rd, box / rate barrier weights
+constexpr int SG_GS = 0, SG_WP = 154, SG_Q = 166, SG_RD = 247, SG_WB = 255, SG_WR = 273, SG_SIZE = 288;
 constexpr int V_P = 0, V_MN = 16, V_MX = 24, V_KAP = 40, V_D0 = 48, V_D1 = 64, V_RHS = 80, V_DN = 88;  // inside SC_VEC (96)
 constexpr int MAX_SQP_FILTER = 128;
 
@@ -98,7 +123,11 @@ MPCC_HD size_t warp_ws_doubles(int N) {
     const size_t S = N + 1;
     return S * (WL_SIZE + WC_SIZE + 7 * NINEQ + HZ /*G*/ + 8 /*KAP*/ + WF_SIZE + 2 * HZ /*persistent step, iterate*/) + 2 * (MAX_SQP_FILTER + 2);
 }
-MPCC_HD size_t warp_smem_doubles(int N) { return (size_t)2 * (N + 1) * HZ + SC_SIZE; }
+// the sweeps keep the gradient (17 S) and kappa (8 S) in the scratch below SC_VEC behind a 4-slot factor ring; longer
+// horizons get a separate block appended after the scratch
+constexpr int SW_RING = 4, SW_GK = SW_RING * WF_SIZE;
+MPCC_HD size_t warp_smem_extra(int N) { return (25 * (N + 1) <= SC_VEC - SW_GK) ? 0 : (size_t)25 * (N + 1); }
+MPCC_HD size_t warp_smem_doubles(int N) { return (size_t)2 * (N + 1) * HZ + SC_SIZE + warp_smem_extra(N); }
 
 // isPosdef / isNan of one packed-lower 9 x 9 Hessian block, fully unrolled (static indices: registers).
 // pd is cleared at the first non-positive pivot unless that pivot is NaN (NaN is reported through `nan`).
@@ -197,6 +226,40 @@ struct WarpSqp {
         for (int i = lane; i < NPOLY * N; i += 32) { const int k = i / NPOLY, j = i - k * NPOLY; f(OP_ + i, gz_poly(Z, k, j), need_h ? h_poly(k, j) : 0.0); }
     }
 
+    // Same traversal, four rounds at a time: f4(idx[4], gz[4], h[4]) gets four items of one lane (idx < 0: none) so that it
+    // can issue all of its loads before the first dependent use (memory-level parallelism inside a lane).
+    template <class F4>
+    MPCC_HD void for_present4(int lane, const double* Z, bool need_h, F4 f4) const {
+        int idx[4]; double g[4], h[4];
+        for (int base = 18 + lane; base < 18 * S; base += 128) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = base + 32 * u;
+                idx[u] = (i < 18 * S) ? i : -1; g[u] = 0; h[u] = 0;
+                if (i < 18 * S) { const int k = i / 18, c = i - k * 18; g[u] = gz_box(Z, k, c); if (need_h) h[u] = h_box(k, c); }
+            }
+            f4(idx, g, h);
+        }
+        for (int base = lane; base < 14 * N; base += 128) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = base + 32 * u;
+                idx[u] = (i < 14 * N) ? OR_ + i : -1; g[u] = 0; h[u] = 0;
+                if (i < 14 * N) { const int k = i / 14, c = i - k * 14; g[u] = gz_rate(Z, k, c); if (need_h) h[u] = h_rate(k, c); }
+            }
+            f4(idx, g, h);
+        }
+        for (int base = lane; base < NPOLY * N; base += 128) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = base + 32 * u;
+                idx[u] = (i < NPOLY * N) ? OP_ + i : -1; g[u] = 0; h[u] = 0;
+                if (i < NPOLY * N) { const int k = i / NPOLY, j = i - k * NPOLY; g[u] = gz_poly(Z, k, j); if (need_h) h[u] = h_poly(k, j); }
+            }
+            f4(idx, g, h);
+        }
+    }
+
     // ---- gradient of the step QP: G <- H z + f + G'(IV); dst0 (shared) <- same with multipliers ILAM ----
     MPCC_HD void gradient(double* dst0) const {
         W.each([&](int lane) {
@@ -251,6 +314,24 @@ struct WarpSqp {
         });
     }
 
+    // asynchronous fetch of the factorisation inputs of stage k into slot k & 1
+    MPCC_HD void issue_stage_copy(int lane, int k, double* SG) const {
+        if (k >= 0) {
+            double* dst = SG + (k & 1) * SG_SIZE;
+            for (int e = lane; e < SG_SIZE; e += 32) {
+                const double* src;
+                if (e < SG_WP) src = CST + (size_t)k * WC_SIZE + e;
+                else if (e < SG_Q) src = (e - SG_WP < NPOLY) ? IW + OP_ + k * NPOLY + (e - SG_WP) : nullptr;
+                else if (e < SG_RD) src = LIN + (size_t)k * WL_SIZE + WL_Q + (e - SG_Q);
+                else if (e < SG_WB) src = LIN + (size_t)k * WL_SIZE + WL_RD + (e - SG_RD);
+                else if (e < SG_WR) src = IW + k * 18 + (e - SG_WB);
+                else src = (e - SG_WR < 14) ? IW + OR_ + k * 14 + (e - SG_WR) : nullptr;
+                if (src) async_copy8(dst + e, src);
+            }
+        }
+        async_commit();
+    }
+
     // ---- Riccati factorisation; false if some M_nunu is not positive definite ----
     MPCC_HD bool factor() const {
         double* Pc = SC + SC_P;      // 16 x 16 cost-to-go of stage k+1 (rows/cols 0..8 xi, 9..15 previous dq step)
@@ -262,8 +343,7 @@ struct WarpSqp {
         double* U = SC + SC_U;       // 14 x 14 polytopic barrier Hessian  sum_p w_p g_p g_p'
         double* Lc = SC + SC_U;      // Cholesky factor (U is dead by then)
         double* INV = SC + SC_U + 64;
-        double* GS = SC + SC_GS;
-        double* WP = SC + SC_WP;
+        double* SG = SC + SC_STG;
         double* FF = SC + SC_FF;
         // terminal stage: P_N = Q_N + box W
         W.each([&](int lane) {
@@ -277,18 +357,21 @@ struct WarpSqp {
                 }
                 Pc[e] = v;
             }
+            issue_stage_copy(lane, N - 1, SG);
+            async_wait<0>();
         });
         bool ok = true;
         for (int k = N - 1; k >= 0; k--) {
-            const double* L = LIN + (size_t)k * WL_SIZE;
-            const double* wB = IW + k * 18;
-            const double* wR = IW + OR_ + k * 14;
-            const double* wP = IW + OP_ + k * NPOLY;
-            // F1: stage the polytopic rows and their barrier weights, FF = B'Pxx + E'Pwx (8 x 9)
+            const double* SGk = SG + (k & 1) * SG_SIZE;
+            const double* GS = SGk + SG_GS;
+            const double* WP = SGk + SG_WP;
+            const double* Qs = SGk + SG_Q;
+            const double* RDs = SGk + SG_RD;
+            const double* wB = SGk + SG_WB;
+            const double* wR = SGk + SG_WR;
+            // F1: start fetching the next stage's inputs; FF = B'Pxx + E'Pwx (8 x 9)
             W.each([&](int lane) {
-                const double* row = CST + (size_t)k * WC_SIZE;
-                for (int e = lane; e < WC_SIZE; e += 32) GS[e] = row[e];
-                if (lane < NPOLY) WP[lane] = wP[lane];
+                issue_stage_copy(lane, k - 1, SG);
                 for (int e = lane; e < 72; e += 32) {
                     const int i = e / 9, c = e - i * 9;
                     FF[e] = (i < 7) ? dyn.bq[i] * Pc[i * 16 + c] + Pc[(9 + i) * 16 + c] : dyn.bs * Pc[7 * 16 + c] + dyn.bv * Pc[8 * 16 + c];
@@ -322,7 +405,7 @@ struct WarpSqp {
                     } else {
                         v = dyn.bs * FF[i * 9 + 7] + dyn.bv * FF[i * 9 + 8];
                     }
-                    if (i == j) { v += L[WL_RD + j]; if (j < 7) v += wR[j] + wR[7 + j]; }
+                    if (i == j) { v += RDs[j]; if (j < 7) v += wR[j] + wR[7 + j]; }
                     Mnn[e] = v;
                 }
                 for (int e = lane; e < 128; e += 32) {
@@ -344,7 +427,7 @@ struct WarpSqp {
                         v = Pc[e];
                         if (c == 8) v += dyn.asv * Pc[r * 16 + 7];
                         if (r == 8) v += dyn.asv * (Pc[7 * 16 + c] + ((c == 8) ? dyn.asv * Pc[7 * 16 + 7] : 0.0));
-                        v += L[WL_Q + r * 9 + c];
+                        v += Qs[r * 9 + c];
                         if (r == c && k >= 1) v += wB[r] + wB[9 + r];
                         if (r < 7 && c < 7) v += U[r * 14 + c];
                     } else if (r == c && r >= 9 && k >= 1) {
@@ -402,127 +485,133 @@ struct WarpSqp {
                 for (int a = 0; a < 4; a++) { Pc[(r0 + a) * 16 + c0] = acc[a][0]; Pc[(r0 + a) * 16 + c0 + 1] = acc[a][1]; }
                 double* F = FACT + (size_t)k * WF_SIZE;
                 for (int e = lane; e < WF_SIZE; e += 32) F[e] = X[e];  // X and Lam are contiguous in the scratch
+                async_wait<0>();  // the next stage's inputs have landed
             });
         }
         return ok;
     }
 
-    // ---- Riccati vector sweeps: Newton step for the gradient in G -> STEP (shared), KAP (global) ----
+    // ---- Riccati vector sweeps: Newton step for the gradient in G -> STEP (shared) ----
+    // The factor records stream through a 4-slot shared-memory ring filled by asynchronous copies three stages ahead;
+    // the gradient is pulled into shared memory in one burst and kappa never leaves it.
+    MPCC_HD void issue_factor_copy(int lane, int k, double* ring) const {
+        if (k >= 0 && k < N) {
+            const double* F = FACT + (size_t)k * WF_SIZE;
+            double* dst = ring + (k & (SW_RING - 1)) * WF_SIZE;
+#pragma unroll
+            for (int t = 0; t < WF_SIZE / 32; t++) async_copy8(dst + lane + 32 * t, F + lane + 32 * t);
+        }
+        async_commit();
+    }
     MPCC_HD void solve_step() const {
-        double* FS[2] = {SC + SC_P, SC + SC_PM};  // staged factor records, double buffered (the P blocks are dead here)
+        double* ring = SC;                    // the factorisation's blocks are dead during the sweeps
+        const int gk_room = SC_VEC - SW_GK;   // doubles available behind the ring
+        double* GS_ = (25 * S <= gk_room) ? SC + SW_GK : SC + SC_SIZE;  // gradient copy [S][17]
+        double* KS = GS_ + S * HZ;                                      // kappa [S][8]
         double* V = SC + SC_VEC;
         W.each([&](int lane) {
-            if (lane < 16) V[V_P + lane] = (lane < 9) ? G[(size_t)N * HZ + lane] : 0.0;
-            const double* F = FACT + (size_t)(N - 1) * WF_SIZE;
-            double* dst = FS[(N - 1) & 1];
-            for (int e = lane; e < WF_SIZE; e += 32) dst[e] = F[e];
+            issue_factor_copy(lane, N - 1, ring);
+            issue_factor_copy(lane, N - 2, ring);
+            issue_factor_copy(lane, N - 3, ring);
+            for (int e = lane; e < S * HZ; e += 32) async_copy8(GS_ + e, G + e);
+            async_commit();
+            if (lane < 16) V[V_D0 + lane] = 0.0;
+            async_wait<0>();
         });
+        W.each([&](int lane) { if (lane < NX) V[V_D0 + lane] = GS_[N * HZ + lane]; });  // p_N
+        // backward: kappa = L^-1 mn,  p_k = mx - Lam' kappa
         for (int k = N - 1; k >= 0; k--) {
-            const double* Fs = FS[k & 1];
+            const double* Fs = ring + (k & (SW_RING - 1)) * WF_SIZE;
+            const double* g = GS_ + k * HZ;
+            const double* p = V + (((N - 1 - k) & 1) ? V_D1 : V_D0);
+            double* pn = V + (((N - 1 - k) & 1) ? V_D0 : V_D1);
             W.each([&](int lane) {
-                double pre[6];
-                if (k > 0) {
-                    const double* F = FACT + (size_t)(k - 1) * WF_SIZE;
+                issue_factor_copy(lane, k - 3, ring);  // its slot held stage k+1, which is finished
+                if (lane < 8) {
+                    double kp = 0;
 #pragma unroll
-                    for (int t = 0; t < 6; t++) pre[t] = F[lane + 32 * t];
+                    for (int t = 0; t < 8; t++) {
+                        const double mn = (t < 7) ? g[NX + t] + dyn.bq[t] * p[t] + p[9 + t] : g[NX + 7] + dyn.bs * p[7] + dyn.bv * p[8];
+                        kp += Fs[WF_X + lane * 8 + t] * mn;  // X: lower triangular with explicit zeros
+                    }
+                    KS[k * 8 + lane] = kp;
                 }
-                const double* g = G + (size_t)k * HZ;
-                const double* p = V + V_P;
-                if (lane < 8) V[V_MN + lane] = (lane < 7) ? g[NX + lane] + dyn.bq[lane] * p[lane] + p[9 + lane] : g[NX + 7] + dyn.bs * p[7] + dyn.bv * p[8];
+            });
+            W.each([&](int lane) {
                 if (lane < 16) {
                     double mx = 0;
                     if (lane < 9) { mx = g[lane] + p[lane]; if (lane == 8) mx += dyn.asv * p[7]; }
-                    V[V_MX + lane] = mx;
-                }
-                if (k > 0) {
-                    double* dst = FS[(k - 1) & 1];
 #pragma unroll
-                    for (int t = 0; t < 6; t++) dst[lane + 32 * t] = pre[t];
+                    for (int t = 0; t < 8; t++) mx -= Fs[WF_LAM + 16 * t + lane] * KS[k * 8 + t];
+                    pn[lane] = mx;
                 }
-            });
-            W.each([&](int lane) {
-                if (lane < 8) {
-                    double s = 0;
-#pragma unroll
-                    for (int t = 0; t < 8; t++) s += Fs[WF_X + lane * 8 + t] * V[V_MN + t];  // X is lower triangular with explicit zeros
-                    V[V_KAP + lane] = s;
-                    KAP[(size_t)k * 8 + lane] = s;
-                }
-            });
-            W.each([&](int lane) {
-                if (lane < 16) {
-                    double mx = V[V_MX + lane];
-#pragma unroll
-                    for (int t = 0; t < 8; t++) mx -= Fs[WF_LAM + 16 * t + lane] * V[V_KAP + t];
-                    V[V_P + lane] = mx;
-                }
+                async_wait<2>();  // pending: stages k-1, k-2, k-3 -> k-1 has landed
             });
         }
         // forward
         W.each([&](int lane) {
-            if (lane < 16) V[V_D0 + lane] = 0.0;
+            issue_factor_copy(lane, 0, ring);
+            issue_factor_copy(lane, 1, ring);
+            issue_factor_copy(lane, 2, ring);
+            if (lane < 16) { V[V_D0 + lane] = 0.0; V[V_D1 + lane] = 0.0; }
             if (lane < NX) STEP[lane] = 0.0;
-            const double* F = FACT;
-            double* dst = FS[0];
-            for (int e = lane; e < WF_SIZE; e += 32) dst[e] = F[e];
+            async_wait<2>();
         });
         for (int k = 0; k < N; k++) {
-            const double* Fs = FS[k & 1];
+            const double* Fs = ring + (k & (SW_RING - 1)) * WF_SIZE;
             const double* d = V + ((k & 1) ? V_D1 : V_D0);
             double* dn_ = V + ((k & 1) ? V_D0 : V_D1);
             W.each([&](int lane) {
-                double pre[6];
-                if (k + 1 < N) {
-                    const double* F = FACT + (size_t)(k + 1) * WF_SIZE;
-#pragma unroll
-                    for (int t = 0; t < 6; t++) pre[t] = F[lane + 32 * t];
-                }
+                if (k + 3 < N) issue_factor_copy(lane, k + 3, ring); else async_commit();
                 if (lane < 8) {
-                    double s = KAP[(size_t)k * 8 + lane];
+                    double s = KS[k * 8 + lane];
 #pragma unroll
                     for (int c = 0; c < 16; c++) s += Fs[WF_LAM + 16 * lane + c] * d[c];
                     V[V_RHS + lane] = -s;
                 }
-                if (k + 1 < N) {
-                    double* dst = FS[(k + 1) & 1];
-#pragma unroll
-                    for (int t = 0; t < 6; t++) dst[lane + 32 * t] = pre[t];
-                }
-            });
-            W.each([&](int lane) {
-                if (lane < 8) {
-                    double s = 0;
-#pragma unroll
-                    for (int t = 0; t < 8; t++) s += Fs[WF_X + t * 8 + lane] * V[V_RHS + t];
-                    V[V_DN + lane] = s;
-                    STEP[k * HZ + NX + lane] = s;
-                }
             });
             W.each([&](int lane) {
                 if (lane < 16) {
+                    const int i = (lane < 8) ? lane : ((lane == 8) ? 7 : lane - 9);  // the entry of dn = L^-T rhs this lane needs
+                    double dni = 0;
+#pragma unroll
+                    for (int t = 0; t < 8; t++) dni += Fs[WF_X + t * 8 + i] * V[V_RHS + t];
                     double nx;
-                    if (lane < 7) nx = d[lane] + dyn.bq[lane] * V[V_DN + lane];
-                    else if (lane == 7) nx = d[7] + dyn.asv * d[8] + dyn.bs * V[V_DN + 7];
-                    else if (lane == 8) nx = d[8] + dyn.bv * V[V_DN + 7];
-                    else nx = V[V_DN + lane - 9];
+                    if (lane < 7) nx = d[lane] + dyn.bq[lane] * dni;
+                    else if (lane == 7) nx = d[7] + dyn.asv * d[8] + dyn.bs * dni;
+                    else if (lane == 8) nx = d[8] + dyn.bv * dni;
+                    else nx = dni;
                     dn_[lane] = nx;
                     if (lane < NX) STEP[(k + 1) * HZ + lane] = nx;
+                    if (lane < 8) STEP[k * HZ + NX + lane] = dni;
                 }
+                async_wait<2>();
             });
         }
-        W.each([&](int lane) { if (lane < NU) STEP[N * HZ + NX + lane] = 0.0; });
+        W.each([&](int lane) { if (lane < NU) STEP[N * HZ + NX + lane] = 0.0; async_wait<0>(); });
     }
 
     // slack / multiplier steps from the primal step; largest step keeping t, lam > 0
     MPCC_HD double ineq_steps() const {
+        // the per-constraint vectors are disjoint arrays: loads may run ahead of the stores
+        const double* __restrict__ rp_ = IRP; const double* __restrict__ lam_ = ILAM; const double* __restrict__ v_ = IV;
+        const double* __restrict__ w_ = IW; const double* __restrict__ t_ = IT;
+        double* __restrict__ dt_ = IDT; double* __restrict__ dl_ = IDLAM;
         return W.rmin([&](int lane) {
             double a = 1.0;
-            for_present(lane, STEP, false, [&](int i, double g, double) {
-                const double dt = -IRP[i] - g;
-                const double dl = -ILAM[i] + IV[i] + IW[i] * g;
-                IDT[i] = dt; IDLAM[i] = dl;
-                if (dt < 0) a = fmin(a, -IT[i] / dt);
-                if (dl < 0) a = fmin(a, -ILAM[i] / dl);
+            for_present4(lane, STEP, false, [&](const int* idx, const double* g, const double*) {
+                double rp[4], lam[4], v[4], w[4], t[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) if (idx[u] >= 0) { const int i = idx[u]; rp[u] = rp_[i]; lam[u] = lam_[i]; v[u] = v_[i]; w[u] = w_[i]; t[u] = t_[i]; }
+#pragma unroll
+                for (int u = 0; u < 4; u++) if (idx[u] >= 0) {
+                    const int i = idx[u];
+                    const double dt = -rp[u] - g[u];
+                    const double dl = -lam[u] + v[u] + w[u] * g[u];
+                    dt_[i] = dt; dl_[i] = dl;
+                    if (dt < 0) a = fmin(a, -t[u] / dt);
+                    if (dl < 0) a = fmin(a, -lam[u] / dl);
+                }
             });
             return a;
         });
@@ -573,17 +662,25 @@ struct WarpSqp {
         const double m_tot = 43.0 * N;
         for (int it = 0; it < opt.max_iter; it++) {
             // residuals, barrier weights, predictor v = lam rp / t
+            const double* __restrict__ t_ = IT; const double* __restrict__ lam_ = ILAM;
+            double* __restrict__ rp_ = IRP; double* __restrict__ w_ = IW; double* __restrict__ v_ = IV;
             const double nrp = W.rmax([&](int lane) {
                 double nr = 0, mu_p = 0;
-                for_present(lane, VAR, true, [&](int i, double g, double h) {
-                    const double t = IT[i], lam = ILAM[i];
-                    const double rp = g + t - h;
-                    IRP[i] = rp;
-                    nr = fmax(nr, fabs(rp));
-                    mu_p += t * lam;
-                    const double w = lam / t;
-                    IW[i] = w;
-                    IV[i] = w * rp;
+                for_present4(lane, VAR, true, [&](const int* idx, const double* g, const double* h) {
+                    double t[4], lam[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) if (idx[u] >= 0) { t[u] = t_[idx[u]]; lam[u] = lam_[idx[u]]; }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) if (idx[u] >= 0) {
+                        const int i = idx[u];
+                        const double rp = g[u] + t[u] - h[u];
+                        rp_[i] = rp;
+                        nr = fmax(nr, fabs(rp));
+                        mu_p += t[u] * lam[u];
+                        const double w = lam[u] / t[u];
+                        w_[i] = w;
+                        v_[i] = w * rp;
+                    }
                 });
                 RED[lane] = mu_p;
                 return nr;
@@ -622,16 +719,23 @@ struct WarpSqp {
             // corrector: v = (lam rp + sigma mu - dt_a dlam_a) / t
             W.each([&](int lane) {
                 const double sm = sigma * mu;
-                for (int i = 18 + lane; i < 18 * S; i += 32) IV[i] = (ILAM[i] * IRP[i] + sm - IDT[i] * IDLAM[i]) / IT[i];
-                for (int i = OR_ + lane; i < OR_ + 14 * N; i += 32) IV[i] = (ILAM[i] * IRP[i] + sm - IDT[i] * IDLAM[i]) / IT[i];
-                for (int i = OP_ + lane; i < OP_ + NPOLY * N; i += 32) IV[i] = (ILAM[i] * IRP[i] + sm - IDT[i] * IDLAM[i]) / IT[i];
+                const double* __restrict__ cl = ILAM; const double* __restrict__ crp = IRP; const double* __restrict__ cdt = IDT;
+                const double* __restrict__ cdl = IDLAM; const double* __restrict__ ct = IT; double* __restrict__ cv = IV;
+#pragma unroll 4
+                for (int i = 18 + lane; i < 18 * S; i += 32) cv[i] = (cl[i] * crp[i] + sm - cdt[i] * cdl[i]) / ct[i];
+#pragma unroll 4
+                for (int i = OR_ + lane; i < OR_ + 14 * N; i += 32) cv[i] = (cl[i] * crp[i] + sm - cdt[i] * cdl[i]) / ct[i];
+#pragma unroll 4
+                for (int i = OP_ + lane; i < OP_ + NPOLY * N; i += 32) cv[i] = (cl[i] * crp[i] + sm - cdt[i] * cdl[i]) / ct[i];
             });
             gradient(nullptr);
             solve_step();
             const double a = fmin(1.0, 0.995 * ineq_steps());
             W.each([&](int lane) {
                 for (int o = lane; o < S * HZ; o += 32) VAR[o] += a * STEP[o];
-                for (int i = lane; i < tot; i += 32) { IT[i] += a * IDT[i]; ILAM[i] += a * IDLAM[i]; }  // absent: dt = dl = 0
+                double* __restrict__ ut = IT; double* __restrict__ ul = ILAM; const double* __restrict__ udt = IDT; const double* __restrict__ udl = IDLAM;
+#pragma unroll 4
+                for (int i = lane; i < tot; i += 32) { ut[i] += a * udt[i]; ul[i] += a * udl[i]; }  // absent: dt = dl = 0
             });
             st.iters = it + 1;
         }
@@ -667,21 +771,26 @@ struct WarpSqp {
     //      else only the objective and the l1 constraint violation ----
     template <bool FULL>
     MPCC_HD void eval_horizon(const double* cur_u, const double* rb, size_t rb_stride, size_t rb_stage, double alpha, bool write_cst, double& obj, double& gap,
-                              bool* notpd, bool* nan) const {
+                              bool* notpd, bool* nan, bool write_lin = true) const {
         double* RED = SC + SC_RED;
+        double* XT = VAR;  // the evaluation point, gathered once into shared memory (VAR is free outside the QP solve)
+        W.each([&](int lane) {
+            for (int e = lane; e < S * HZ; e += 32) {
+                const int kk = e / HZ, r = e - kk * HZ;
+                double v = GUESS[e];
+                if (alpha != 0.0) {
+                    if (r < NX) v += alpha * (Tx(r) * SSTEP[e]);
+                    else v = (kk < N) ? v + alpha * (Tu(r - NX) * SSTEP[e]) : 0.0;
+                }
+                XT[e] = v;
+            }
+        });
         obj = W.rsum([&](int lane) {
             double o_acc = 0, g_acc = 0;
             bool pd_l = true, nan_l = false;
             for (int k = lane; k <= N; k += 32) {
                 double x[NX], u[NU], up[DOF], un[DOF], xn[NX];
-                auto gx = [&](int kk, int e) -> double {
-                    double v = GUESS[kk * HZ + e];
-                    if (alpha != 0.0) {
-                        if (e < NX) v += alpha * (Tx(e) * SSTEP[kk * HZ + e]);
-                        else v = (kk < N) ? v + alpha * (Tu(e - NX) * SSTEP[kk * HZ + e]) : 0.0;
-                    }
-                    return v;
-                };
+                auto gx = [&](int kk, int e) -> double { return XT[kk * HZ + e]; };
                 for (int e = 0; e < NX; e++) x[e] = gx(k, e);
                 for (int e = 0; e < NU; e++) u[e] = gx(k, NX + e);
                 for (int j = 0; j < DOF; j++) {
@@ -690,12 +799,21 @@ struct WarpSqp {
                 }
                 for (int e = 0; e < NX; e++) xn[e] = (k < N) ? gx(k + 1, e) : 0.0;
                 StageLin sl;
-                RbView rv{rb + (size_t)k * rb_stage, rb_stride};
+                // pull this stage's RobotData record in one burst (independent loads in flight together) instead of
+                // one dependent global load at a time inside stage_eval
+                double rbl[RB_DOUBLES];
+                {
+                    const double* src = rb + (size_t)k * rb_stage;
+#pragma unroll 10
+                    for (int e = 0; e < RB_DOUBLES; e++) rbl[e] = src[(size_t)e * rb_stride];
+                }
+                RbView rv{rbl, 1};
                 stage_eval<FULL>(P, T, Ts, N, k, x, u, up, un, xn, rv, sl);
                 o_acc += sl.obj; g_acc += sl.gap;
                 if (FULL) {
                     block9_pd_nan(sl.Q, pd_l, nan_l);
                     if (k < N) for (int j = 0; j < NU; j++) if (sl.Rd[j] != sl.Rd[j]) nan_l = true;
+                    if (!write_lin) continue;
                     double* L = LIN + (size_t)k * WL_SIZE;
                     for (int r = 0; r < 9; r++) for (int c = 0; c < 9; c++) L[WL_Q + r * 9 + c] = sl.Q[(r >= c) ? sym9(r, c) : sym9(c, r)];
                     for (int m = 0; m < NX; m++) { L[WL_q + m] = sl.q[m]; L[WL_b + m] = sl.b[m]; L[WL_XLO + m] = sl.xlo[m]; L[WL_XHI + m] = sl.xhi[m]; }
@@ -738,6 +856,27 @@ struct WarpSqp {
         }
     }
 
+    // Will the QP of the linearisation at GUESS fail solve()'s stage-0 test (xi_0 = 0 outside its box)?  The box of stage 0
+    // depends on the iterate only (state bounds, s trust region, the mis-indexed input-bound rows landing on stage 0):
+    // same expressions as stage_eval + the quirk pass, evaluated before linearising so that a QP known to fail is not assembled.
+    MPCC_HD bool stage0_infeasible() const {
+        return W.any([&](int lane) {
+            if (lane >= NX) return false;
+            const int m = lane;
+            const double x = GUESS[m], sv = GUESS[7], Lt = T.s[N_SPLINE - 1];
+            double lo = P.lx[m], hi = P.ux[m];
+            if (m == 7) { lo = fmax(sv - P.s_trust_region, 0.0); hi = fmin(sv + P.s_trust_region, Lt); }
+            double xlo = (lo - x) / P.Tx[m], xhi = (hi - x) / P.Tx[m];
+            if (m < NU * N) {  // flat column c = m < 9 of the input-bound rows: row (i, kk) with 8 i + kk = c
+                const int i = m / NU, kk = m - i * NU;
+                const double uv = GUESS[i * HZ + NX + kk];
+                xlo = fmax(xlo, (P.lu[kk] - uv) / Tu(kk));
+                xhi = fmin(xhi, (P.uu[kk] - uv) / Tu(kk));
+            }
+            return xlo > 1e-9 || xhi < -1e-9;
+        });
+    }
+
     // ---- the SQP loop (solveOCP) ----
     MPCC_HD SqpResult run(const double* cur_u, const double* rb, size_t rb_stride, size_t rb_stage, SqpLogRef* log) {
         SqpResult res;
@@ -750,15 +889,18 @@ struct WarpSqp {
         bool done = false;
         bool have_lin = false, lin_notpd = false, lin_nan = false;  // LIN already holds the linearisation of GUESS
         double inf_step = 0.0;                                       // inf-norm of the persistent step
+        bool last_rejected = false;
         for (it = 0; it < max_iter; it++) {
             const double t_a = now_ns();
+            bool qp_known_infeasible = false;
             if (!have_lin) {
                 double obj, gap;
-                eval_horizon<true>(cur_u, rb, rb_stride, rb_stage, 0.0, it == 0, obj, gap, &lin_notpd, &lin_nan);
+                qp_known_infeasible = (it > 0) && stage0_infeasible();  // (it == 0 also writes the cycle constants)
+                eval_horizon<true>(cur_u, rb, rb_stride, rb_stage, 0.0, it == 0, obj, gap, &lin_notpd, &lin_nan, !qp_known_infeasible);
             }
             have_lin = false;
             // mis-indexed input-bound rows (osqp_interface.cpp:273) intersected into the state boxes
-            W.each([&](int lane) {
+            if (!qp_known_infeasible) W.each([&](int lane) {
                 for (int c = lane; c < NU * N; c += 32) {
                     const int k = c / NX, m = c - k * NX, i = c / NU, kk = c - i * NU;
                     const double uv = GUESS[i * HZ + NX + kk];
@@ -772,7 +914,9 @@ struct WarpSqp {
             if (lin_notpd) { res.status = NON_PD_HESSIAN; done = true; break; }
             if (lin_nan) { res.status = NAN_HESSIAN; done = true; break; }
             const double t_b = now_ns();
-            QpStats qs = solve();
+            QpStats qs;
+            if (qp_known_infeasible) { qs.ok = 0; qs.iters = 0; qs.res_dual = qs.res_prim = qs.gap = 0; }
+            else qs = solve();
             res.qp_iters += qs.iters;
             if (qs.ok) {
                 inf_step = W.rmax([&](int lane) {
@@ -793,7 +937,7 @@ struct WarpSqp {
                     double o2, g2;
                     // If this trial is accepted and the loop goes on (alpha |step| >= eps_prim), the next iteration linearises
                     // exactly at this point: evaluate it in full right away instead of values now and everything later.
-                    const bool spec = (i == 0) && (inf_step >= P.eps_prim) && (it + 1 < max_iter);
+                    const bool spec = (i == 0) && (inf_step >= P.eps_prim) && (it + 1 < max_iter) && !last_rejected;
                     bool sp_notpd = false, sp_nan = false;
                     if (spec) eval_horizon<true>(cur_u, rb, rb_stride, rb_stage, alpha, false, o2, g2, &sp_notpd, &sp_nan);
                     else eval_horizon<false>(cur_u, rb, rb_stride, rb_stage, alpha, false, o2, g2, nullptr, nullptr);
@@ -820,6 +964,7 @@ struct WarpSqp {
                 }
                 alpha *= P.line_search_tau;
             }
+            last_rejected = !accepted;  // after a rejection do not speculate: rejections come in runs (stale step, tiny alpha)
             tm_get_alpha += now_ns() - t_c;
             if (accepted && it < 32) res.accept_mask |= (1u << it);
             // ---- take the step (osqp_interface.cpp:549-551) ----

@@ -21,4 +21,8 @@ for c in range(8):
     for k in sorted(set(it.tolist())):
         m = it == k
         print(f"    iters={k}: n={m.sum()} mean {t[m].mean():.3f} ms max {t[m].max():.3f} | set_qp {tt[m,1].mean():.3f} solve_qp {tt[m,2].mean():.3f} get_alpha {tt[m,3].mean():.3f}")
+    qi, qf = mpc.qp_counters()
+    big = np.where(it >= 50)[0]
+    for b in big[:4]:
+        print(f"    straggler b={b}: iters {it[b]} qp_iters {qi[b]} qp_fail {qf[b]} status {r['status'][b]} x_in {np.array2string(x0[b], precision=4)} u_in {np.array2string(u0[b], precision=3)}")
     u0 = r["u0"]; x0 = mpc.sim_time_step(r["x0"], u0)
