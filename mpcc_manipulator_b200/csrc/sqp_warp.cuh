@@ -126,7 +126,10 @@ MPCC_HD size_t warp_ws_doubles(int N) {
 // the sweeps keep the gradient (17 S) and kappa (8 S) in the scratch below SC_VEC behind a 4-slot factor ring; longer
 // horizons get a separate block appended after the scratch
 constexpr int SW_RING = 4, SW_GK = SW_RING * WF_SIZE;
-MPCC_HD size_t warp_smem_extra(int N) { return (25 * (N + 1) <= SC_VEC - SW_GK) ? 0 : (size_t)25 * (N + 1); }
+constexpr int XG_ROOM = SC_U;  // the iterate's working copy sits in the factorisation's block area between QP solves
+MPCC_HD size_t warp_smem_extra(int N) {
+    return ((25 * (N + 1) <= SC_VEC - SW_GK) ? 0 : (size_t)25 * (N + 1)) + ((HZ * (N + 1) <= XG_ROOM) ? 0 : (size_t)HZ * (N + 1));
+}
 MPCC_HD size_t warp_smem_doubles(int N) { return (size_t)2 * (N + 1) * HZ + SC_SIZE + warp_smem_extra(N); }
 
 // isPosdef / isNan of one packed-lower 9 x 9 Hessian block, fully unrolled (static indices: registers).
@@ -166,6 +169,9 @@ struct WarpSqp {
     double *LIN, *CST, *IT, *ILAM, *IRP, *IW, *IV, *IDT, *IDLAM, *G, *KAP, *FACT, *SSTEP, *GUESS, *FILT;
     // per-warp shared memory
     double *VAR, *STEP, *SC;
+    // working copies between QP solves: the iterate (in the scratch) and the persistent step (in STEP); their homes
+    // GUESS / SSTEP in the global workspace are written before and re-read after every executed QP solve
+    double *XG, *XS;
     int OR_, OP_;  // offsets of the rate / polytopic sub-arrays inside the per-constraint vectors
     // the reference's ComputeTime phases (osqp_interface.h:71-79) for this instance, in ns: set_qp, solve_qp, get_alpha
     double tm_set_qp = 0, tm_solve_qp = 0, tm_get_alpha = 0;
@@ -188,6 +194,8 @@ struct WarpSqp {
         G = gws; gws += S_ * HZ; KAP = gws; gws += S_ * 8; FACT = gws; gws += S_ * WF_SIZE; SSTEP = gws; gws += S_ * HZ; GUESS = gws; gws += S_ * HZ; FILT = gws;
         VAR = sm; STEP = sm + S_ * HZ; SC = sm + 2 * S_ * HZ;
         OR_ = 18 * S; OP_ = 32 * S;
+        XG = (HZ * S <= XG_ROOM) ? SC : SC + SC_SIZE;
+        XS = STEP;
     }
     MPCC_HD void init_scratch() const {
         W.each([&](int lane) {
@@ -506,7 +514,7 @@ struct WarpSqp {
     MPCC_HD void solve_step() const {
         double* ring = SC;                    // the factorisation's blocks are dead during the sweeps
         const int gk_room = SC_VEC - SW_GK;   // doubles available behind the ring
-        double* GS_ = (25 * S <= gk_room) ? SC + SW_GK : SC + SC_SIZE;  // gradient copy [S][17]
+        double* GS_ = (25 * S <= gk_room) ? SC + SW_GK : SC + SC_SIZE + ((HZ * S <= XG_ROOM) ? 0 : HZ * S);  // gradient copy [S][17]
         double* KS = GS_ + S * HZ;                                      // kappa [S][8]
         double* V = SC + SC_VEC;
         W.each([&](int lane) {
@@ -777,10 +785,10 @@ struct WarpSqp {
         W.each([&](int lane) {
             for (int e = lane; e < S * HZ; e += 32) {
                 const int kk = e / HZ, r = e - kk * HZ;
-                double v = GUESS[e];
+                double v = XG[e];
                 if (alpha != 0.0) {
-                    if (r < NX) v += alpha * (Tx(r) * SSTEP[e]);
-                    else v = (kk < N) ? v + alpha * (Tu(r - NX) * SSTEP[e]) : 0.0;
+                    if (r < NX) v += alpha * (Tx(r) * XS[e]);
+                    else v = (kk < N) ? v + alpha * (Tu(r - NX) * XS[e]) : 0.0;
                 }
                 XT[e] = v;
             }
@@ -856,24 +864,29 @@ struct WarpSqp {
         }
     }
 
-    // Will the QP of the linearisation at GUESS fail solve()'s stage-0 test (xi_0 = 0 outside its box)?  The box of stage 0
-    // depends on the iterate only (state bounds, s trust region, the mis-indexed input-bound rows landing on stage 0):
+    // Will the QP of the linearisation at the iterate fail solve()'s box test (xi_0 = 0 outside its box, or an empty box at a
+    // later stage)?  The boxes depend on the iterate only (state bounds, s trust region, the mis-indexed input-bound rows):
     // same expressions as stage_eval + the quirk pass, evaluated before linearising so that a QP known to fail is not assembled.
-    MPCC_HD bool stage0_infeasible() const {
+    MPCC_HD bool qp_box_infeasible() const {
         return W.any([&](int lane) {
-            if (lane >= NX) return false;
-            const int m = lane;
-            const double x = GUESS[m], sv = GUESS[7], Lt = T.s[N_SPLINE - 1];
-            double lo = P.lx[m], hi = P.ux[m];
-            if (m == 7) { lo = fmax(sv - P.s_trust_region, 0.0); hi = fmin(sv + P.s_trust_region, Lt); }
-            double xlo = (lo - x) / P.Tx[m], xhi = (hi - x) / P.Tx[m];
-            if (m < NU * N) {  // flat column c = m < 9 of the input-bound rows: row (i, kk) with 8 i + kk = c
-                const int i = m / NU, kk = m - i * NU;
-                const double uv = GUESS[i * HZ + NX + kk];
-                xlo = fmax(xlo, (P.lu[kk] - uv) / Tu(kk));
-                xhi = fmin(xhi, (P.uu[kk] - uv) / Tu(kk));
+            const double Lt = T.s[N_SPLINE - 1];
+            bool bad = false;
+            for (int o = lane; o < S * NX; o += 32) {
+                const int k = o / NX, m = o - k * NX;
+                const double x = XG[k * HZ + m], sv = XG[k * HZ + 7];
+                double lo = P.lx[m], hi = P.ux[m];
+                if (m == 7) { lo = fmax(sv - P.s_trust_region, 0.0); hi = fmin(sv + P.s_trust_region, Lt); }
+                double xlo = (lo - x) / P.Tx[m], xhi = (hi - x) / P.Tx[m];
+                if (o < NU * N) {  // flat column c = o of the input-bound rows: row (i, kk) with 8 i + kk = c
+                    const int i = o / NU, kk = o - i * NU;
+                    const double uv = XG[i * HZ + NX + kk];
+                    xlo = fmax(xlo, (P.lu[kk] - uv) / Tu(kk));
+                    xhi = fmin(xhi, (P.uu[kk] - uv) / Tu(kk));
+                }
+                if (k == 0) { if (xlo > 1e-9 || xhi < -1e-9) bad = true; }
+                else if (xlo > xhi) bad = true;
             }
-            return xlo > 1e-9 || xhi < -1e-9;
+            return bad;
         });
     }
 
@@ -884,7 +897,7 @@ struct WarpSqp {
         const int max_iter = (int)P.max_iter, ls_max = (int)P.line_search_max_iter;
         const int HN = S * HZ;
         init_scratch();
-        W.each([&](int lane) { for (int e = lane; e < HN; e += 32) SSTEP[e] = 0.0; });
+        W.each([&](int lane) { for (int e = lane; e < HN; e += 32) { XS[e] = 0.0; XG[e] = GUESS[e]; } });
         int n_filt = 0, it = 0;
         bool done = false;
         bool have_lin = false, lin_notpd = false, lin_nan = false;  // LIN already holds the linearisation of GUESS
@@ -895,7 +908,7 @@ struct WarpSqp {
             bool qp_known_infeasible = false;
             if (!have_lin) {
                 double obj, gap;
-                qp_known_infeasible = (it > 0) && stage0_infeasible();  // (it == 0 also writes the cycle constants)
+                qp_known_infeasible = (it > 0) && qp_box_infeasible();  // (it == 0 also writes the cycle constants)
                 eval_horizon<true>(cur_u, rb, rb_stride, rb_stage, 0.0, it == 0, obj, gap, &lin_notpd, &lin_nan, !qp_known_infeasible);
             }
             have_lin = false;
@@ -903,7 +916,7 @@ struct WarpSqp {
             if (!qp_known_infeasible) W.each([&](int lane) {
                 for (int c = lane; c < NU * N; c += 32) {
                     const int k = c / NX, m = c - k * NX, i = c / NU, kk = c - i * NU;
-                    const double uv = GUESS[i * HZ + NX + kk];
+                    const double uv = XG[i * HZ + NX + kk];
                     const double lo = (P.lu[kk] - uv) / Tu(kk), hi = (P.uu[kk] - uv) / Tu(kk);
                     double* L = LIN + (size_t)k * WL_SIZE;
                     L[WL_XLO + m] = fmax(L[WL_XLO + m], lo);
@@ -916,16 +929,21 @@ struct WarpSqp {
             const double t_b = now_ns();
             QpStats qs;
             if (qp_known_infeasible) { qs.ok = 0; qs.iters = 0; qs.res_dual = qs.res_prim = qs.gap = 0; }
-            else qs = solve();
+            else {
+                W.each([&](int lane) { for (int e = lane; e < HN; e += 32) { GUESS[e] = XG[e]; SSTEP[e] = XS[e]; } });  // the QP solve uses all of the scratch
+                qs = solve();
+                W.each([&](int lane) { for (int e = lane; e < HN; e += 32) XG[e] = GUESS[e]; });
+            }
             res.qp_iters += qs.iters;
             if (qs.ok) {
                 inf_step = W.rmax([&](int lane) {
                     double m = 0;
-                    for (int e = lane; e < HN; e += 32) { const int k = e / HZ, r = e - k * HZ; const double v = (r < NX || k < N) ? VAR[e] : 0.0; SSTEP[e] = v; m = fmax(m, fabs(v)); }
+                    for (int e = lane; e < HN; e += 32) { const int k = e / HZ, r = e - k * HZ; const double v = (r < NX || k < N) ? VAR[e] : 0.0; XS[e] = v; m = fmax(m, fabs(v)); }
                     return m;
                 });
             } else {
                 res.qp_fail++;  // step keeps its previous value (osqp_interface.cpp:479-505)
+                if (!qp_known_infeasible) W.each([&](int lane) { for (int e = lane; e < HN; e += 32) XS[e] = SSTEP[e]; });
             }
             const double t_c = now_ns();
             tm_set_qp += t_b - t_a; tm_solve_qp += t_c - t_b;
@@ -971,16 +989,16 @@ struct WarpSqp {
             W.each([&](int lane) {
                 for (int e = lane; e < HN; e += 32) {
                     const int k = e / HZ, r = e - k * HZ;
-                    const double s = SSTEP[e];
-                    if (r < NX) GUESS[e] += alpha * (Tx(r) * s);
-                    else if (k < N) GUESS[e] += alpha * (Tu(r - NX) * s);
-                    else GUESS[e] = 0.0;
+                    const double s = XS[e];
+                    if (r < NX) XG[e] += alpha * (Tx(r) * s);
+                    else if (k < N) XG[e] += alpha * (Tu(r - NX) * s);
+                    else XG[e] = 0.0;
                 }
             });
             const double inf = inf_step;
             if (log && log->n < log->max_log) {
                 W.each([&](int lane) {
-                    if (log->steps) for (int e = lane; e < HN; e += 32) log->steps[(size_t)log->n * HN + e] = SSTEP[e];
+                    if (log->steps) for (int e = lane; e < HN; e += 32) log->steps[(size_t)log->n * HN + e] = XS[e];
                     if (lane == 0) { log->alphas[log->n] = alpha; log->qp_ok[log->n] = qs.ok; }
                 });
                 log->n++;
@@ -989,6 +1007,7 @@ struct WarpSqp {
         }
         if (!done) { res.status = MAX_ITER_EXCEEDED; res.iters = max_iter; }
         else if (res.status != SOLVED) res.iters = it;
+        W.each([&](int lane) { for (int e = lane; e < HN; e += 32) GUESS[e] = XG[e]; });
         return res;
     }
 };

@@ -99,7 +99,7 @@ int emu_warp_solve_qp(const double* params, const double* table, double Ts, int 
     Warp wp; wp.reverse = reverse != 0;
     WarpSqp w{P, *(const TrackTable*)table, make_dyn(P, Ts), Ts, N, S, QpOptions{qp_max_iter, qp_eps}, wp};
     w.carve(gws.data(), sm.data());
-    for (int e = 0; e < HN; e++) w.GUESS[e] = guess[e];
+    for (int e = 0; e < HN; e++) { w.GUESS[e] = guess[e]; w.XG[e] = guess[e]; w.XS[e] = 0.0; }
     w.init_scratch();
     double obj, gap;
     bool f1, f2;
