@@ -112,7 +112,7 @@ constexpr int WC_SIZE = NPOLY * 14;   // cycle constants per stage: 11 normalise
 constexpr int WF_X = 0, WF_LAM = 64, WF_SIZE = 192;  // factor record: L^-1 (8 x 8, lower), Lam (8 x 16)
 // shared-memory scratch of one warp (doubles)
 constexpr int SC_P = 0, SC_PM = 256, SC_MNN = 512, SC_MNX = 576, SC_X = 704, SC_LAM = 768, SC_U = 896, SC_STG = 1092, SC_FF = 1668,
-              SC_VEC = 1740, SC_TXU = 1836, SC_RED = 1854, SC_SIZE = 1918;
+              SC_VEC = 1740, SC_TXU = 1836, SC_DYN = 1854, SC_RED = 1872, SC_SIZE = 1936;
 // staged inputs of one stage of the factorisation (two slots, filled by asynchronous copies one stage ahead):
 // polytopic rows, their barrier weights, Q, Rd, box / rate barrier weights
 constexpr int SG_GS = 0, SG_WP = 154, SG_Q = 166, SG_RD = 247, SG_WB = 255, SG_WR = 273, SG_SIZE = 288;
@@ -201,10 +201,18 @@ struct WarpSqp {
         W.each([&](int lane) {
             if (lane < NX) SC[SC_TXU + lane] = P.Tx[lane];
             else if (lane < HZ) SC[SC_TXU + lane] = P.Tu[lane - NX];
+            if (lane == 0) { SC[SC_DYN] = dyn.asv; SC[SC_DYN + 1] = dyn.bs; SC[SC_DYN + 2] = dyn.bv; }
+            if (lane < DOF) { SC[SC_DYN + 3 + lane] = dyn.bq[lane]; SC[SC_DYN + 10 + lane] = dyn.cpl[lane]; }
         });
     }
     MPCC_HD double Tx(int m) const { return SC[SC_TXU + m]; }
     MPCC_HD double Tu(int j) const { return SC[SC_TXU + NX + j]; }
+    // normalised dynamics constants, read from shared memory (lane-dependent indices would otherwise put the struct in local memory)
+    MPCC_HD double d_asv() const { return SC[SC_DYN]; }
+    MPCC_HD double d_bs() const { return SC[SC_DYN + 1]; }
+    MPCC_HD double d_bv() const { return SC[SC_DYN + 2]; }
+    MPCC_HD double d_bq(int j) const { return SC[SC_DYN + 3 + j]; }
+    MPCC_HD double d_cpl(int j) const { return SC[SC_DYN + 10 + j]; }
 
     // G z of one constraint on a [S][17] (xi | nu) vector in shared memory
     MPCC_HD double gz_box(const double* Z, int k, int c) const { return (c < 9) ? -Z[k * HZ + c] : Z[k * HZ + c - 9]; }
@@ -299,8 +307,8 @@ struct WarpSqp {
                 double base = L[WL_RD + j] * z[j] + L[WL_r + j];
                 double sv = 0, sl = 0;
                 if (j < DOF) {
-                    if (k >= 1) base += dyn.cpl[j] * z[j - HZ];
-                    if (k <= N - 2) base += dyn.cpl[j] * z[j + HZ];
+                    if (k >= 1) base += d_cpl(j) * z[j - HZ];
+                    if (k <= N - 2) base += d_cpl(j) * z[j + HZ];
                     const int ir = OR_ + k * 14;
                     sv = IV[ir + 7 + j] - IV[ir + j];
                     if (dst0) sl = ILAM[ir + 7 + j] - ILAM[ir + j];
@@ -349,8 +357,6 @@ struct WarpSqp {
         double* X = SC + SC_X;       // L^-1
         double* Lam = SC + SC_LAM;   // L^-1 Mnx
         double* U = SC + SC_U;       // 14 x 14 polytopic barrier Hessian  sum_p w_p g_p g_p'
-        double* Lc = SC + SC_U;      // Cholesky factor (U is dead by then)
-        double* INV = SC + SC_U + 64;
         double* SG = SC + SC_STG;
         double* FF = SC + SC_FF;
         // terminal stage: P_N = Q_N + box W
@@ -382,11 +388,9 @@ struct WarpSqp {
                 issue_stage_copy(lane, k - 1, SG);
                 for (int e = lane; e < 72; e += 32) {
                     const int i = e / 9, c = e - i * 9;
-                    FF[e] = (i < 7) ? dyn.bq[i] * Pc[i * 16 + c] + Pc[(9 + i) * 16 + c] : dyn.bs * Pc[7 * 16 + c] + dyn.bv * Pc[8 * 16 + c];
+                    FF[e] = (i < 7) ? d_bq(i) * Pc[i * 16 + c] + Pc[(9 + i) * 16 + c] : d_bs() * Pc[7 * 16 + c] + d_bv() * Pc[8 * 16 + c];
                 }
-            });
-            // F2: U = sum_p (w_p g_p) g_p'  in 2 x 2 register blocks
-            W.each([&](int lane) {
+                // F2 (same phase: independent of FF): U = sum_p (w_p g_p) g_p'  in 2 x 2 register blocks
                 for (int blk = lane; blk < 49; blk += 32) {
                     const int bi = blk / 7, bj = blk - bi * 7;
                     double a00 = 0, a01 = 0, a10 = 0, a11 = 0;
@@ -407,11 +411,11 @@ struct WarpSqp {
                     const int i = e >> 3, j = e & 7;
                     double v;
                     if (j < 7) {
-                        v = dyn.bq[j] * FF[i * 9 + j];
-                        if (i < 7) v += dyn.bq[i] * Pc[(9 + j) * 16 + i] + Pc[(9 + i) * 16 + 9 + j] + U[(7 + i) * 14 + 7 + j];
-                        else v += dyn.bs * Pc[(9 + j) * 16 + 7] + dyn.bv * Pc[(9 + j) * 16 + 8];
+                        v = d_bq(j) * FF[i * 9 + j];
+                        if (i < 7) v += d_bq(i) * Pc[(9 + j) * 16 + i] + Pc[(9 + i) * 16 + 9 + j] + U[(7 + i) * 14 + 7 + j];
+                        else v += d_bs() * Pc[(9 + j) * 16 + 7] + d_bv() * Pc[(9 + j) * 16 + 8];
                     } else {
-                        v = dyn.bs * FF[i * 9 + 7] + dyn.bv * FF[i * 9 + 8];
+                        v = d_bs() * FF[i * 9 + 7] + d_bv() * FF[i * 9 + 8];
                     }
                     if (i == j) { v += RDs[j]; if (j < 7) v += wR[j] + wR[7 + j]; }
                     Mnn[e] = v;
@@ -421,10 +425,10 @@ struct WarpSqp {
                     double v = 0;
                     if (c < 9) {
                         v = FF[i * 9 + c];
-                        if (c == 8) v += dyn.asv * FF[i * 9 + 7];
+                        if (c == 8) v += d_asv() * FF[i * 9 + 7];
                         if (i < 7 && c < 7) v += U[(7 + i) * 14 + c];
                     } else if (c - 9 == i && k >= 1) {
-                        v = dyn.cpl[i] - (wR[i] + wR[7 + i]);
+                        v = d_cpl(i) - (wR[i] + wR[7 + i]);
                     }
                     Mnx[e] = v;
                 }
@@ -433,8 +437,8 @@ struct WarpSqp {
                     double v = 0;
                     if (r < 9 && c < 9) {
                         v = Pc[e];
-                        if (c == 8) v += dyn.asv * Pc[r * 16 + 7];
-                        if (r == 8) v += dyn.asv * (Pc[7 * 16 + c] + ((c == 8) ? dyn.asv * Pc[7 * 16 + 7] : 0.0));
+                        if (c == 8) v += d_asv() * Pc[r * 16 + 7];
+                        if (r == 8) v += d_asv() * (Pc[7 * 16 + c] + ((c == 8) ? d_asv() * Pc[7 * 16 + 7] : 0.0));
                         v += Qs[r * 9 + c];
                         if (r == c && k >= 1) v += wB[r] + wB[9 + r];
                         if (r < 7 && c < 7) v += U[r * 14 + c];
@@ -444,39 +448,47 @@ struct WarpSqp {
                     PM[e] = v;
                 }
             });
-            // F4: Cholesky Mnn = Lc Lc' column by column (lane = row); 1 / Lc_jj kept in INV
+            // F4 + F5: every lane c < 24 factors Mnn = Lc Lc' in its own registers (no barriers or shared-memory round trips on
+            //     the pivot chain), then solves its column of [Lam | X] = Lc^-1 [Mnx | I] by forward substitution
+            const bool bad = W.any([&](int lane) {
+                if (lane >= 24) return false;
+                double Lr[36], inv[8];
+                bool pd = true;
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                W.each([&](int lane) {
-                    if (lane >= j && lane < 8) {
-                        const int i = lane;
-                        double djj = Mnn[j * 8 + j], s = Mnn[i * 8 + j];
+                for (int i = 0; i < 8; i++)
 #pragma unroll
-                        for (int t = 0; t < 8; t++)
-                            if (t < j) { const double ljt = Lc[j * 8 + t]; djj -= ljt * ljt; s -= Lc[i * 8 + t] * ljt; }
-                        const double inv = MPCC_RSQRT(djj);
-                        if (i == j) { Lc[j * 8 + j] = djj * inv; INV[j] = (djj > 0.0) ? inv : -1.0; }
-                        else Lc[i * 8 + j] = s * inv;
-                    }
-                });
-            }
-            if (W.any([&](int lane) { return lane < 8 && !(INV[lane] > 0.0 && INV[lane] < 1e150); })) { ok = false; break; }
-            // F5: [Lam | X] = Lc^-1 [Mnx | I] by forward substitution, one column per lane (16 + 8 columns)
-            W.each([&](int lane) {
-                if (lane < 24) {
-                    const int c = lane;
-                    double col[8];
+                    for (int j = 0; j < 8; j++) if (j <= i) Lr[i * (i + 1) / 2 + j] = Mnn[i * 8 + j];
 #pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        double s = (c < 16) ? Mnx[i * 16 + (c & 15)] : ((i == c - 16) ? 1.0 : 0.0);
+                for (int j = 0; j < 8; j++) {
+                    double d = Lr[j * (j + 1) / 2 + j];
 #pragma unroll
-                        for (int t = 0; t < 8; t++) if (t < i) s -= Lc[i * 8 + t] * col[t];
-                        col[i] = s * INV[i];
-                    }
+                    for (int t = 0; t < 8; t++) if (t < j) d -= Lr[j * (j + 1) / 2 + t] * Lr[j * (j + 1) / 2 + t];
+                    if (!(d > 0.0 && d < 1e300)) pd = false;
+                    const double iv = MPCC_RSQRT(d);
+                    inv[j] = iv;
 #pragma unroll
-                    for (int i = 0; i < 8; i++) { if (c < 16) Lam[i * 16 + c] = col[i]; else X[i * 8 + c - 16] = col[i]; }
+                    for (int i = 0; i < 8; i++)
+                        if (i > j) {
+                            double v = Lr[i * (i + 1) / 2 + j];
+#pragma unroll
+                            for (int t = 0; t < 8; t++) if (t < j) v -= Lr[i * (i + 1) / 2 + t] * Lr[j * (j + 1) / 2 + t];
+                            Lr[i * (i + 1) / 2 + j] = v * iv;
+                        }
                 }
+                const int c = lane;
+                double col[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    double v = (c < 16) ? Mnx[i * 16 + (c & 15)] : ((i == c - 16) ? 1.0 : 0.0);
+#pragma unroll
+                    for (int t = 0; t < 8; t++) if (t < i) v -= Lr[i * (i + 1) / 2 + t] * col[t];
+                    col[i] = v * inv[i];
+                }
+#pragma unroll
+                for (int i = 0; i < 8; i++) { if (c < 16) Lam[i * 16 + c] = col[i]; else X[i * 8 + c - 16] = col[i]; }
+                return !pd;
             });
+            if (bad) { ok = false; break; }
             // F6: P_k = [Mxx 0; 0 Mww] - Lam' Lam  in 4 x 2 register blocks; F7: store the factor record
             W.each([&](int lane) {
                 const int r0 = 4 * (lane >> 3), c0 = 2 * (lane & 7);
@@ -539,7 +551,7 @@ struct WarpSqp {
                     double kp = 0;
 #pragma unroll
                     for (int t = 0; t < 8; t++) {
-                        const double mn = (t < 7) ? g[NX + t] + dyn.bq[t] * p[t] + p[9 + t] : g[NX + 7] + dyn.bs * p[7] + dyn.bv * p[8];
+                        const double mn = (t < 7) ? g[NX + t] + d_bq(t) * p[t] + p[9 + t] : g[NX + 7] + d_bs() * p[7] + d_bv() * p[8];
                         kp += Fs[WF_X + lane * 8 + t] * mn;  // X: lower triangular with explicit zeros
                     }
                     KS[k * 8 + lane] = kp;
@@ -548,7 +560,7 @@ struct WarpSqp {
             W.each([&](int lane) {
                 if (lane < 16) {
                     double mx = 0;
-                    if (lane < 9) { mx = g[lane] + p[lane]; if (lane == 8) mx += dyn.asv * p[7]; }
+                    if (lane < 9) { mx = g[lane] + p[lane]; if (lane == 8) mx += d_asv() * p[7]; }
 #pragma unroll
                     for (int t = 0; t < 8; t++) mx -= Fs[WF_LAM + 16 * t + lane] * KS[k * 8 + t];
                     pn[lane] = mx;
@@ -585,9 +597,9 @@ struct WarpSqp {
 #pragma unroll
                     for (int t = 0; t < 8; t++) dni += Fs[WF_X + t * 8 + i] * V[V_RHS + t];
                     double nx;
-                    if (lane < 7) nx = d[lane] + dyn.bq[lane] * dni;
-                    else if (lane == 7) nx = d[7] + dyn.asv * d[8] + dyn.bs * dni;
-                    else if (lane == 8) nx = d[8] + dyn.bv * dni;
+                    if (lane < 7) nx = d[lane] + d_bq(lane) * dni;
+                    else if (lane == 7) nx = d[7] + d_asv() * d[8] + d_bs() * dni;
+                    else if (lane == 8) nx = d[8] + d_bv() * dni;
                     else nx = dni;
                     dn_[lane] = nx;
                     if (lane < NX) STEP[(k + 1) * HZ + lane] = nx;
@@ -660,7 +672,7 @@ struct WarpSqp {
         W.each([&](int lane) {
             if (lane == 7) {
                 double x = 0;
-                for (int k = 0; k <= N; k++) { VAR[k * HZ + 7] = x; if (k < N) x += dyn.asv * VAR[k * HZ + 8] + LIN[(size_t)k * WL_SIZE + WL_b + 7]; }
+                for (int k = 0; k <= N; k++) { VAR[k * HZ + 7] = x; if (k < N) x += d_asv() * VAR[k * HZ + 8] + LIN[(size_t)k * WL_SIZE + WL_b + 7]; }
             }
             for (int i = lane; i < tot; i += 32) { IT[i] = 1.0; ILAM[i] = 0.0; IW[i] = 0.0; IV[i] = 0.0; IRP[i] = 0.0; IDT[i] = 0.0; IDLAM[i] = 0.0; }
         });
@@ -700,14 +712,14 @@ struct WarpSqp {
                 if (lane < 8) for (int k = N - 1; k >= 1; k--) STEP[k * HZ + lane] += STEP[(k + 1) * HZ + lane];
             });
             W.each([&](int lane) {
-                if (lane == 8) for (int k = N - 1; k >= 1; k--) STEP[k * HZ + 8] += STEP[(k + 1) * HZ + 8] + dyn.asv * STEP[(k + 1) * HZ + 7];
+                if (lane == 8) for (int k = N - 1; k >= 1; k--) STEP[k * HZ + 8] += STEP[(k + 1) * HZ + 8] + d_asv() * STEP[(k + 1) * HZ + 7];
             });
             const double nrd = W.rmax([&](int lane) {
                 double nr = 0;
                 for (int o = lane; o < NU * N; o += 32) {
                     const int k = o / NU, j = o - k * NU;
                     const double* pn = STEP + (k + 1) * HZ;
-                    const double btp = (j < 7) ? dyn.bq[j] * pn[j] : dyn.bs * pn[7] + dyn.bv * pn[8];
+                    const double btp = (j < 7) ? d_bq(j) * pn[j] : d_bs() * pn[7] + d_bv() * pn[8];
                     nr = fmax(nr, fabs(STEP[k * HZ + NX + j] + btp));
                 }
                 return nr;
@@ -756,7 +768,7 @@ struct WarpSqp {
                         VAR[k * HZ + lane] = x;
                         if (k < N) {
                             const double b = LIN[(size_t)k * WL_SIZE + WL_b + lane];
-                            x = (lane < 7) ? x + dyn.bq[lane] * VAR[k * HZ + NX + lane] + b : x + dyn.bv * VAR[k * HZ + NX + 7] + b;
+                            x = (lane < 7) ? x + d_bq(lane) * VAR[k * HZ + NX + lane] + b : x + d_bv() * VAR[k * HZ + NX + 7] + b;
                         }
                     }
                 }
@@ -766,7 +778,7 @@ struct WarpSqp {
                     double x = 0;
                     for (int k = 0; k <= N; k++) {
                         VAR[k * HZ + 7] = x;
-                        if (k < N) x = x + dyn.asv * VAR[k * HZ + 8] + dyn.bs * VAR[k * HZ + NX + 7] + LIN[(size_t)k * WL_SIZE + WL_b + 7];
+                        if (k < N) x = x + d_asv() * VAR[k * HZ + 8] + d_bs() * VAR[k * HZ + NX + 7] + LIN[(size_t)k * WL_SIZE + WL_b + 7];
                     }
                 }
             });
@@ -849,7 +861,7 @@ struct WarpSqp {
                 for (int k = 0; k < N; k++) {
                     const double kap = (k == 0 || k == N - 1) ? 2.0 : 4.0;
                     const double rd = (j < 7) ? tu * ((2.0 * P.r_dq + 1e-6) + kap * P.r_ddq_solver) * tu : tu * (2.0 * P.r_dVs + 1e-6) * tu;
-                    d = (k == 0 || j == 7) ? rd : rd - dyn.cpl[j] * dyn.cpl[j] / d;
+                    d = (k == 0 || j == 7) ? rd : rd - d_cpl(j) * d_cpl(j) / d;
                     if (d <= 0.0) { pd_l = false; break; }
                 }
             }
