@@ -252,7 +252,8 @@ def run_ours(args):
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")  # > 126 MB L2
     launches = {"n": 0}
     gathered = {}
-    from mpcc_manipulator_b200.sharding import gather_results
+    from mpcc_manipulator_b200.sharding import ResultGatherer
+    gatherer = ResultGatherer(B, world, f"cuda:{local}") if world > 1 else None
 
     def step():
         """device-resident closed-loop step: cycle -> (gather) -> plant"""
@@ -262,7 +263,7 @@ def run_ours(args):
         with torch.cuda.stream(stream):
             if world > 1:
                 # the path's only collective: gather the applied controls and per-instance status / iterations (NCCL)
-                gathered["u0"], gathered["status"], gathered["iters"] = gather_results(u_out, st_out, it_out, world * B, dist)
+                gathered["u0"], gathered["status"], gathered["iters"] = gatherer(u_out, st_out, it_out, dist)
             u.copy_(u_out)
         mpc.sim_time_step_device(x.data_ptr(), u.data_ptr(), xn.data_ptr())
         launches["n"] += 1

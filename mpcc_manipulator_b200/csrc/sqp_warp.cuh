@@ -786,14 +786,9 @@ struct WarpSqp {
         return st;
     }
 
-    // ---- horizon evaluation at guess + alpha T step, lane = stage.
-    //      FULL: fill LIN (and, if write_cst, the polytopic rows), test the Hessian blocks (notpd / nan);
-    //      else only the objective and the l1 constraint violation ----
-    template <bool FULL>
-    MPCC_HD void eval_horizon(const double* cur_u, const double* rb, size_t rb_stride, size_t rb_stage, double alpha, bool write_cst, double& obj, double& gap,
-                              bool* notpd, bool* nan, bool write_lin = true) const {
-        double* RED = SC + SC_RED;
-        double* XT = VAR;  // the evaluation point, gathered once into shared memory (VAR is free outside the QP solve)
+    // the evaluation point guess + alpha T step, gathered once into shared memory (VAR is free outside the QP solve)
+    MPCC_HD void gather_point(double alpha) const {
+        double* XT = VAR;
         W.each([&](int lane) {
             for (int e = lane; e < S * HZ; e += 32) {
                 const int kk = e / HZ, r = e - kk * HZ;
@@ -805,6 +800,17 @@ struct WarpSqp {
                 XT[e] = v;
             }
         });
+    }
+
+    // ---- horizon evaluation at guess + alpha T step, lane = stage.
+    //      FULL: fill LIN (and, if write_cst, the polytopic rows), test the Hessian blocks (notpd / nan);
+    //      else only the objective and the l1 constraint violation ----
+    template <bool FULL>
+    MPCC_HD void eval_horizon(const double* cur_u, const double* rb, size_t rb_stride, size_t rb_stage, double alpha, bool write_cst, double& obj, double& gap,
+                              bool* notpd, bool* nan, bool write_lin = true, bool gathered = false) const {
+        double* RED = SC + SC_RED;
+        const double* XT = VAR;  // the evaluation point, see gather_point()
+        if (!gathered) gather_point(alpha);
         obj = W.rsum([&](int lane) {
             double o_acc = 0, g_acc = 0;
             bool pd_l = true, nan_l = false;
@@ -879,19 +885,19 @@ struct WarpSqp {
     // Will the QP of the linearisation at the iterate fail solve()'s box test (xi_0 = 0 outside its box, or an empty box at a
     // later stage)?  The boxes depend on the iterate only (state bounds, s trust region, the mis-indexed input-bound rows):
     // same expressions as stage_eval + the quirk pass, evaluated before linearising so that a QP known to fail is not assembled.
-    MPCC_HD bool qp_box_infeasible() const {
+    MPCC_HD bool qp_box_infeasible(const double* X) const {
         return W.any([&](int lane) {
             const double Lt = T.s[N_SPLINE - 1];
             bool bad = false;
             for (int o = lane; o < S * NX; o += 32) {
                 const int k = o / NX, m = o - k * NX;
-                const double x = XG[k * HZ + m], sv = XG[k * HZ + 7];
+                const double x = X[k * HZ + m], sv = X[k * HZ + 7];
                 double lo = P.lx[m], hi = P.ux[m];
                 if (m == 7) { lo = fmax(sv - P.s_trust_region, 0.0); hi = fmin(sv + P.s_trust_region, Lt); }
                 double xlo = (lo - x) / P.Tx[m], xhi = (hi - x) / P.Tx[m];
                 if (o < NU * N) {  // flat column c = o of the input-bound rows: row (i, kk) with 8 i + kk = c
                     const int i = o / NU, kk = o - i * NU;
-                    const double uv = XG[i * HZ + NX + kk];
+                    const double uv = X[i * HZ + NX + kk];
                     xlo = fmax(xlo, (P.lu[kk] - uv) / Tu(kk));
                     xhi = fmin(xhi, (P.uu[kk] - uv) / Tu(kk));
                 }
@@ -912,18 +918,20 @@ struct WarpSqp {
         W.each([&](int lane) { for (int e = lane; e < HN; e += 32) { XS[e] = 0.0; XG[e] = GUESS[e]; } });
         int n_filt = 0, it = 0;
         bool done = false;
-        bool have_lin = false, lin_notpd = false, lin_nan = false;  // LIN already holds the linearisation of GUESS
+        bool have_lin = false, lin_notpd = false, lin_nan = false;  // LIN already holds the linearisation of the iterate
+        bool lin_infeasible = false;                               // ... and its QP is known to fail the box test (LIN not written)
         double inf_step = 0.0;                                       // inf-norm of the persistent step
         bool last_rejected = false;
         for (it = 0; it < max_iter; it++) {
             const double t_a = now_ns();
-            bool qp_known_infeasible = false;
+            bool qp_known_infeasible = lin_infeasible;
             if (!have_lin) {
                 double obj, gap;
-                qp_known_infeasible = (it > 0) && qp_box_infeasible();  // (it == 0 also writes the cycle constants)
-                eval_horizon<true>(cur_u, rb, rb_stride, rb_stage, 0.0, it == 0, obj, gap, &lin_notpd, &lin_nan, !qp_known_infeasible);
+                gather_point(0.0);
+                qp_known_infeasible = (it > 0) && qp_box_infeasible(VAR);  // (it == 0 also writes the cycle constants)
+                eval_horizon<true>(cur_u, rb, rb_stride, rb_stage, 0.0, it == 0, obj, gap, &lin_notpd, &lin_nan, !qp_known_infeasible, true);
             }
-            have_lin = false;
+            have_lin = false; lin_infeasible = false;
             // mis-indexed input-bound rows (osqp_interface.cpp:273) intersected into the state boxes
             if (!qp_known_infeasible) W.each([&](int lane) {
                 for (int c = lane; c < NU * N; c += 32) {
@@ -968,9 +976,12 @@ struct WarpSqp {
                     // If this trial is accepted and the loop goes on (alpha |step| >= eps_prim), the next iteration linearises
                     // exactly at this point: evaluate it in full right away instead of values now and everything later.
                     const bool spec = (i == 0) && (inf_step >= P.eps_prim) && (it + 1 < max_iter) && !last_rejected;
-                    bool sp_notpd = false, sp_nan = false;
-                    if (spec) eval_horizon<true>(cur_u, rb, rb_stride, rb_stage, alpha, false, o2, g2, &sp_notpd, &sp_nan);
-                    else eval_horizon<false>(cur_u, rb, rb_stride, rb_stage, alpha, false, o2, g2, nullptr, nullptr);
+                    bool sp_notpd = false, sp_nan = false, sp_infeasible = false;
+                    if (spec) {
+                        gather_point(alpha);
+                        sp_infeasible = qp_box_infeasible(VAR);
+                        eval_horizon<true>(cur_u, rb, rb_stride, rb_stage, alpha, false, o2, g2, &sp_notpd, &sp_nan, !sp_infeasible, true);
+                    } else eval_horizon<false>(cur_u, rb, rb_stride, rb_stage, alpha, false, o2, g2, nullptr, nullptr);
                     if (W.any([&](int lane) {
                             bool dom = false;
                             for (int j = lane; j < n_filt; j += 32) if (o2 >= FILT[2 * j] && g2 >= FILT[2 * j + 1]) dom = true;
@@ -988,7 +999,7 @@ struct WarpSqp {
                         }
                         W.each([&](int lane) { if (lane == 0) { FILT[2 * w] = o2; FILT[2 * w + 1] = g2; } });
                         n_filt = w + 1;
-                        if (spec) { have_lin = true; lin_notpd = sp_notpd; lin_nan = sp_nan; }
+                        if (spec) { have_lin = true; lin_notpd = sp_notpd; lin_nan = sp_nan; lin_infeasible = sp_infeasible; }
                         break;
                     }
                 }

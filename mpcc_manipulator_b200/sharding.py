@@ -35,6 +35,23 @@ def gather_results(u0, status, iters, total, dist=None):
     return gu[keep], gs[keep, 0], gs[keep, 1]
 
 
+class ResultGatherer:
+    """gather_results with every buffer allocated once (the per-cycle path of bench.py): equal blocks of b instances per rank."""
+
+    def __init__(self, b, world, device):
+        import torch
+        self.b, self.world = b, world
+        self.ps = torch.zeros((b, 2), dtype=torch.int32, device=device)
+        self.gu = torch.empty((world * b, 8), dtype=torch.float64, device=device)
+        self.gs = torch.empty((world * b, 2), dtype=torch.int32, device=device)
+
+    def __call__(self, u0, status, iters, dist):
+        self.ps[:, 0] = status; self.ps[:, 1] = iters
+        dist.all_gather_into_tensor(self.gu, u0)
+        dist.all_gather_into_tensor(self.gs, self.ps)
+        return self.gu, self.gs[:, 0], self.gs[:, 1]
+
+
 def reduce_counters(solved, failed, max_iters, dist=None):
     """Sum / max of the per-rank statistics (solved, failed, largest SQP iteration count)."""
     import torch

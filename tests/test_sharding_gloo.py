@@ -59,3 +59,34 @@ def test_gather_gloo(world, total):
     assert np.array_equal(gu, idx[:, None] * 10.0 + np.arange(8)[None])
     assert np.array_equal(gs, idx % 3) and np.array_equal(gi, idx % 5 + 1)
     assert solved == int((idx % 3 == 0).sum()) and failed == total - solved and mx == 5
+
+
+def _worker2(rank, world, port, b, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mpcc_manipulator_b200.sharding import ResultGatherer
+    g = ResultGatherer(b, world, "cpu")
+    idx = torch.arange(rank * b, (rank + 1) * b)
+    for rep in range(2):  # buffers are reused across cycles
+        gu, gs, gi = g((idx[:, None] * 10 + torch.arange(8)[None] + rep).to(torch.float64), (idx % 3).to(torch.int32), (idx % 5 + 1).to(torch.int32), dist)
+    if rank == 0:
+        out.put((gu.numpy().copy(), gs.numpy().copy(), gi.numpy().copy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_result_gatherer_gloo():
+    world, b = 2, 16
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker2, args=(r, world, port, b, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    gu, gs, gi = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    idx = np.arange(world * b)
+    assert np.array_equal(gu, idx[:, None] * 10.0 + np.arange(8)[None] + 1)
+    assert np.array_equal(gs, idx % 3) and np.array_equal(gi, idx % 5 + 1)
