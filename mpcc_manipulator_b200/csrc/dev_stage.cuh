@@ -54,9 +54,15 @@ MPCC_HD double viol(double c, double l, double u) { return fmax(l - c, 0.0) + fm
 //   u_prev      dq of stage k-1, or the currently applied input for k == 0
 //   u_next      dq of stage k+1 (read only if k <= N-2)
 //   x_next      state of stage k+1 (read only if k < N)
+//   rbf_pre     optional: RBF(h_j) [11] | RBF'(h_j) [11] of this stage, computed by an earlier call.  h_j depends on the
+//               (frozen) RobotData and the parameters only, so the values are constant over a control cycle.
+//   rbf_out     optional: where to store them
+//   hess_only   (FULL) fill only the Hessian blocks Q, Rd -- what the positive-definiteness / NaN test of
+//               osqp_interface.cpp:454-473 looks at; used when the QP of this linearisation is already known to fail
 template <bool FULL>
 MPCC_HDN void stage_eval(const Params& P, const TrackTable& T, double Ts, int N, int k, const double* x, const double* u,
-                         const double* u_prev, const double* u_next, const double* x_next, const RbView& rb, StageLin& o) {
+                         const double* u_prev, const double* u_next, const double* x_next, const RbView& rb, StageLin& o,
+                         const double* rbf_pre = nullptr, double* rbf_out = nullptr, bool hess_only = false) {
     const double s = x[7], vs = x[8];
     const bool term = (k == N);
 
@@ -117,7 +123,7 @@ MPCC_HDN void stage_eval(const Params& P, const TrackTable& T, double Ts, int N,
 
     // ---- l1 violation of every row this stage owns (osqp_interface.cpp:824-833) ----
     double gap = 0;
-    {
+    if (!(FULL && hess_only)) {
         // state box with the s trust region around the iterate itself (bounds.cpp:85-103)
 #pragma unroll
         for (int m = 0; m < NX; m++) {
@@ -127,7 +133,7 @@ MPCC_HDN void stage_eval(const Params& P, const TrackTable& T, double Ts, int N,
             if (FULL) { o.xlo[m] = (lo - x[m]) / P.Tx[m]; o.xhi[m] = (hi - x[m]) / P.Tx[m]; }
         }
     }
-    if (!term) {
+    if (!term && !(FULL && hess_only)) {
         // input box rows: value is u itself (osqp_interface.cpp:274-276)
 #pragma unroll
         for (int j = 0; j < NU; j++) gap += viol(u[j], P.lu[j], P.uu[j]);
@@ -169,9 +175,11 @@ MPCC_HDN void stage_eval(const Params& P, const TrackTable& T, double Ts, int N,
                 dotp += g * u[m];
                 if (FULL) o.pg[j * DOF + m] = g;
             }
-            double c = -dotp + rbf(-0.5, h);
+            const double rv = rbf_pre ? rbf_pre[j] : rbf(-0.5, h);
+            double c = -dotp + rv;
             gap += fmax(c, 0.0);
-            if (FULL) { o.pd[j] = drbf(-0.5, h); o.prhs[j] = -c; }
+            if (FULL) { o.pd[j] = rbf_pre ? rbf_pre[NPC + j] : drbf(-0.5, h); o.prhs[j] = -c; }
+            if (rbf_out) { rbf_out[j] = rv; rbf_out[NPC + j] = drbf(-0.5, h); }
         }
     }
     o.gap = gap;
@@ -228,6 +236,7 @@ MPCC_HDN void stage_eval(const Params& P, const TrackTable& T, double Ts, int N,
         }
     }
     double fx[NX];
+    if (!hess_only) {
 #pragma unroll
     for (int c = 0; c < 8; c++) {
         double g = 0;
@@ -239,6 +248,7 @@ MPCC_HDN void stage_eval(const Params& P, const TrackTable& T, double Ts, int N,
     fx[8] = 2.0 * P.q_vs * dv;
 #pragma unroll
     for (int m = 0; m < NX; m++) o.q[m] = P.Tx[m] * fx[m];
+    }
 #pragma unroll
     for (int r_ = 0; r_ < NX; r_++)
 #pragma unroll

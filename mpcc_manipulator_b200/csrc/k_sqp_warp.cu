@@ -24,8 +24,14 @@ __global__ void k_order(const int32_t* __restrict__ hist, int32_t* __restrict__ 
 }
 
 // SQP loop + epilogue, one WARP per instance (sqp_warp.cuh)
-constexpr int SQPW_WARPS = 2;  // warps (instances) per CTA
-__global__ void __launch_bounds__(SQPW_WARPS * 32, 5) k_sqp_warp(CycleArgs a, double* wws, size_t ws_per, size_t sm_per) {
+#ifndef MPCC_SQPW_WARPS
+#define MPCC_SQPW_WARPS 2
+#endif
+#ifndef MPCC_SQPW_MINB
+#define MPCC_SQPW_MINB 5
+#endif
+constexpr int SQPW_WARPS = MPCC_SQPW_WARPS;  // warps (instances) per CTA
+__global__ void __launch_bounds__(SQPW_WARPS * 32, MPCC_SQPW_MINB) k_sqp_warp(CycleArgs a, double* wws, size_t ws_per, size_t sm_per) {
     extern __shared__ __align__(16) double sqpw_smem[];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int slot = blockIdx.x * SQPW_WARPS + wid;
@@ -69,7 +75,7 @@ __global__ void __launch_bounds__(SQPW_WARPS * 32, 5) k_sqp_warp(CycleArgs a, do
     }
 }
 // solveOCP probe, one warp per instance: AoS guess / RobotData, optional iteration log
-__global__ void __launch_bounds__(SQPW_WARPS * 32, 5) k_solve_ocp_warp(CycleArgs a, double* wws, size_t ws_per, size_t sm_per, double* guess, const double* rb,
+__global__ void __launch_bounds__(SQPW_WARPS * 32, MPCC_SQPW_MINB) k_solve_ocp_warp(CycleArgs a, double* wws, size_t ws_per, size_t sm_per, double* guess, const double* rb,
                                                                     const double* cur_u_all, int n, double* steps, double* alphas, int32_t* qp_ok, int max_log, int32_t* n_logged) {
     extern __shared__ __align__(16) double sqpw_smem[];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;

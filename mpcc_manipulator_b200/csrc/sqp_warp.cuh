@@ -121,7 +121,7 @@ constexpr int MAX_SQP_FILTER = 128;
 
 MPCC_HD size_t warp_ws_doubles(int N) {
     const size_t S = N + 1;
-    return S * (WL_SIZE + WC_SIZE + 7 * NINEQ + HZ /*G*/ + 8 /*KAP*/ + WF_SIZE + 2 * HZ /*persistent step, iterate*/) + 2 * (MAX_SQP_FILTER + 2);
+    return S * (WL_SIZE + WC_SIZE + 7 * NINEQ + HZ /*G*/ + 8 /*KAP*/ + WF_SIZE + 2 * HZ /*persistent step, iterate*/ + 2 * NPOLY /*barrier values*/) + 2 * (MAX_SQP_FILTER + 2);
 }
 // the sweeps keep the gradient (17 S) and kappa (8 S) in the scratch below SC_VEC behind a 4-slot factor ring; longer
 // horizons get a separate block appended after the scratch
@@ -166,7 +166,7 @@ struct WarpSqp {
     QpOptions opt;
     Warp W;
     // per-instance global workspace
-    double *LIN, *CST, *IT, *ILAM, *IRP, *IW, *IV, *IDT, *IDLAM, *G, *KAP, *FACT, *SSTEP, *GUESS, *FILT;
+    double *LIN, *CST, *IT, *ILAM, *IRP, *IW, *IV, *IDT, *IDLAM, *G, *KAP, *FACT, *SSTEP, *GUESS, *RBFV, *FILT;
     // per-warp shared memory
     double *VAR, *STEP, *SC;
     // working copies between QP solves: the iterate (in the scratch) and the persistent step (in STEP); their homes
@@ -191,7 +191,7 @@ struct WarpSqp {
         CST = gws; gws += S_ * WC_SIZE;
         IT = gws; gws += S_ * NINEQ; ILAM = gws; gws += S_ * NINEQ; IRP = gws; gws += S_ * NINEQ; IW = gws; gws += S_ * NINEQ;
         IV = gws; gws += S_ * NINEQ; IDT = gws; gws += S_ * NINEQ; IDLAM = gws; gws += S_ * NINEQ;
-        G = gws; gws += S_ * HZ; KAP = gws; gws += S_ * 8; FACT = gws; gws += S_ * WF_SIZE; SSTEP = gws; gws += S_ * HZ; GUESS = gws; gws += S_ * HZ; FILT = gws;
+        G = gws; gws += S_ * HZ; KAP = gws; gws += S_ * 8; FACT = gws; gws += S_ * WF_SIZE; SSTEP = gws; gws += S_ * HZ; GUESS = gws; gws += S_ * HZ; RBFV = gws; gws += S_ * 2 * NPOLY; FILT = gws;
         VAR = sm; STEP = sm + S_ * HZ; SC = sm + 2 * S_ * HZ;
         OR_ = 18 * S; OP_ = 32 * S;
         XG = (HZ * S <= XG_ROOM) ? SC : SC + SC_SIZE;
@@ -834,7 +834,15 @@ struct WarpSqp {
                     for (int e = 0; e < RB_DOUBLES; e++) rbl[e] = src[(size_t)e * rb_stride];
                 }
                 RbView rv{rbl, 1};
-                stage_eval<FULL>(P, T, Ts, N, k, x, u, up, un, xn, rv, sl);
+                // the relaxed-barrier values of the polytopic rows are constant over the cycle: computed by the first
+                // linearisation (write_cst), re-read afterwards (11 logarithms and divisions less per evaluation)
+                double rbfv[2 * NPOLY];
+                double* rbf_home = RBFV + (size_t)k * 2 * NPOLY;
+                if (!write_cst) {
+#pragma unroll
+                    for (int j = 0; j < 2 * NPOLY; j++) rbfv[j] = rbf_home[j];
+                }
+                stage_eval<FULL>(P, T, Ts, N, k, x, u, up, un, xn, rv, sl, write_cst ? nullptr : rbfv, write_cst ? rbf_home : nullptr, FULL && !write_lin);
                 o_acc += sl.obj; g_acc += sl.gap;
                 if (FULL) {
                     block9_pd_nan(sl.Q, pd_l, nan_l);
