@@ -318,7 +318,9 @@ def run_ours(args):
     hx = torch.empty((B, 9), dtype=torch.float64).pin_memory(); hu = torch.empty((B, 8), dtype=torch.float64).pin_memory()
     huo = torch.empty((B, 8), dtype=torch.float64).pin_memory()
     hst = torch.empty(B, dtype=torch.int32).pin_memory(); hit = torch.empty(B, dtype=torch.int32).pin_memory(); hok = torch.empty(B, dtype=torch.int32).pin_memory()
-    hx.copy_(x.cpu()); hu.copy_(u.cpu())
+    # same closed loop from the same start as the device-resident measurement: forget the warm starts, replay the warm-up
+    mpc.reset()
+    hx.copy_(torch.from_numpy(x_host)); hu.copy_(torch.from_numpy(u_host))
     Ts = 0.01
 
     def e2e_step():
@@ -334,7 +336,7 @@ def run_ours(args):
         hu.copy_(huo)
 
     e2e_steps = max(3, min(args.steps, 20))
-    for _ in range(2):
+    for _ in range(args.warmup):
         e2e_step()
     if world > 1:
         dist.barrier()

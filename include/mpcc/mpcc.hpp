@@ -159,6 +159,15 @@ public:
         check(mpcc_cuda_eval_robot_data(h_, q[0].data(), obs ? (*obs)[0].data() : nullptr, (int32_t)q.size(), rb.data()));
         return rb;
     }
+    // Stage linearisation by the device code (Cost::getCost, Constraints::getConstraints, Bounds, dynamics defect) for
+    // instance 0's parameters / track 0: the 212 doubles of the normalised QP blocks (layout: csrc/dev_stage.cuh StageLin)
+    std::array<double, MPCC_STAGE_LIN_DOUBLES> evalStage(const State& x, const Input& u, const std::array<double, 7>& dq_prev, const std::array<double, 7>& dq_next,
+                                                         const State& x_next, const double* rb150, int k) {
+        std::array<double, MPCC_STAGE_LIN_DOUBLES> out;
+        const int32_t kk = k;
+        check(mpcc_cuda_eval_stage(h_, &x.q1, &u.dq1, dq_prev.data(), dq_next.data(), &x_next.q1, rb150, &kk, 1, out.data()));
+        return out;
+    }
     void reset() { check(mpcc_cuda_reset(h_)); }
     double getTrackLength(int track = 0) const { return track_len_.at(track); }
     int batch() const { return B_; }
@@ -179,6 +188,45 @@ public:
     std::array<double, 42> getJacobian(const std::array<double, 7>& q) { auto rb = o_->robotData({q}); std::array<double, 42> J; for (int i = 0; i < 42; i++) J[i] = rb[19 + i]; return J; }  // [Jv; Jw]
     double getManipulability(const std::array<double, 7>& q) { return o_->robotData({q})[61]; }
     std::array<double, 7> getDManipulability(const std::array<double, 7>& q) { auto rb = o_->robotData({q}); std::array<double, 7> d; for (int i = 0; i < 7; i++) d[i] = rb[62 + i]; return d; }
+private:
+    BatchMPC* o_;
+};
+
+// Views of one stage linearisation in the reference's vocabulary (normalised by T_x / T_u, i.e. what the QP sees).
+// Cost::getCost (cost.cpp:290-357): value, gradient, Gauss-Newton Hessian;  Constraints::getConstraints
+// (constraints.cpp:192-243): the 11 polytopic rows c + C dx + D du <= 0 as gradients, RBF slopes and right-hand sides.
+struct CostGrad { std::array<double, 9> f_x; std::array<double, 8> f_u; };
+struct CostHess { std::array<double, 81> f_xx; std::array<double, 8> f_uu_diag; };
+struct ConstraintsInfo { std::array<double, 11> rhs; std::array<double, 77> grad_h; std::array<double, 11> drbf; double l1_violation; };
+class Cost {
+public:
+    explicit Cost(BatchMPC* owner) : o_(owner) {}
+    double getCost(const State& x, const Input& u, const std::array<double, 7>& dq_prev, const std::array<double, 7>& dq_next, const State& x_next,
+                   const double* rb150, int k, CostGrad* grad, CostHess* hess) {
+        auto v = o_->evalStage(x, u, dq_prev, dq_next, x_next, rb150, k);
+        if (grad) { for (int i = 0; i < 9; i++) grad->f_x[i] = v[45 + i]; for (int j = 0; j < 8; j++) grad->f_u[j] = v[62 + j]; }
+        if (hess) {
+            int q = 0;
+            for (int r = 0; r < 9; r++) for (int c = 0; c <= r; c++) { hess->f_xx[9 * r + c] = hess->f_xx[9 * c + r] = v[q++]; }
+            for (int j = 0; j < 8; j++) hess->f_uu_diag[j] = v[54 + j];
+        }
+        return v[210];
+    }
+private:
+    BatchMPC* o_;
+};
+class Constraints {
+public:
+    explicit Constraints(BatchMPC* owner) : o_(owner) {}
+    ConstraintsInfo getConstraints(const State& x, const Input& u, const std::array<double, 7>& dq_prev, const std::array<double, 7>& dq_next, const State& x_next,
+                                   const double* rb150, int k) {
+        auto v = o_->evalStage(x, u, dq_prev, dq_next, x_next, rb150, k);
+        ConstraintsInfo c;
+        for (int i = 0; i < 77; i++) c.grad_h[i] = v[111 + i];
+        for (int j = 0; j < 11; j++) { c.drbf[j] = v[188 + j]; c.rhs[j] = v[199 + j]; }
+        c.l1_violation = v[211];
+        return c;
+    }
 private:
     BatchMPC* o_;
 };
