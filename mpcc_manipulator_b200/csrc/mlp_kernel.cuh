@@ -28,7 +28,7 @@ constexpr int MLP_KC = 16;                    // k-steps per weight chunk
 constexpr int MLP_CHUNK_D = MLP_KC * 256;     // doubles per chunk (32 KB)
 // chunk sequence of one tile: env L0 (2) L1 L2 L3 (16 each) | self L0 (2) L1 (4, K split over 4 thread groups)
 constexpr int MLP_NCHUNK = 2 + 48 + 2 + 4;    // 56
-constexpr size_t MLP_SMEM_BYTES = (size_t)(256 * 64 + 2 * MLP_CHUNK_D) * sizeof(double);  // 196608
+constexpr size_t MLP_SMEM_BYTES = (size_t)(256 * 64 + 2 * MLP_CHUNK_D + 9 * 256) * sizeof(double);  // 215040: X tile | weight ring | env output layer
 
 struct MlpArgs {
     const double* wpack;      // MLP_NCHUNK * MLP_CHUNK_D doubles, packed by pack_mlp_weights()
@@ -81,6 +81,8 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp(MlpArgs a) {
     double2* Xs = reinterpret_cast<double2*>(smem_raw);                              // [256 k][4 c4][8 tx]
     double2* Wbuf = reinterpret_cast<double2*>(smem_raw + 256 * 64 * sizeof(double));  // 2 x [2048 double2]
     double* Xd = reinterpret_cast<double*>(Xs);
+    double* Wout = reinterpret_cast<double*>(smem_raw + (256 * 64 + 2 * MLP_CHUNK_D) * sizeof(double));  // env output layer 9 x 256, resident
+    for (int i = threadIdx.x; i < 9 * 256; i += MLP_THREADS) Wout[i] = a.w_out_env[i];  // visible after the first __syncthreads() below
 
     const int tid = threadIdx.x;
     const int tx = tid & 7;         // sample within the tile
@@ -168,9 +170,9 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp(MlpArgs a) {
 #pragma unroll 4
                 for (int k = 0; k < 256; k++) {
                     const double xv = xcol[k * 64];
-                    o[0] = fma(__ldg(a.w_out_env + rg * 256 + k), xv, o[0]);
-                    o[1] = fma(__ldg(a.w_out_env + (rg + 4) * 256 + k), xv, o[1]);
-                    if (rg == 0) o[2] = fma(__ldg(a.w_out_env + 8 * 256 + k), xv, o[2]);
+                    o[0] = fma(Wout[rg * 256 + k], xv, o[0]);
+                    o[1] = fma(Wout[(rg + 4) * 256 + k], xv, o[1]);
+                    if (rg == 0) o[2] = fma(Wout[8 * 256 + k], xv, o[2]);
                 }
                 const int ns = tile * MLP_TILE_S + smp;
                 if (ns < a.NS) {
