@@ -88,6 +88,9 @@ int mpcc_load_params_json(const char* model_path, const char* cost_path, const c
 
 /* Track ingestion (Track::Track + ArcLengthSpline::gen6DSpline): waypoints -> table. R: n x 9 rotation matrices */
 int mpcc_fit_track(int32_t n, const double* X, const double* Y, const double* Z, const double* R, double* table_out);
+/* n_tracks fits at once on n_threads host threads (0: all cores): X, Y, Z [n_tracks][n], R [n_tracks][n][9] -> tables
+ * [n_tracks][MPCC_TRACK_DOUBLES].  For heterogeneous batches (one track per instance). */
+int mpcc_fit_tracks(int32_t n_tracks, int32_t n, const double* X, const double* Y, const double* Z, const double* R, double* tables_out, int32_t n_threads);
 int mpcc_load_track_json(const char* track_path, const double* init_position3 /* nullable */, double* table_out);
 /* tables: n_tracks x MPCC_TRACK_DOUBLES; track_of_instance: batch indices or NULL (all instances use track 0).
  * Invalidates every warm start (MPC::setTrack, mpc.cpp:192-197). */

@@ -17,7 +17,7 @@ EXPORTS = [
     "mpcc_cuda_run_cycle_device", "mpcc_cuda_read_results", "mpcc_cuda_result_pointers", "mpcc_cuda_stream", "mpcc_cuda_synchronize",
     "mpcc_cuda_get_warm_state", "mpcc_cuda_set_warm_state", "mpcc_cuda_sim_time_step", "mpcc_cuda_eval_robot_data", "mpcc_cuda_eval_stage",
     "mpcc_cuda_eval_track", "mpcc_cuda_solve_ocp", "mpcc_cuda_get_stats", "mpcc_cuda_sim_time_step_device", "mpcc_cuda_set_profiling",
-    "mpcc_cuda_get_kernel_times", "mpcc_cuda_fp64_peak", "mpcc_cuda_read_decisions", "mpcc_cuda_read_qp_counters", "mpcc_cuda_read_compute_time",
+    "mpcc_cuda_get_kernel_times", "mpcc_cuda_fp64_peak", "mpcc_cuda_read_decisions", "mpcc_fit_tracks", "mpcc_cuda_read_qp_counters", "mpcc_cuda_read_compute_time",
 ]
 
 
@@ -75,6 +75,15 @@ def fit_track(X, Y, Z, R):
     X, Y, Z, R = _f64(X), _f64(Y), _f64(Z), _f64(R)
     t = np.zeros(TRACK_DOUBLES)
     _check(lib().mpcc_fit_track(len(X), _p(X), _p(Y), _p(Z), _p(R), _p(t)))
+    return t
+
+
+def fit_tracks(X, Y, Z, R, n_threads=0):
+    """Bulk ArcLengthSpline::gen6DSpline: X, Y, Z [n_tracks][n], R [n_tracks][n][9] -> tables [n_tracks][TRACK_DOUBLES]."""
+    X, Y, Z, R = _f64(X), _f64(Y), _f64(Z), _f64(R)
+    nt, n = X.shape
+    t = np.zeros((nt, TRACK_DOUBLES))
+    _check(lib().mpcc_fit_tracks(nt, n, _p(X), _p(Y), _p(Z), _p(R), _p(t), n_threads))
     return t
 
 

@@ -18,6 +18,7 @@
 #include <string>
 #include <vector>
 #include <stdexcept>
+#include <thread>
 
 using namespace mpcc;
 
@@ -390,6 +391,30 @@ int mpcc_fit_track(int32_t n, const double* X, const double* Y, const double* Z,
     } catch (const std::exception& ex) {
         return fail(MPCC_ERR_INVALID, ex.what());
     }
+}
+
+// Bulk track ingestion for heterogeneous batches (configuration C4): n_tracks independent fits on the host cores.
+int mpcc_fit_tracks(int32_t n_tracks, int32_t n, const double* X, const double* Y, const double* Z, const double* R, double* tables_out, int32_t n_threads) {
+    if (!X || !Y || !Z || !R || !tables_out || n_tracks < 1 || n < 2) return fail(MPCC_ERR_INVALID, "bad argument");
+    unsigned hw = std::thread::hardware_concurrency();
+    int nt = n_threads > 0 ? n_threads : (int)(hw ? hw : 1);
+    if (nt > n_tracks) nt = n_tracks;
+    std::vector<std::string> errs(nt);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nt; t++)
+        pool.emplace_back([&, t]() {
+            try {
+                for (int i = t; i < n_tracks; i += nt) {
+                    Waypoints w;
+                    const size_t o = (size_t)i * n;
+                    w.X.assign(X + o, X + o + n); w.Y.assign(Y + o, Y + o + n); w.Z.assign(Z + o, Z + o + n); w.R.assign(R + 9 * o, R + 9 * (o + n));
+                    fit_track(w, *(TrackTable*)(tables_out + (size_t)i * TRACK_DOUBLES));
+                }
+            } catch (const std::exception& ex) { errs[t] = ex.what(); }
+        });
+    for (auto& th : pool) th.join();
+    for (auto& e : errs) if (!e.empty()) return fail(MPCC_ERR_INVALID, e);
+    return MPCC_OK;
 }
 
 int mpcc_load_track_json(const char* track_path, const double* init_position3, double* table_out) {

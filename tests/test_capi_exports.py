@@ -72,3 +72,16 @@ def test_create_argument_validation():
         assert lib.mpcc_cuda_create(C.byref(cfg), C.byref(h)) == 1  # MPCC_ERR_INVALID
         assert len(lib.mpcc_cuda_last_error()) > 0
     assert lib.mpcc_cuda_create(None, C.byref(h)) == 1
+
+
+def test_bulk_track_fit_matches_single_fits():
+    from mpcc_manipulator_b200 import capi
+    rng = np.random.default_rng(2)
+    nt, n = 37, 100
+    t = np.linspace(np.pi / 2, 5 * np.pi / 2, n)
+    a, b, c = rng.uniform(1.5, 3, nt), rng.uniform(1.5, 3, nt), rng.uniform(0, 2.5, nt)
+    X = 0.1 * a[:, None] * np.sin(t)[None] + 0.55; Y = 0.1 * b[:, None] * np.sin(2 * t)[None]; Z = 0.1 * c[:, None] * np.cos(t)[None] + 0.52
+    R = np.tile(np.diag([1., -1., -1.]).ravel(), (nt, n, 1))
+    tabs = capi.fit_tracks(X, Y, Z, R, n_threads=4)
+    for i in (0, 5, 36):
+        assert np.array_equal(tabs[i], capi.fit_track(X[i], Y[i], Z[i], R[i]))
