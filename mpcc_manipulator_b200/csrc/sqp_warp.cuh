@@ -112,7 +112,7 @@ constexpr int WC_SIZE = NPOLY * 14;   // cycle constants per stage: 11 normalise
 constexpr int WF_X = 0, WF_LAM = 64, WF_SIZE = 192;  // factor record: L^-1 (8 x 8, lower), Lam (8 x 16)
 // shared-memory scratch of one warp (doubles)
 constexpr int SC_P = 0, SC_PM = 256, SC_MNN = 512, SC_MNX = 576, SC_X = 704, SC_LAM = 768, SC_U = 896, SC_STG = 1092, SC_FF = 1668,
-              SC_VEC = 1740, SC_TXU = 1836, SC_DYN = 1854, SC_RED = 1872, SC_SIZE = 1936;
+              SC_VEC = 1740, SC_TXU = 1836, SC_DYN = 1854, SC_RED = 1872, SC_SIZE = 2032;  // RED: 5 x 32 per-lane accumulators
 // staged inputs of one stage of the factorisation (two slots, filled by asynchronous copies one stage ahead):
 // polytopic rows, their barrier weights, Q, Rd, box / rate barrier weights
 constexpr int SG_GS = 0, SG_WP = 154, SG_Q = 166, SG_RD = 247, SG_WB = 255, SG_WR = 273, SG_SIZE = 288;
@@ -121,7 +121,7 @@ constexpr int MAX_SQP_FILTER = 128;
 
 MPCC_HD size_t warp_ws_doubles(int N) {
     const size_t S = N + 1;
-    return S * (WL_SIZE + WC_SIZE + 7 * NINEQ + HZ /*G*/ + 8 /*KAP*/ + WF_SIZE + 2 * HZ /*persistent step, iterate*/ + 2 * NPOLY /*barrier values*/) + 2 * (MAX_SQP_FILTER + 2);
+    return S * (WL_SIZE + WC_SIZE + 8 * NINEQ + HZ /*G*/ + 8 /*KAP*/ + WF_SIZE + 2 * HZ /*persistent step, iterate*/ + 2 * NPOLY /*barrier values*/) + 2 * (MAX_SQP_FILTER + 2);
 }
 // the sweeps keep the gradient (17 S) and kappa (8 S) in the scratch below SC_VEC behind a 4-slot factor ring; longer
 // horizons get a separate block appended after the scratch
@@ -166,7 +166,7 @@ struct WarpSqp {
     QpOptions opt;
     Warp W;
     // per-instance global workspace
-    double *LIN, *CST, *IT, *ILAM, *IRP, *IW, *IV, *IDT, *IDLAM, *G, *KAP, *FACT, *SSTEP, *GUESS, *RBFV, *FILT;
+    double *LIN, *CST, *IT, *ILAM, *IRP, *IW, *IV, *IDT, *IDLAM, *IH, *G, *KAP, *FACT, *SSTEP, *GUESS, *RBFV, *FILT;
     // per-warp shared memory
     double *VAR, *STEP, *SC;
     // working copies between QP solves: the iterate (in the scratch) and the persistent step (in STEP); their homes
@@ -190,7 +190,7 @@ struct WarpSqp {
         LIN = gws; gws += S_ * WL_SIZE;
         CST = gws; gws += S_ * WC_SIZE;
         IT = gws; gws += S_ * NINEQ; ILAM = gws; gws += S_ * NINEQ; IRP = gws; gws += S_ * NINEQ; IW = gws; gws += S_ * NINEQ;
-        IV = gws; gws += S_ * NINEQ; IDT = gws; gws += S_ * NINEQ; IDLAM = gws; gws += S_ * NINEQ;
+        IV = gws; gws += S_ * NINEQ; IDT = gws; gws += S_ * NINEQ; IDLAM = gws; gws += S_ * NINEQ; IH = gws; gws += S_ * NINEQ;
         G = gws; gws += S_ * HZ; KAP = gws; gws += S_ * 8; FACT = gws; gws += S_ * WF_SIZE; SSTEP = gws; gws += S_ * HZ; GUESS = gws; gws += S_ * HZ; RBFV = gws; gws += S_ * 2 * NPOLY; FILT = gws;
         VAR = sm; STEP = sm + S_ * HZ; SC = sm + 2 * S_ * HZ;
         OR_ = 18 * S; OP_ = 32 * S;
@@ -274,6 +274,71 @@ struct WarpSqp {
             }
             f4(idx, g, h);
         }
+    }
+
+    // ---- streamed per-constraint passes ------------------------------------------------------------------------------
+    // The per-constraint vectors of an instance (t, lam, rp, ... : 43 S doubles each, global) are consumed in flat order.
+    // Instead of every lane waiting for its own loads round after round, tiles of consecutive items travel through a 3-slot
+    // ring in the (idle) factorisation scratch by asynchronous copies issued two tiles ahead, so that only the first tile of a
+    // pass exposes memory latency.  body(i, kind, k, c, v, j, row): constraint i (kind 0 box / 1 rate / 2 polytopic, stage k,
+    // row c), its staged inputs v[a * TS + j] for a < NA, and for polytopic rows the staged coefficient row (14 doubles).
+    template <int NA, int TS, bool ROWS, class F>
+    MPCC_HD void stream_range(const double* const (&A)[NA], int lo, int hi, F body) const {
+        constexpr int SLOT = NA * TS + (ROWS ? TS * 14 : 0);
+        static_assert(3 * SLOT <= SC_TXU, "ring must stay below the resident constants");
+        double* ring = SC;
+        const int ntiles = (hi - lo + TS - 1) / TS;
+        if (ntiles <= 0) return;
+        auto issue = [&](int lane, int t) {
+            if (t < ntiles) {
+                double* dst = ring + (t % 3) * SLOT;
+                const int base = lo + t * TS;
+                const int cnt = (hi - base < TS) ? hi - base : TS;
+#pragma unroll
+                for (int a = 0; a < NA; a++)
+                    for (int j = lane; j < cnt; j += 32) async_copy8(dst + a * TS + j, A[a] + base + j);
+                if (ROWS) {
+                    const double* src = CST + (size_t)(base - OP_) * 14;
+                    for (int e = lane; e < cnt * 14; e += 32) async_copy8(dst + NA * TS + e, src + e);
+                }
+            }
+            async_commit();
+        };
+        W.each([&](int lane) { issue(lane, 0); issue(lane, 1); async_wait<1>(); });  // tile 0 has landed
+        for (int t = 0; t < ntiles; t++) {
+            W.each([&](int lane) {
+                issue(lane, t + 2);  // into the slot consumed in the previous phase
+                const double* v = ring + (t % 3) * SLOT;
+                const int base = lo + t * TS;
+                const int cnt = (hi - base < TS) ? hi - base : TS;
+                for (int j = lane; j < cnt; j += 32) {
+                    const int i = base + j;
+                    int kind, k, c;
+                    if (ROWS) { kind = 2; k = (i - OP_) / NPOLY; c = (i - OP_) - k * NPOLY; }
+                    else if (i < OR_) { kind = 0; k = i / 18; c = i - k * 18; }
+                    else { kind = 1; k = (i - OR_) / 14; c = (i - OR_) - k * 14; }
+                    body(lane, i, kind, k, c, v, j, ROWS ? v + NA * TS + j * 14 : nullptr);
+                }
+                async_wait<1>();  // pending: tiles t+1, t+2 -> tile t+1 has landed
+            });
+        }
+        W.each([&](int) { async_wait<0>(); });
+    }
+    // all PRESENT constraints: box and rate rows are adjacent in the vectors ([18, 18 S + 14 N)), polytopic rows [OP_, OP_ + 11 N)
+    template <int NA, class F>
+    MPCC_HD void stream_constraints(const double* const (&A)[NA], F body) const {
+        stream_range<NA, 96, false>(A, 18, OR_ + 14 * N, body);
+        stream_range<NA, 32, true>(A, OP_, OP_ + NPOLY * N, body);
+    }
+    // G z of constraint (kind, k, c) on a [S][17] vector in shared memory; polytopic rows use the staged coefficient row
+    MPCC_HD double gz_of(const double* Z, int kind, int k, int c, const double* row) const {
+        if (kind == 0) return gz_box(Z, k, c);
+        if (kind == 1) return gz_rate(Z, k, c);
+        const double* z = Z + k * HZ;
+        double s = 0;
+#pragma unroll
+        for (int m = 0; m < DOF; m++) s += row[m] * z[m] + row[7 + m] * z[NX + m];
+        return s;
     }
 
     // ---- gradient of the step QP: G <- H z + f + G'(IV); dst0 (shared) <- same with multipliers ILAM ----
@@ -611,30 +676,33 @@ struct WarpSqp {
         W.each([&](int lane) { if (lane < NU) STEP[N * HZ + NX + lane] = 0.0; async_wait<0>(); });
     }
 
-    // slack / multiplier steps from the primal step; largest step keeping t, lam > 0
-    MPCC_HD double ineq_steps() const {
-        // the per-constraint vectors are disjoint arrays: loads may run ahead of the stores
-        const double* __restrict__ rp_ = IRP; const double* __restrict__ lam_ = ILAM; const double* __restrict__ v_ = IV;
-        const double* __restrict__ w_ = IW; const double* __restrict__ t_ = IT;
-        double* __restrict__ dt_ = IDT; double* __restrict__ dl_ = IDLAM;
-        return W.rmin([&](int lane) {
-            double a = 1.0;
-            for_present4(lane, STEP, false, [&](const int* idx, const double* g, const double*) {
-                double rp[4], lam[4], v[4], w[4], t[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) if (idx[u] >= 0) { const int i = idx[u]; rp[u] = rp_[i]; lam[u] = lam_[i]; v[u] = v_[i]; w[u] = w_[i]; t[u] = t_[i]; }
-#pragma unroll
-                for (int u = 0; u < 4; u++) if (idx[u] >= 0) {
-                    const int i = idx[u];
-                    const double dt = -rp[u] - g[u];
-                    const double dl = -lam[u] + v[u] + w[u] * g[u];
-                    dt_[i] = dt; dl_[i] = dl;
-                    if (dt < 0) a = fmin(a, -t[u] / dt);
-                    if (dl < 0) a = fmin(a, -lam[u] / dl);
-                }
-            });
-            return a;
+    // slack / multiplier steps from the primal step; largest step keeping t, lam > 0.  With sums != nullptr also returns
+    // s1 = sum(t dl + lam dt) and s2 = sum(dt dl), from which mu(alpha) = (sum t lam + alpha s1 + alpha^2 s2) / m follows.
+    MPCC_HD double ineq_steps(double* sums) const {
+        double* RED = SC + SC_RED;
+        W.each([&](int lane) { RED[lane] = 1.0; RED[32 + lane] = 0.0; RED[64 + lane] = 0.0; });
+        const double* const in[5] = {IRP, ILAM, IV, IW, IT};
+        double* dt_ = IDT; double* dl_ = IDLAM;
+        stream_constraints<5>(in, [&](int lane, int i, int kind, int k, int c, const double* v, int j, const double* row) {
+            constexpr int TSB = 96, TSP = 32;
+            const int ts = (kind == 2) ? TSP : TSB;
+            const double rp = v[j], lam = v[ts + j], vv = v[2 * ts + j], w = v[3 * ts + j], t = v[4 * ts + j];
+            const double g = gz_of(STEP, kind, k, c, row);
+            const double dt = -rp - g;
+            const double dl = -lam + vv + w * g;
+            dt_[i] = dt; dl_[i] = dl;
+            double a = RED[lane];
+            if (dt < 0) a = fmin(a, -t / dt);
+            if (dl < 0) a = fmin(a, -lam / dl);
+            RED[lane] = a;
+            RED[32 + lane] += t * dl + lam * dt;
+            RED[64 + lane] += dt * dl;
         });
+        if (sums) {
+            sums[0] = W.rsum([&](int lane) { return RED[32 + lane]; });
+            sums[1] = W.rsum([&](int lane) { return RED[64 + lane]; });
+        }
+        return W.rmin([&](int lane) { return RED[lane]; });
     }
 
     // ---- interior-point loop; on success VAR holds the step (xi = exact rollout of nu) ----
@@ -677,35 +745,30 @@ struct WarpSqp {
             for (int i = lane; i < tot; i += 32) { IT[i] = 1.0; ILAM[i] = 0.0; IW[i] = 0.0; IV[i] = 0.0; IRP[i] = 0.0; IDT[i] = 0.0; IDLAM[i] = 0.0; }
         });
         W.each([&](int lane) {
-            for_present(lane, VAR, true, [&](int i, double g, double h) { IT[i] = fmax(h - g, 1.0); ILAM[i] = 1.0; });
+            for_present(lane, VAR, true, [&](int i, double g, double h) { IT[i] = fmax(h - g, 1.0); ILAM[i] = 1.0; IH[i] = h; });
         });
         const double m_tot = 43.0 * N;
         for (int it = 0; it < opt.max_iter; it++) {
             // residuals, barrier weights, predictor v = lam rp / t
-            const double* __restrict__ t_ = IT; const double* __restrict__ lam_ = ILAM;
-            double* __restrict__ rp_ = IRP; double* __restrict__ w_ = IW; double* __restrict__ v_ = IV;
-            const double nrp = W.rmax([&](int lane) {
-                double nr = 0, mu_p = 0;
-                for_present4(lane, VAR, true, [&](const int* idx, const double* g, const double* h) {
-                    double t[4], lam[4];
-#pragma unroll
-                    for (int u = 0; u < 4; u++) if (idx[u] >= 0) { t[u] = t_[idx[u]]; lam[u] = lam_[idx[u]]; }
-#pragma unroll
-                    for (int u = 0; u < 4; u++) if (idx[u] >= 0) {
-                        const int i = idx[u];
-                        const double rp = g[u] + t[u] - h[u];
-                        rp_[i] = rp;
-                        nr = fmax(nr, fabs(rp));
-                        mu_p += t[u] * lam[u];
-                        const double w = lam[u] / t[u];
-                        w_[i] = w;
-                        v_[i] = w * rp;
-                    }
+            W.each([&](int lane) { RED[lane] = 0.0; RED[32 + lane] = 0.0; });
+            {
+                const double* const in[3] = {IT, ILAM, IH};
+                double* rp_ = IRP; double* w_ = IW; double* v_ = IV;
+                stream_constraints<3>(in, [&](int lane, int i, int kind, int k, int c, const double* v, int j, const double* row) {
+                    const int ts = (kind == 2) ? 32 : 96;
+                    const double t = v[j], lam = v[ts + j], h = v[2 * ts + j];
+                    const double rp = gz_of(VAR, kind, k, c, row) + t - h;
+                    rp_[i] = rp;
+                    RED[lane] = fmax(RED[lane], fabs(rp));
+                    RED[32 + lane] += t * lam;
+                    const double w = lam / t;
+                    w_[i] = w;
+                    v_[i] = w * rp;
                 });
-                RED[lane] = mu_p;
-                return nr;
-            });
-            const double mu = W.rsum([&](int lane) { return RED[lane]; }) / m_tot;
+            }
+            const double nrp = W.rmax([&](int lane) { return RED[lane]; });
+            const double sum_tl = W.rsum([&](int lane) { return RED[32 + lane]; });
+            const double mu = sum_tl / m_tot;
             gradient(STEP);  // G <- predictor gradient; STEP <- Lagrangian gradient (scratch until the step is computed)
             // costates: in-place suffix recursion p_k = g_k + A' p_{k+1} on the xi part of STEP
             W.each([&](int lane) {
@@ -729,34 +792,33 @@ struct WarpSqp {
             if (!(nrd == nrd) || !(mu == mu)) break;
             if (!factor()) break;
             solve_step();
-            const double a_aff = ineq_steps();
-            const double mu_aff = W.rsum([&](int lane) {
-                double s = 0;
-                for (int i = lane; i < tot; i += 32) s += (IT[i] + a_aff * IDT[i]) * (ILAM[i] + a_aff * IDLAM[i]);  // absent: (1)(0)
-                return s;
-            }) / m_tot;
+            double sums[2];
+            const double a_aff = ineq_steps(sums);
+            const double mu_aff = (sum_tl + a_aff * sums[0] + a_aff * a_aff * sums[1]) / m_tot;
             const double sigma = (mu > 0) ? (mu_aff / mu) * (mu_aff / mu) * (mu_aff / mu) : 0.0;
             // corrector: v = (lam rp + sigma mu - dt_a dlam_a) / t
-            W.each([&](int lane) {
+            {
                 const double sm = sigma * mu;
-                const double* __restrict__ cl = ILAM; const double* __restrict__ crp = IRP; const double* __restrict__ cdt = IDT;
-                const double* __restrict__ cdl = IDLAM; const double* __restrict__ ct = IT; double* __restrict__ cv = IV;
-#pragma unroll 4
-                for (int i = 18 + lane; i < 18 * S; i += 32) cv[i] = (cl[i] * crp[i] + sm - cdt[i] * cdl[i]) / ct[i];
-#pragma unroll 4
-                for (int i = OR_ + lane; i < OR_ + 14 * N; i += 32) cv[i] = (cl[i] * crp[i] + sm - cdt[i] * cdl[i]) / ct[i];
-#pragma unroll 4
-                for (int i = OP_ + lane; i < OP_ + NPOLY * N; i += 32) cv[i] = (cl[i] * crp[i] + sm - cdt[i] * cdl[i]) / ct[i];
-            });
+                const double* const in[5] = {ILAM, IRP, IDT, IDLAM, IT};
+                double* v_ = IV;
+                stream_constraints<5>(in, [&](int, int i, int kind, int, int, const double* v, int j, const double*) {
+                    const int ts = (kind == 2) ? 32 : 96;
+                    v_[i] = (v[j] * v[ts + j] + sm - v[2 * ts + j] * v[3 * ts + j]) / v[4 * ts + j];
+                });
+            }
             gradient(nullptr);
             solve_step();
-            const double a = fmin(1.0, 0.995 * ineq_steps());
-            W.each([&](int lane) {
-                for (int o = lane; o < S * HZ; o += 32) VAR[o] += a * STEP[o];
-                double* __restrict__ ut = IT; double* __restrict__ ul = ILAM; const double* __restrict__ udt = IDT; const double* __restrict__ udl = IDLAM;
-#pragma unroll 4
-                for (int i = lane; i < tot; i += 32) { ut[i] += a * udt[i]; ul[i] += a * udl[i]; }  // absent: dt = dl = 0
-            });
+            const double a = fmin(1.0, 0.995 * ineq_steps(nullptr));
+            W.each([&](int lane) { for (int o = lane; o < S * HZ; o += 32) VAR[o] += a * STEP[o]; });
+            {
+                const double* const in[4] = {IT, ILAM, IDT, IDLAM};
+                double* t_ = IT; double* l_ = ILAM;
+                stream_constraints<4>(in, [&](int, int i, int kind, int, int, const double* v, int j, const double*) {
+                    const int ts = (kind == 2) ? 32 : 96;
+                    t_[i] = v[j] + a * v[2 * ts + j];
+                    l_[i] = v[ts + j] + a * v[3 * ts + j];
+                });
+            }
             st.iters = it + 1;
         }
         if (st.ok) {
