@@ -13,9 +13,18 @@
 // Mapping.  One persistent CTA per SM walks over tiles of 8 samples = 64 columns.  The activation
 // tile X (256 x 64 doubles, 128 KB) stays in shared memory across all layers of both networks; the
 // weights stream from L2 through a double-buffered 2 x 32 KB shared-memory ring with cp.async, in
-// chunks pre-packed on the host in exactly the order the threads read them.  Each thread owns an
-// 8 (neurons) x 8 (columns of ONE sample) register tile, so the ReLU mask is thread-local.
-// The work is a dense fp64 contraction: tcgen05 has no f64 kind, so the DFMA pipe is the roof.
+// chunks pre-packed on the host in exactly the order the lanes read them.
+// The contraction runs on the FP64 tensor path, mma.sync.m8n8k4.f64 (DMMA): tcgen05 has no f64 kind,
+// and on sm_100 DMMA and DFMA share one pipe of the same peak (tools/probes/fp64_pipes_probe.cu) --
+// what DMMA buys is operand traffic: a warp owns 32 neurons x 64 columns as 4 x 8 fragments and needs
+// 6 LDS.128 per 32 DMMA (= 256 MAC per lane), where an 8x8 DFMA register tile needs 32 LDS.128 for the
+// same 256 DFMA and loses ~20 % of the pipe to them (tools/probes/mlp_loop_probe.cu, mlp_mma_probe.cu).
+// An n-fragment is one column KIND (value or tangent j) of the 8 samples, so a lane's accumulators for
+// a neuron hold all 8 columns of its two samples and the ReLU mask stays thread-local.
+//
+// Shared layout of X ("fragment order"): element (k, c, s) = neuron k, column c, sample s sits at double
+//     (((k >> 2) * 4 + (c >> 1)) * 32 + (s * 4 + (k & 3))) * 2 + (c & 1)
+// so the B fragments of 4 k-steps x 2 columns are ONE conflict-free LDS.128 per lane.
 #pragma once
 #include "mpcc_types.h"
 #include <cuda_runtime.h>
@@ -24,9 +33,9 @@ namespace mpcc {
 
 constexpr int MLP_THREADS = 256;
 constexpr int MLP_TILE_S = 8;                 // samples per tile
-constexpr int MLP_KC = 16;                    // k-steps per weight chunk
+constexpr int MLP_KC = 16;                    // k-steps per weight chunk of a 256-neuron layer
 constexpr int MLP_CHUNK_D = MLP_KC * 256;     // doubles per chunk (32 KB)
-// chunk sequence of one tile: env L0 (2) L1 L2 L3 (16 each) | self L0 (2) L1 (4, K split over 4 thread groups)
+// chunk sequence of one tile: env L0 (2) L1 L2 L3 (16 each) | self L0 (2) L1 (4 chunks of 64 k-steps x 64 neurons)
 constexpr int MLP_NCHUNK = 2 + 48 + 2 + 4;    // 56
 constexpr size_t MLP_SMEM_BYTES = (size_t)(256 * 64 + 2 * MLP_CHUNK_D + 9 * 256) * sizeof(double);  // 215040: X tile | weight ring | env output layer
 
@@ -54,41 +63,49 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
-// one 16-k-step chunk of the 8x8 register-tile contraction.
-//   Wb: chunk buffer as double2; thread reads Wb[(kk*WSTR_K + wofs) + i*WSTR_I]  for i = 0..3
-//   Xs: activation tile as double2; thread reads Xs[((k0+kk)*4 + c4)*8 + tx] for c4 = 0..3
-template <int WSTR_K, int WSTR_I>
-__device__ __forceinline__ void mlp_chunk(const double2* __restrict__ Wb, int wofs, const double2* __restrict__ Xs, int k0, int tx,
-                                          int ksteps, double (&acc)[8][8]) {
-#pragma unroll 4
-    for (int kk = 0; kk < ksteps; kk++) {
-        double2 w2[4], x2[4];
+// D (8x8) += A (8x4, row) * B (4x8, col) in fp64.  Lane l holds A[l >> 2][l & 3], B[l & 3][l >> 2], D[l >> 2][2 (l & 3) + {0, 1}].
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// double2 slot of X element (k, column pair j, sample s) in the fragment-ordered tile
+__device__ __forceinline__ int xl2(int k, int j, int s) { return ((k >> 2) * 4 + j) * 32 + s * 4 + (k & 3); }
+
+// one 16-k-step chunk of a 256-neuron layer: the warp's 32 neurons (4 m-fragments) x 64 columns (8 n-fragments).
+//   Wc: chunk as double2 [kb 4][warp 8][m-pair 2][lane 32]   Xs: activation tile, kb0 = first 4-k block of the chunk
+__device__ __forceinline__ void mlp_chunk(const double2* __restrict__ Wc, const double2* __restrict__ Xs, int kb0, int warp, int lane,
+                                          double (&acc)[4][8][2]) {
 #pragma unroll
-        for (int i = 0; i < 4; i++) w2[i] = Wb[kk * WSTR_K + wofs + i * WSTR_I];
+    for (int kb = 0; kb < MLP_KC / 4; kb++) {
+        const double2 a01 = Wc[((kb * 8 + warp) * 2 + 0) * 32 + lane], a23 = Wc[((kb * 8 + warp) * 2 + 1) * 32 + lane];
+        double2 b[4];
 #pragma unroll
-        for (int c = 0; c < 4; c++) x2[c] = Xs[((k0 + kk) * 4 + c) * 8 + tx];
-        double w[8] = {w2[0].x, w2[0].y, w2[1].x, w2[1].y, w2[2].x, w2[2].y, w2[3].x, w2[3].y};
-        double x[8] = {x2[0].x, x2[0].y, x2[1].x, x2[1].y, x2[2].x, x2[2].y, x2[3].x, x2[3].y};
+        for (int j = 0; j < 4; j++) b[j] = Xs[((kb0 + kb) * 4 + j) * 32 + lane];
+        const double a[4] = {a01.x, a01.y, a23.x, a23.y};
 #pragma unroll
-        for (int r = 0; r < 8; r++)
+        for (int mb = 0; mb < 4; mb++)
 #pragma unroll
-            for (int c = 0; c < 8; c++) acc[r][c] = fma(w[r], x[c], acc[r][c]);
+            for (int j = 0; j < 4; j++) {
+                dmma884(acc[mb][2 * j][0], acc[mb][2 * j][1], a[mb], b[j].x);
+                dmma884(acc[mb][2 * j + 1][0], acc[mb][2 * j + 1][1], a[mb], b[j].y);
+            }
     }
 }
 
 __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp(MlpArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double2* Xs = reinterpret_cast<double2*>(smem_raw);                              // [256 k][4 c4][8 tx]
+    double2* Xs = reinterpret_cast<double2*>(smem_raw);                              // fragment-ordered activation tile
     double2* Wbuf = reinterpret_cast<double2*>(smem_raw + 256 * 64 * sizeof(double));  // 2 x [2048 double2]
     double* Xd = reinterpret_cast<double*>(Xs);
-    double* Wout = reinterpret_cast<double*>(smem_raw + (256 * 64 + 2 * MLP_CHUNK_D) * sizeof(double));  // env output layer 9 x 256, resident
-    for (int i = threadIdx.x; i < 9 * 256; i += MLP_THREADS) Wout[i] = a.w_out_env[i];  // visible after the first __syncthreads() below
+    // env output layer (9 x 256), resident, as A fragments: rows 0..7 [kb 64][lane 32] | row 8 [256]
+    double* Wo0 = reinterpret_cast<double*>(smem_raw + (256 * 64 + 2 * MLP_CHUNK_D) * sizeof(double));
+    double* Wo1 = Wo0 + 8 * 256;
+    for (int i = threadIdx.x; i < 8 * 256; i += MLP_THREADS) Wo0[i] = a.w_out_env[((i & 31) >> 2) * 256 + (i >> 5) * 4 + (i & 3)];
+    for (int i = threadIdx.x; i < 256; i += MLP_THREADS) Wo1[i] = a.w_out_env[8 * 256 + i];  // visible after the first __syncthreads() below
 
-    const int tid = threadIdx.x;
-    const int tx = tid & 7;         // sample within the tile
-    const int ty = tid >> 3;        // mode A: row group 0..31
-    const int grp = tid >> 6;       // mode B: K group 0..3
-    const int tyb = (tid & 63) >> 3;  // mode B: row group 0..7
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int fr = lane >> 2, fq = lane & 3;  // fragment row / quad index
+    const int tx = tid & 7, ty = tid >> 3;    // input staging: sample, encoded row
 
     int p = 0;    // position in the chunk sequence
     int buf = 0;  // ring slot holding chunk p
@@ -99,23 +116,26 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp(MlpArgs a) {
         for (int i = 0; i < (MLP_CHUNK_D / 2) / MLP_THREADS; i++) cp_async16(dst + tid + i * MLP_THREADS, src + tid + i * MLP_THREADS);
         cp_async_commit();
     };
+    auto next_chunk = [&]() {  // chunk p has landed for everyone; start fetching p + 1 into the slot the previous chunk used
+        cp_async_wait_all();
+        __syncthreads();
+        prefetch((p + 1) % MLP_NCHUNK, buf ^ 1);
+    };
+    auto advance = [&]() { buf ^= 1; p = (p + 1) % MLP_NCHUNK; };
     if ((int)blockIdx.x < a.n_tiles) prefetch(0, 0);
 
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-        const int n = tile * MLP_TILE_S + tx;  // this thread's sample
-        const bool live = n < a.NS;
-        double acc[8][8];
-
+        const int s0 = tile * MLP_TILE_S;
         for (int net = 0; net < 2; net++) {  // 0: env, 1: self
             // ---- stage the encoded input X0 (32 rows) : row k = ty of sample tx ----
             __syncthreads();  // previous users of Xs are done
             {
                 const int nin = (net == 0) ? 10 : 7;  // raw inputs; encoded rows = 3 * nin
-                const int k = ty;
+                const int k = ty, n = s0 + tx;
                 double v[8];
 #pragma unroll
                 for (int c = 0; c < 8; c++) v[c] = 0.0;
-                if (live && k < 3 * nin) {
+                if (n < a.NS && k < 3 * nin) {
                     const int src = k % nin, kind = k / nin;  // kind 0: x, 1: sin x, 2: cos x
                     double xin;
                     if (src < 7) xin = a.qs[(size_t)src * a.NS + n];
@@ -126,131 +146,133 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp(MlpArgs a) {
                     if (src < 7) v[1 + src] = (kind == 0) ? 1.0 : (kind == 1 ? cs : -sn);
                 }
 #pragma unroll
-                for (int c4 = 0; c4 < 4; c4++) Xs[(k * 4 + c4) * 8 + tx] = make_double2(v[2 * c4], v[2 * c4 + 1]);
+                for (int j = 0; j < 4; j++) Xs[xl2(k, j, tx)] = make_double2(v[2 * j], v[2 * j + 1]);
             }
-            const int n_hidden = (net == 0) ? 4 : 1;  // mode-A layers producing 256 neurons
+            const int n_hidden = (net == 0) ? 4 : 1;  // layers producing 256 neurons
             for (int layer = 0; layer < n_hidden; layer++) {
+                double acc[4][8][2];
 #pragma unroll
-                for (int r = 0; r < 8; r++)
+                for (int mb = 0; mb < 4; mb++)
 #pragma unroll
-                    for (int c = 0; c < 8; c++) acc[r][c] = 0.0;
+                    for (int c = 0; c < 8; c++) acc[mb][c][0] = acc[mb][c][1] = 0.0;
                 const int nch = (layer == 0) ? 2 : 16;
                 for (int ch = 0; ch < nch; ch++) {
-                    cp_async_wait_all();
-                    __syncthreads();
-                    prefetch((p + 1) % MLP_NCHUNK, buf ^ 1);
-                    mlp_chunk<4 * 32, 32>(Wbuf + buf * (MLP_CHUNK_D / 2), ty, Xs, ch * MLP_KC, tx, MLP_KC, acc);
-                    buf ^= 1;
-                    p = (p + 1) % MLP_NCHUNK;
+                    next_chunk();
+                    mlp_chunk(Wbuf + buf * (MLP_CHUNK_D / 2), Xs, ch * (MLP_KC / 4), warp, lane, acc);
+                    advance();
                 }
                 // bias + ReLU mask, then the tile becomes the next layer's input
                 const double* bias = a.bias + ((net == 0) ? (MLP_BIAS_ENV + layer * 256) : MLP_BIAS_SELF0);
+                double bv[4];
+#pragma unroll
+                for (int mb = 0; mb < 4; mb++) bv[mb] = bias[warp * 32 + mb * 8 + fr];
                 __syncthreads();  // everyone finished reading Xs
 #pragma unroll
-                for (int i = 0; i < 4; i++)
+                for (int mb = 0; mb < 4; mb++)
 #pragma unroll
                     for (int e = 0; e < 2; e++) {
-                        const int r = i * 2 + e, row = i * 64 + ty * 2 + e;
-                        const double pre = acc[r][0] + bias[row];
+                        const int row = warp * 32 + mb * 8 + fr, s = 2 * fq + e;
+                        const double pre = acc[mb][0][e] + bv[mb];
                         const bool on = pre > 0.0;
 #pragma unroll
-                        for (int c4 = 0; c4 < 4; c4++) {
-                            double v0 = (c4 == 0) ? pre : acc[r][2 * c4];
-                            double v1 = acc[r][2 * c4 + 1];
-                            Xs[(row * 4 + c4) * 8 + tx] = on ? make_double2(v0, v1) : make_double2(0.0, 0.0);
+                        for (int j = 0; j < 4; j++) {
+                            const double v0 = (j == 0) ? pre : acc[mb][2 * j][e], v1 = acc[mb][2 * j + 1][e];
+                            Xs[xl2(row, j, s)] = on ? make_double2(v0, v1) : make_double2(0.0, 0.0);
                         }
                     }
             }
             if (net == 0) {
-                // ---- env output layer: 9 x 256, value + 7 tangents ----
+                // ---- env output layer: 9 x 256 as two m-fragments (rows 0..7, row 8); warp = column kind ----
                 __syncthreads();
-                const int col = tid & 63, smp = col >> 3, cc = col & 7, rg = tid >> 6;
-                double o[3] = {0.0, 0.0, 0.0};
-                const double* xcol = Xd + ((cc >> 1) * 8 + smp) * 2 + (cc & 1);
+                double o[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};  // [k parity][m-fragment][sample]
+                const double* xb = Xd + ((warp >> 1) * 32 + lane) * 2 + (warp & 1);
 #pragma unroll 4
-                for (int k = 0; k < 256; k++) {
-                    const double xv = xcol[k * 64];
-                    o[0] = fma(Wout[rg * 256 + k], xv, o[0]);
-                    o[1] = fma(Wout[(rg + 4) * 256 + k], xv, o[1]);
-                    if (rg == 0) o[2] = fma(Wout[8 * 256 + k], xv, o[2]);
-                }
-                const int ns = tile * MLP_TILE_S + smp;
-                if (ns < a.NS) {
+                for (int kb = 0; kb < 64; kb += 2) {
 #pragma unroll
-                    for (int j = 0; j < 3; j++) {
-                        const int l = rg + 4 * j;
-                        if (l < 9 && (j < 2 || rg == 0)) {
-                            if (cc == 0) a.rb[(size_t)(RB_ENV + l) * a.NS + ns] = o[j] + a.bias[MLP_BIAS_ENV_OUT + l];
-                            else a.rb[(size_t)(RB_DENV + l * 7 + (cc - 1)) * a.NS + ns] = o[j];
+                    for (int h = 0; h < 2; h++) {
+                        const double bx = xb[(kb + h) * 256];
+                        const double a0 = Wo0[(kb + h) * 32 + lane], a1 = (lane < 4) ? Wo1[(kb + h) * 4 + lane] : 0.0;
+                        dmma884(o[h][0][0], o[h][0][1], a0, bx);
+                        dmma884(o[h][1][0], o[h][1][1], a1, bx);
+                    }
+                }
+#pragma unroll
+                for (int mb = 0; mb < 2; mb++)
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        const int l = mb * 8 + fr, ns = s0 + 2 * fq + e;
+                        if (l < 9 && ns < a.NS) {
+                            const double v = o[0][mb][e] + o[1][mb][e];
+                            if (warp == 0) a.rb[(size_t)(RB_ENV + l) * a.NS + ns] = v + a.bias[MLP_BIAS_ENV_OUT + l];
+                            else a.rb[(size_t)(RB_DENV + l * 7 + (warp - 1)) * a.NS + ns] = v;
                         }
                     }
-                    if (tid < 8 && (tile * MLP_TILE_S + tid) < a.NS) {
-                        const int n2 = tile * MLP_TILE_S + tid;
-                        a.rb[(size_t)RB_OBSR * a.NS + n2] = a.obs[(size_t)(n2 / a.S) * 4 + 3];
-                    }
+                if (tid < 8 && (s0 + tid) < a.NS) {
+                    const int n2 = s0 + tid;
+                    a.rb[(size_t)RB_OBSR * a.NS + n2] = a.obs[(size_t)(n2 / a.S) * 4 + 3];
                 }
             } else {
-                // ---- self layer 1: 64 x 256, K split over the 4 thread groups (64 k each) ----
+                // ---- self layer 1: 64 x 256; warp = m-fragment (8 neurons) x all 8 column kinds, full K ----
+                double acc[8][2];
 #pragma unroll
-                for (int r = 0; r < 8; r++)
-#pragma unroll
-                    for (int c = 0; c < 8; c++) acc[r][c] = 0.0;
+                for (int c = 0; c < 8; c++) acc[c][0] = acc[c][1] = 0.0;
                 for (int ch = 0; ch < 4; ch++) {
-                    cp_async_wait_all();
-                    __syncthreads();
-                    prefetch((p + 1) % MLP_NCHUNK, buf ^ 1);
-                    mlp_chunk<4 * 4 * 8, 8>(Wbuf + buf * (MLP_CHUNK_D / 2), grp * 32 + tyb, Xs, grp * 64 + ch * MLP_KC, tx, MLP_KC, acc);
-                    buf ^= 1;
-                    p = (p + 1) % MLP_NCHUNK;
-                }
-                __syncthreads();  // done reading Xs: reuse it as reduction scratch [3][64 threads][64]
-                if (grp > 0) {
-                    double* dst = Xd + ((size_t)(grp - 1) * 64 + (tid & 63)) * 64;
+                    next_chunk();
+                    const double2* Wc = Wbuf + buf * (MLP_CHUNK_D / 2);  // [kb pair 8][warp 8][lane 32] -> {kb even, kb odd}
+#pragma unroll 2
+                    for (int kp = 0; kp < 8; kp++) {
+                        const double2 a2 = Wc[(kp * 8 + warp) * 32 + lane];
 #pragma unroll
-                    for (int r = 0; r < 8; r++)
+                        for (int h = 0; h < 2; h++) {
+                            const int kb = ch * 16 + kp * 2 + h;
+                            double2 b[4];
 #pragma unroll
-                        for (int c = 0; c < 8; c++) dst[r * 8 + c] = acc[r][c];
-                }
-                __syncthreads();
-                if (grp == 0) {
+                            for (int j = 0; j < 4; j++) b[j] = Xs[(kb * 4 + j) * 32 + lane];
+                            const double av = h ? a2.y : a2.x;
 #pragma unroll
-                    for (int g2 = 0; g2 < 3; g2++) {
-                        const double* src = Xd + ((size_t)g2 * 64 + tid) * 64;
-#pragma unroll
-                        for (int r = 0; r < 8; r++)
-#pragma unroll
-                            for (int c = 0; c < 8; c++) acc[r][c] += src[r * 8 + c];
-                    }
-                }
-                __syncthreads();  // scratch consumed
-                if (grp == 0) {
-#pragma unroll
-                    for (int i = 0; i < 4; i++)
-#pragma unroll
-                        for (int e = 0; e < 2; e++) {
-                            const int r = i * 2 + e, row = i * 16 + tyb * 2 + e;
-                            const double pre = acc[r][0] + a.bias[MLP_BIAS_SELF1 + row];
-                            const bool on = pre > 0.0;
-#pragma unroll
-                            for (int c4 = 0; c4 < 4; c4++) {
-                                double v0 = (c4 == 0) ? pre : acc[r][2 * c4];
-                                double v1 = acc[r][2 * c4 + 1];
-                                Xs[(row * 4 + c4) * 8 + tx] = on ? make_double2(v0, v1) : make_double2(0.0, 0.0);
+                            for (int j = 0; j < 4; j++) {
+                                dmma884(acc[2 * j][0], acc[2 * j][1], av, b[j].x);
+                                dmma884(acc[2 * j + 1][0], acc[2 * j + 1][1], av, b[j].y);
                             }
                         }
+                    }
+                    advance();
+                }
+                const double bv = a.bias[MLP_BIAS_SELF1 + warp * 8 + fr];
+                __syncthreads();  // done reading Xs: rows 0..63 become the layer's output
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int row = warp * 8 + fr, s = 2 * fq + e;
+                    const double pre = acc[0][e] + bv;
+                    const bool on = pre > 0.0;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const double v0 = (j == 0) ? pre : acc[2 * j][e], v1 = acc[2 * j + 1][e];
+                        Xs[xl2(row, j, s)] = on ? make_double2(v0, v1) : make_double2(0.0, 0.0);
+                    }
                 }
                 __syncthreads();
-                // ---- self output layer: 1 x 64 ----
-                if (tid < 64) {
-                    const int smp = tid >> 3, cc = tid & 7;
-                    const double* xcol = Xd + ((cc >> 1) * 8 + smp) * 2 + (cc & 1);
-                    double o = 0.0;
-#pragma unroll 8
-                    for (int k = 0; k < 64; k++) o = fma(__ldg(a.w_out_self + k), xcol[k * 64], o);
-                    const int ns = tile * MLP_TILE_S + smp;
-                    if (ns < a.NS) {
-                        if (cc == 0) a.rb[(size_t)RB_SEL * a.NS + ns] = o + a.bias[MLP_BIAS_SELF_OUT];
-                        else a.rb[(size_t)(RB_DSEL + cc - 1) * a.NS + ns] = o;
+                // ---- self output layer: 1 x 64, row 0 of one m-fragment; warp = column kind ----
+                {
+                    double o[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+                    const double* xb = Xd + ((warp >> 1) * 32 + lane) * 2 + (warp & 1);
+#pragma unroll
+                    for (int kb = 0; kb < 16; kb += 2)
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            const double av = (lane < 4) ? __ldg(a.w_out_self + (kb + h) * 4 + lane) : 0.0;
+                            dmma884(o[h][0], o[h][1], av, xb[(kb + h) * 256]);
+                        }
+                    if (lane < 4) {
+#pragma unroll
+                        for (int e = 0; e < 2; e++) {
+                            const int ns = s0 + 2 * lane + e;
+                            if (ns < a.NS) {
+                                const double v = o[0][e] + o[1][e];
+                                if (warp == 0) a.rb[(size_t)RB_SEL * a.NS + ns] = v + a.bias[MLP_BIAS_SELF_OUT];
+                                else a.rb[(size_t)(RB_DSEL + warp - 1) * a.NS + ns] = v;
+                            }
+                        }
                     }
                 }
             }
@@ -261,36 +283,37 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp(MlpArgs a) {
 
 #endif  // __CUDACC__
 
-// Host-side packing of both networks' hidden-layer weights into the chunk stream k_mlp consumes.
-//   mode A chunk (256 output rows, 16 k):  [kk][i][ty][e]  = W[i*64 + ty*2 + e][k0 + kk]
-//   mode B chunk (64 output rows, K split): [kk][g][i][ty'][e] = W[i*16 + ty'*2 + e][g*64 + ch*16 + kk]
+// Host-side packing of both networks' hidden-layer weights into the chunk stream k_mlp consumes (A fragments of
+// mma.m8n8k4: lane l holds neuron l >> 2 of its m-fragment at k-step l & 3 of the 4-k block).
+//   256-neuron layer, chunk = 16 k-steps:  [kb 4][warp 8][m-pair 2][lane 32][e 2]   = W[32 warp + (2 mp + e) 8 + (l >> 2)][k0 + 4 kb + (l & 3)]
+//   self layer 1 (64 neurons), chunk = 64 k-steps: [kb pair 8][warp 8][lane 32][h 2] = W[8 warp + (l >> 2)][64 ch + 4 (2 kp + h) + (l & 3)]
 // Layer 0 of each net is zero-padded from 30 / 21 encoded inputs to K = 32.
 inline void pack_mlp_weights(const double* const env_W[5], const double* const self_W[3], double* out) {
-    auto packA = [&](const double* W, int in_dim, int k_pad, double*& o) {
+    auto pack256 = [&](const double* W, int in_dim, int k_pad, double*& o) {
         for (int k0 = 0; k0 < k_pad; k0 += MLP_KC)
-            for (int kk = 0; kk < MLP_KC; kk++)
-                for (int i = 0; i < 4; i++)
-                    for (int ty = 0; ty < 32; ty++)
-                        for (int e = 0; e < 2; e++) {
-                            int row = i * 64 + ty * 2 + e, k = k0 + kk;
-                            *o++ = (k < in_dim) ? W[(size_t)row * in_dim + k] : 0.0;
-                        }
+            for (int kb = 0; kb < MLP_KC / 4; kb++)
+                for (int warp = 0; warp < 8; warp++)
+                    for (int mp = 0; mp < 2; mp++)
+                        for (int l = 0; l < 32; l++)
+                            for (int e = 0; e < 2; e++) {
+                                const int row = 32 * warp + (2 * mp + e) * 8 + (l >> 2), k = k0 + 4 * kb + (l & 3);
+                                *o++ = (k < in_dim) ? W[(size_t)row * in_dim + k] : 0.0;
+                            }
     };
     double* o = out;
-    packA(env_W[0], 30, 32, o);
-    packA(env_W[1], 256, 256, o);
-    packA(env_W[2], 256, 256, o);
-    packA(env_W[3], 256, 256, o);
-    packA(self_W[0], 21, 32, o);
+    pack256(env_W[0], 30, 32, o);
+    pack256(env_W[1], 256, 256, o);
+    pack256(env_W[2], 256, 256, o);
+    pack256(env_W[3], 256, 256, o);
+    pack256(self_W[0], 21, 32, o);
     for (int ch = 0; ch < 4; ch++)
-        for (int kk = 0; kk < MLP_KC; kk++)
-            for (int g = 0; g < 4; g++)
-                for (int i = 0; i < 4; i++)
-                    for (int ty = 0; ty < 8; ty++)
-                        for (int e = 0; e < 2; e++) {
-                            int row = i * 16 + ty * 2 + e, k = g * 64 + ch * MLP_KC + kk;
-                            *o++ = self_W[1][(size_t)row * 256 + k];
-                        }
+        for (int kp = 0; kp < 8; kp++)
+            for (int warp = 0; warp < 8; warp++)
+                for (int l = 0; l < 32; l++)
+                    for (int h = 0; h < 2; h++) {
+                        const int row = 8 * warp + (l >> 2), k = 64 * ch + 4 * (2 * kp + h) + (l & 3);
+                        *o++ = self_W[1][(size_t)row * 256 + k];
+                    }
 }
 
 }  // namespace mpcc
