@@ -23,8 +23,10 @@
 // a neuron hold all 8 columns of its two samples and the ReLU mask stays thread-local.
 //
 // Shared layout of X ("fragment order"): element (k, c, s) = neuron k, column c, sample s sits at double
-//     (((k >> 2) * 4 + (c >> 1)) * 32 + (s * 4 + (k & 3))) * 2 + (c & 1)
-// so the B fragments of 4 k-steps x 2 columns are ONE conflict-free LDS.128 per lane.
+//     (((k >> 2) * 4 + (c >> 1)) * 32 + slot(k & 3, s)) * 2 + (c & 1),   slot(q, s) = 8 (s >> 1) + ((q + 4 (s & 1) + 2 (s >> 1)) & 7)
+// so the B fragments of 4 k-steps x 2 columns are ONE LDS.128 per lane, and both that read (a quarter-warp holds
+// q = 0..3 of two adjacent samples) and the epilogue's D-fragment write-back (a quarter-warp holds two q of the four
+// samples of one parity) touch eight distinct 16-byte banks.
 #pragma once
 #include "mpcc_types.h"
 #include <cuda_runtime.h>
@@ -69,18 +71,20 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 }
 
 // double2 slot of X element (k, column pair j, sample s) in the fragment-ordered tile
-__device__ __forceinline__ int xl2(int k, int j, int s) { return ((k >> 2) * 4 + j) * 32 + s * 4 + (k & 3); }
+__device__ __forceinline__ int xslot(int q, int s) { return 8 * (s >> 1) + ((q + 4 * (s & 1) + 2 * (s >> 1)) & 7); }
+__device__ __forceinline__ int xl2(int k, int j, int s) { return ((k >> 2) * 4 + j) * 32 + xslot(k & 3, s); }
 
 // one 16-k-step chunk of a 256-neuron layer: the warp's 32 neurons (4 m-fragments) x 64 columns (8 n-fragments).
 //   Wc: chunk as double2 [kb 4][warp 8][m-pair 2][lane 32]   Xs: activation tile, kb0 = first 4-k block of the chunk
-__device__ __forceinline__ void mlp_chunk(const double2* __restrict__ Wc, const double2* __restrict__ Xs, int kb0, int warp, int lane,
+//   bslot = xslot(lane & 3, lane >> 2): where this lane's B-fragment element sits in a 32-slot row of Xs
+__device__ __forceinline__ void mlp_chunk(const double2* __restrict__ Wc, const double2* __restrict__ Xs, int kb0, int warp, int lane, int bslot,
                                           double (&acc)[4][8][2]) {
 #pragma unroll
     for (int kb = 0; kb < MLP_KC / 4; kb++) {
         const double2 a01 = Wc[((kb * 8 + warp) * 2 + 0) * 32 + lane], a23 = Wc[((kb * 8 + warp) * 2 + 1) * 32 + lane];
         double2 b[4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) b[j] = Xs[((kb0 + kb) * 4 + j) * 32 + lane];
+        for (int j = 0; j < 4; j++) b[j] = Xs[((kb0 + kb) * 4 + j) * 32 + bslot];
         const double a[4] = {a01.x, a01.y, a23.x, a23.y};
 #pragma unroll
         for (int mb = 0; mb < 4; mb++)
@@ -105,6 +109,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp(MlpArgs a) {
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int fr = lane >> 2, fq = lane & 3;  // fragment row / quad index
+    const int bslot = xslot(fq, fr);
     const int tx = tid & 7, ty = tid >> 3;    // input staging: sample, encoded row
 
     int p = 0;    // position in the chunk sequence
@@ -158,7 +163,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp(MlpArgs a) {
                 const int nch = (layer == 0) ? 2 : 16;
                 for (int ch = 0; ch < nch; ch++) {
                     next_chunk();
-                    mlp_chunk(Wbuf + buf * (MLP_CHUNK_D / 2), Xs, ch * (MLP_KC / 4), warp, lane, acc);
+                    mlp_chunk(Wbuf + buf * (MLP_CHUNK_D / 2), Xs, ch * (MLP_KC / 4), warp, lane, bslot, acc);
                     advance();
                 }
                 // bias + ReLU mask, then the tile becomes the next layer's input
@@ -185,7 +190,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp(MlpArgs a) {
                 // ---- env output layer: 9 x 256 as two m-fragments (rows 0..7, row 8); warp = column kind ----
                 __syncthreads();
                 double o[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};  // [k parity][m-fragment][sample]
-                const double* xb = Xd + ((warp >> 1) * 32 + lane) * 2 + (warp & 1);
+                const double* xb = Xd + ((warp >> 1) * 32 + bslot) * 2 + (warp & 1);
 #pragma unroll 4
                 for (int kb = 0; kb < 64; kb += 2) {
 #pragma unroll
@@ -227,7 +232,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp(MlpArgs a) {
                             const int kb = ch * 16 + kp * 2 + h;
                             double2 b[4];
 #pragma unroll
-                            for (int j = 0; j < 4; j++) b[j] = Xs[(kb * 4 + j) * 32 + lane];
+                            for (int j = 0; j < 4; j++) b[j] = Xs[(kb * 4 + j) * 32 + bslot];
                             const double av = h ? a2.y : a2.x;
 #pragma unroll
                             for (int j = 0; j < 4; j++) {
@@ -255,7 +260,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp(MlpArgs a) {
                 // ---- self output layer: 1 x 64, row 0 of one m-fragment; warp = column kind ----
                 {
                     double o[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-                    const double* xb = Xd + ((warp >> 1) * 32 + lane) * 2 + (warp & 1);
+                    const double* xb = Xd + ((warp >> 1) * 32 + bslot) * 2 + (warp & 1);
 #pragma unroll
                     for (int kb = 0; kb < 16; kb += 2)
 #pragma unroll
