@@ -6,9 +6,11 @@
 #if defined(__CUDACC__)
 #define MPCC_HD __host__ __device__ __forceinline__
 #define MPCC_HDN inline __host__ __device__
+#define MPCC_HDNI __host__ __device__ __noinline__   // one copy in the kernel image: keeps the instruction footprint of the hot loops small
 #else
 #define MPCC_HD inline
 #define MPCC_HDN inline
+#define MPCC_HDNI inline
 #endif
 
 namespace mpcc {

@@ -280,55 +280,64 @@ struct WarpSqp {
     // The per-constraint vectors of an instance (t, lam, rp, ... : 43 S doubles each, global) are consumed in flat order.
     // Instead of every lane waiting for its own loads round after round, tiles of consecutive items travel through a 3-slot
     // ring in the (idle) factorisation scratch by asynchronous copies issued two tiles ahead, so that only the first tile of a
-    // pass exposes memory latency.  body(i, kind, k, c, v, j, row): constraint i (kind 0 box / 1 rate / 2 polytopic, stage k,
-    // row c), its staged inputs v[a * TS + j] for a < NA, and for polytopic rows the staged coefficient row (14 doubles).
-    template <int NA, int TS, bool ROWS, class F>
-    MPCC_HD void stream_range(const double* const (&A)[NA], int lo, int hi, F body) const {
-        constexpr int SLOT = NA * TS + (ROWS ? TS * 14 : 0);
-        static_assert(3 * SLOT <= SC_TXU, "ring must stay below the resident constants");
+    // pass exposes memory latency.  The PRESENT constraints are two flat ranges: box and rate rows, adjacent in the vectors
+    // ([18, 18 S + 14 N), tiles of 96), and the polytopic rows ([OP_, OP_ + 11 N), tiles of 32 with their coefficient rows).
+    // body(lane, i, kind, k, c, v, j, row): constraint i (kind 0 box / 1 rate / 2 polytopic, stage k, row c), its staged
+    // inputs v[a * ts + j] (ts = 96 or 32 by kind) for the a-th vector of `ids`, and for polytopic rows the staged
+    // coefficient row (14 doubles).  `ids` packs the vectors' indices (IT = 0, ILAM, IRP, IW, IV, IDT, IDLAM, IH = 7), 3 bits each.
+    // One generic tile loop and ONE out-of-line copy routine serve all passes: the interior-point iteration is bound by
+    // instruction fetch (ncu: stall_no_instruction), so its code footprint matters more than a few address computations.
+    enum : unsigned { CV_T = 0, CV_LAM, CV_RP, CV_W, CV_V, CV_DT, CV_DLAM, CV_H };  // order of carve()
+    MPCC_HD static unsigned vec_ids(unsigned a, unsigned b = 0, unsigned c = 0, unsigned d = 0, unsigned e = 0) { return a | (b << 3) | (c << 6) | (d << 9) | (e << 12); }
+    struct TileGeom { int base, cnt, ts, rows; };
+    MPCC_HD TileGeom tile_geom(int t, int nt1) const {
+        TileGeom g;
+        if (t < nt1) { g.base = 18 + 96 * t; g.ts = 96; g.rows = 0; const int end = OR_ + 14 * N; g.cnt = (end - g.base < 96) ? end - g.base : 96; }
+        else { g.base = OP_ + 32 * (t - nt1); g.ts = 32; g.rows = 1; const int end = OP_ + NPOLY * N; g.cnt = (end - g.base < 32) ? end - g.base : 32; }
+        return g;
+    }
+    static MPCC_HDNI void issue_tile(int lane, const double* vec0, size_t vec_stride, const double* cst, int op, double* dst, unsigned ids, int na,
+                                     int base, int cnt, int ts, int rows) {
+        for (int a = 0; a < na; a++) {
+            const double* src = vec0 + (size_t)((ids >> (3 * a)) & 7u) * vec_stride + base;
+            for (int j = lane; j < cnt; j += 32) async_copy8(dst + a * ts + j, src + j);
+        }
+        if (rows) {
+            const double* src = cst + (size_t)(base - op) * 14;
+            for (int e = lane; e < cnt * 14; e += 32) async_copy8(dst + na * ts + e, src + e);
+        }
+    }
+    template <class F>
+    MPCC_HD void stream_constraints(unsigned ids, int na, F body) const {
+        const int nt1 = (OR_ + 14 * N - 18 + 95) / 96, nt = nt1 + (NPOLY * N + 31) / 32;
+        const int s1 = na * 96, s2 = na * 32 + 32 * 14, slot = (s1 > s2) ? s1 : s2;  // <= 608 for na <= 5: three slots stay below SC_TXU
         double* ring = SC;
-        const int ntiles = (hi - lo + TS - 1) / TS;
-        if (ntiles <= 0) return;
+        const size_t vstride = (size_t)S * NINEQ;
         auto issue = [&](int lane, int t) {
-            if (t < ntiles) {
-                double* dst = ring + (t % 3) * SLOT;
-                const int base = lo + t * TS;
-                const int cnt = (hi - base < TS) ? hi - base : TS;
-#pragma unroll
-                for (int a = 0; a < NA; a++)
-                    for (int j = lane; j < cnt; j += 32) async_copy8(dst + a * TS + j, A[a] + base + j);
-                if (ROWS) {
-                    const double* src = CST + (size_t)(base - OP_) * 14;
-                    for (int e = lane; e < cnt * 14; e += 32) async_copy8(dst + NA * TS + e, src + e);
-                }
+            if (t < nt) {
+                const TileGeom g = tile_geom(t, nt1);
+                issue_tile(lane, IT, vstride, CST, OP_, ring + (t % 3) * slot, ids, na, g.base, g.cnt, g.ts, g.rows);
             }
             async_commit();
         };
         W.each([&](int lane) { issue(lane, 0); issue(lane, 1); async_wait<1>(); });  // tile 0 has landed
-        for (int t = 0; t < ntiles; t++) {
+        for (int t = 0; t < nt; t++) {
             W.each([&](int lane) {
                 issue(lane, t + 2);  // into the slot consumed in the previous phase
-                const double* v = ring + (t % 3) * SLOT;
-                const int base = lo + t * TS;
-                const int cnt = (hi - base < TS) ? hi - base : TS;
-                for (int j = lane; j < cnt; j += 32) {
-                    const int i = base + j;
+                const double* v = ring + (t % 3) * slot;
+                const TileGeom g = tile_geom(t, nt1);
+                for (int j = lane; j < g.cnt; j += 32) {
+                    const int i = g.base + j;
                     int kind, k, c;
-                    if (ROWS) { kind = 2; k = (i - OP_) / NPOLY; c = (i - OP_) - k * NPOLY; }
+                    if (g.rows) { kind = 2; k = (i - OP_) / NPOLY; c = (i - OP_) - k * NPOLY; }
                     else if (i < OR_) { kind = 0; k = i / 18; c = i - k * 18; }
                     else { kind = 1; k = (i - OR_) / 14; c = (i - OR_) - k * 14; }
-                    body(lane, i, kind, k, c, v, j, ROWS ? v + NA * TS + j * 14 : nullptr);
+                    body(lane, i, kind, k, c, v, j, g.rows ? v + na * g.ts + j * 14 : nullptr);
                 }
                 async_wait<1>();  // pending: tiles t+1, t+2 -> tile t+1 has landed
             });
         }
         W.each([&](int) { async_wait<0>(); });
-    }
-    // all PRESENT constraints: box and rate rows are adjacent in the vectors ([18, 18 S + 14 N)), polytopic rows [OP_, OP_ + 11 N)
-    template <int NA, class F>
-    MPCC_HD void stream_constraints(const double* const (&A)[NA], F body) const {
-        stream_range<NA, 96, false>(A, 18, OR_ + 14 * N, body);
-        stream_range<NA, 32, true>(A, OP_, OP_ + NPOLY * N, body);
     }
     // G z of constraint (kind, k, c) on a [S][17] vector in shared memory; polytopic rows use the staged coefficient row
     MPCC_HD double gz_of(const double* Z, int kind, int k, int c, const double* row) const {
@@ -681,9 +690,8 @@ struct WarpSqp {
     MPCC_HD double ineq_steps(double* sums) const {
         double* RED = SC + SC_RED;
         W.each([&](int lane) { RED[lane] = 1.0; RED[32 + lane] = 0.0; RED[64 + lane] = 0.0; });
-        const double* const in[5] = {IRP, ILAM, IV, IW, IT};
         double* dt_ = IDT; double* dl_ = IDLAM;
-        stream_constraints<5>(in, [&](int lane, int i, int kind, int k, int c, const double* v, int j, const double* row) {
+        stream_constraints(vec_ids(CV_RP, CV_LAM, CV_V, CV_W, CV_T), 5, [&](int lane, int i, int kind, int k, int c, const double* v, int j, const double* row) {
             constexpr int TSB = 96, TSP = 32;
             const int ts = (kind == 2) ? TSP : TSB;
             const double rp = v[j], lam = v[ts + j], vv = v[2 * ts + j], w = v[3 * ts + j], t = v[4 * ts + j];
@@ -752,9 +760,8 @@ struct WarpSqp {
             // residuals, barrier weights, predictor v = lam rp / t
             W.each([&](int lane) { RED[lane] = 0.0; RED[32 + lane] = 0.0; });
             {
-                const double* const in[3] = {IT, ILAM, IH};
                 double* rp_ = IRP; double* w_ = IW; double* v_ = IV;
-                stream_constraints<3>(in, [&](int lane, int i, int kind, int k, int c, const double* v, int j, const double* row) {
+                stream_constraints(vec_ids(CV_T, CV_LAM, CV_H), 3, [&](int lane, int i, int kind, int k, int c, const double* v, int j, const double* row) {
                     const int ts = (kind == 2) ? 32 : 96;
                     const double t = v[j], lam = v[ts + j], h = v[2 * ts + j];
                     const double rp = gz_of(VAR, kind, k, c, row) + t - h;
@@ -769,56 +776,63 @@ struct WarpSqp {
             const double nrp = W.rmax([&](int lane) { return RED[lane]; });
             const double sum_tl = W.rsum([&](int lane) { return RED[32 + lane]; });
             const double mu = sum_tl / m_tot;
-            gradient(STEP);  // G <- predictor gradient; STEP <- Lagrangian gradient (scratch until the step is computed)
-            // costates: in-place suffix recursion p_k = g_k + A' p_{k+1} on the xi part of STEP
-            W.each([&](int lane) {
-                if (lane < 8) for (int k = N - 1; k >= 1; k--) STEP[k * HZ + lane] += STEP[(k + 1) * HZ + lane];
-            });
-            W.each([&](int lane) {
-                if (lane == 8) for (int k = N - 1; k >= 1; k--) STEP[k * HZ + 8] += STEP[(k + 1) * HZ + 8] + d_asv() * STEP[(k + 1) * HZ + 7];
-            });
-            const double nrd = W.rmax([&](int lane) {
-                double nr = 0;
-                for (int o = lane; o < NU * N; o += 32) {
-                    const int k = o / NU, j = o - k * NU;
-                    const double* pn = STEP + (k + 1) * HZ;
-                    const double btp = (j < 7) ? d_bq(j) * pn[j] : d_bs() * pn[7] + d_bv() * pn[8];
-                    nr = fmax(nr, fabs(STEP[k * HZ + NX + j] + btp));
+            // Two passes over ONE copy of gradient / sweeps / step lengths (the loop is kept rolled on purpose: code footprint).
+            //   pass 0: Lagrangian gradient and residual test, factorisation, affine (predictor) step, centring parameter
+            //   pass 1: corrector right-hand side, combined step, update
+            double sums[2] = {0.0, 0.0};
+            bool stop = false;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+            for (int pass = 0; pass < 2; pass++) {
+                gradient(pass == 0 ? STEP : nullptr);  // G <- gradient of this pass; pass 0: STEP <- Lagrangian gradient (scratch until the step is computed)
+                if (pass == 0) {
+                    // costates: in-place suffix recursion p_k = g_k + A' p_{k+1} on the xi part of STEP
+                    W.each([&](int lane) {
+                        if (lane < 8) for (int k = N - 1; k >= 1; k--) STEP[k * HZ + lane] += STEP[(k + 1) * HZ + lane];
+                    });
+                    W.each([&](int lane) {
+                        if (lane == 8) for (int k = N - 1; k >= 1; k--) STEP[k * HZ + 8] += STEP[(k + 1) * HZ + 8] + d_asv() * STEP[(k + 1) * HZ + 7];
+                    });
+                    const double nrd = W.rmax([&](int lane) {
+                        double nr = 0;
+                        for (int o = lane; o < NU * N; o += 32) {
+                            const int k = o / NU, j = o - k * NU;
+                            const double* pn = STEP + (k + 1) * HZ;
+                            const double btp = (j < 7) ? d_bq(j) * pn[j] : d_bs() * pn[7] + d_bv() * pn[8];
+                            nr = fmax(nr, fabs(STEP[k * HZ + NX + j] + btp));
+                        }
+                        return nr;
+                    });
+                    st.iters = it; st.res_dual = nrd; st.res_prim = nrp; st.gap = mu;
+                    if (nrd <= opt.eps * (1.0 + qn) && nrp <= opt.eps && mu <= opt.eps) { st.ok = 1; stop = true; break; }
+                    if (!(nrd == nrd) || !(mu == mu)) { stop = true; break; }
+                    if (!factor()) { stop = true; break; }
                 }
-                return nr;
-            });
-            st.iters = it; st.res_dual = nrd; st.res_prim = nrp; st.gap = mu;
-            if (nrd <= opt.eps * (1.0 + qn) && nrp <= opt.eps && mu <= opt.eps) { st.ok = 1; break; }
-            if (!(nrd == nrd) || !(mu == mu)) break;
-            if (!factor()) break;
-            solve_step();
-            double sums[2];
-            const double a_aff = ineq_steps(sums);
-            const double mu_aff = (sum_tl + a_aff * sums[0] + a_aff * a_aff * sums[1]) / m_tot;
-            const double sigma = (mu > 0) ? (mu_aff / mu) * (mu_aff / mu) * (mu_aff / mu) : 0.0;
-            // corrector: v = (lam rp + sigma mu - dt_a dlam_a) / t
-            {
-                const double sm = sigma * mu;
-                const double* const in[5] = {ILAM, IRP, IDT, IDLAM, IT};
-                double* v_ = IV;
-                stream_constraints<5>(in, [&](int, int i, int kind, int, int, const double* v, int j, const double*) {
-                    const int ts = (kind == 2) ? 32 : 96;
-                    v_[i] = (v[j] * v[ts + j] + sm - v[2 * ts + j] * v[3 * ts + j]) / v[4 * ts + j];
-                });
+                solve_step();
+                const double a_max = ineq_steps(pass == 0 ? sums : nullptr);
+                if (pass == 0) {
+                    const double mu_aff = (sum_tl + a_max * sums[0] + a_max * a_max * sums[1]) / m_tot;
+                    const double sigma = (mu > 0) ? (mu_aff / mu) * (mu_aff / mu) * (mu_aff / mu) : 0.0;
+                    // corrector: v = (lam rp + sigma mu - dt_a dlam_a) / t
+                    const double sm = sigma * mu;
+                    double* v_ = IV;
+                    stream_constraints(vec_ids(CV_LAM, CV_RP, CV_DT, CV_DLAM, CV_T), 5, [&](int, int i, int kind, int, int, const double* v, int j, const double*) {
+                        const int ts = (kind == 2) ? 32 : 96;
+                        v_[i] = (v[j] * v[ts + j] + sm - v[2 * ts + j] * v[3 * ts + j]) / v[4 * ts + j];
+                    });
+                } else {
+                    const double a = fmin(1.0, 0.995 * a_max);
+                    W.each([&](int lane) { for (int o = lane; o < S * HZ; o += 32) VAR[o] += a * STEP[o]; });
+                    double* t_ = IT; double* l_ = ILAM;
+                    stream_constraints(vec_ids(CV_T, CV_LAM, CV_DT, CV_DLAM), 4, [&](int, int i, int kind, int, int, const double* v, int j, const double*) {
+                        const int ts = (kind == 2) ? 32 : 96;
+                        t_[i] = v[j] + a * v[2 * ts + j];
+                        l_[i] = v[ts + j] + a * v[3 * ts + j];
+                    });
+                }
             }
-            gradient(nullptr);
-            solve_step();
-            const double a = fmin(1.0, 0.995 * ineq_steps(nullptr));
-            W.each([&](int lane) { for (int o = lane; o < S * HZ; o += 32) VAR[o] += a * STEP[o]; });
-            {
-                const double* const in[4] = {IT, ILAM, IDT, IDLAM};
-                double* t_ = IT; double* l_ = ILAM;
-                stream_constraints<4>(in, [&](int, int i, int kind, int, int, const double* v, int j, const double*) {
-                    const int ts = (kind == 2) ? 32 : 96;
-                    t_[i] = v[j] + a * v[2 * ts + j];
-                    l_[i] = v[ts + j] + a * v[3 * ts + j];
-                });
-            }
+            if (stop) break;
             st.iters = it + 1;
         }
         if (st.ok) {
