@@ -34,31 +34,31 @@
 namespace mpcc {
 
 // ---- the 32-lane execution abstraction -----------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+// butterfly reductions, one copy each in the kernel image (the QP path calls them ~10 times per interior-point iteration)
+static __device__ __noinline__ double warp_all_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+static __device__ __noinline__ double warp_all_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+static __device__ __noinline__ double warp_all_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+#endif
 struct Warp {
 #if defined(__CUDA_ARCH__)
     int lane;
     template <class F> __device__ __forceinline__ void each(F f) const { f(lane); __syncwarp(); }
-    template <class F> __device__ __forceinline__ double rmax(F f) const {
-        double v = f(lane);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-        __syncwarp();
-        return v;
-    }
-    template <class F> __device__ __forceinline__ double rmin(F f) const {
-        double v = f(lane);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
-        __syncwarp();
-        return v;
-    }
-    template <class F> __device__ __forceinline__ double rsum(F f) const {
-        double v = f(lane);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        __syncwarp();
-        return v;
-    }
+    template <class F> __device__ __forceinline__ double rmax(F f) const { const double v = warp_all_max(f(lane)); __syncwarp(); return v; }
+    template <class F> __device__ __forceinline__ double rmin(F f) const { const double v = warp_all_min(f(lane)); __syncwarp(); return v; }
+    template <class F> __device__ __forceinline__ double rsum(F f) const { const double v = warp_all_sum(f(lane)); __syncwarp(); return v; }
     template <class F> __device__ __forceinline__ bool any(F f) const {
         bool r = __any_sync(0xffffffffu, f(lane));
         __syncwarp();
@@ -76,6 +76,14 @@ struct Warp {
     template <class F> bool any(F f) const { bool v = false; each([&](int l) { v = f(l) || v; }); return v; }
 #endif
 };
+
+// The interior-point iteration is bound by instruction fetch, not issue (ncu: stall_no_instruction dominates with ten
+// warps per SM in different phases of ~100 KB of code): lane-strided loops of the QP path stay rolled.
+#if defined(__CUDACC__)
+#define MPCC_ROLLED _Pragma("unroll 1")
+#else
+#define MPCC_ROLLED
+#endif
 
 #if defined(__CUDA_ARCH__)
 #define MPCC_RSQRT(x) rsqrt(x)
@@ -238,7 +246,9 @@ struct WarpSqp {
     template <class F>
     MPCC_HD void for_present(int lane, const double* Z, bool need_h, F f) const {
         for (int i = 18 + lane; i < 18 * S; i += 32) { const int k = i / 18, c = i - k * 18; f(i, gz_box(Z, k, c), need_h ? h_box(k, c) : 0.0); }
+        MPCC_ROLLED
         for (int i = lane; i < 14 * N; i += 32) { const int k = i / 14, c = i - k * 14; f(OR_ + i, gz_rate(Z, k, c), need_h ? h_rate(k, c) : 0.0); }
+        MPCC_ROLLED
         for (int i = lane; i < NPOLY * N; i += 32) { const int k = i / NPOLY, j = i - k * NPOLY; f(OP_ + i, gz_poly(Z, k, j), need_h ? h_poly(k, j) : 0.0); }
     }
 
@@ -256,6 +266,7 @@ struct WarpSqp {
             }
             f4(idx, g, h);
         }
+        MPCC_ROLLED
         for (int base = lane; base < 14 * N; base += 128) {
 #pragma unroll
             for (int u = 0; u < 4; u++) {
@@ -265,6 +276,7 @@ struct WarpSqp {
             }
             f4(idx, g, h);
         }
+        MPCC_ROLLED
         for (int base = lane; base < NPOLY * N; base += 128) {
 #pragma unroll
             for (int u = 0; u < 4; u++) {
@@ -300,10 +312,12 @@ struct WarpSqp {
                                      int base, int cnt, int ts, int rows) {
         for (int a = 0; a < na; a++) {
             const double* src = vec0 + (size_t)((ids >> (3 * a)) & 7u) * vec_stride + base;
+            MPCC_ROLLED
             for (int j = lane; j < cnt; j += 32) async_copy8(dst + a * ts + j, src + j);
         }
         if (rows) {
             const double* src = cst + (size_t)(base - op) * 14;
+            MPCC_ROLLED
             for (int e = lane; e < cnt * 14; e += 32) async_copy8(dst + na * ts + e, src + e);
         }
     }
@@ -326,6 +340,7 @@ struct WarpSqp {
                 issue(lane, t + 2);  // into the slot consumed in the previous phase
                 const double* v = ring + (t % 3) * slot;
                 const TileGeom g = tile_geom(t, nt1);
+                MPCC_ROLLED
                 for (int j = lane; j < g.cnt; j += 32) {
                     const int i = g.base + j;
                     int kind, k, c;
@@ -353,6 +368,7 @@ struct WarpSqp {
     // ---- gradient of the step QP: G <- H z + f + G'(IV); dst0 (shared) <- same with multipliers ILAM ----
     MPCC_HD void gradient(double* dst0) const {
         W.each([&](int lane) {
+            MPCC_ROLLED
             for (int o = lane; o < NX * S; o += 32) {
                 const int k = o / NX, r = o - k * NX;
                 const double* L = LIN + (size_t)k * WL_SIZE;
@@ -374,6 +390,7 @@ struct WarpSqp {
                 G[k * HZ + r] = base + sv;
                 if (dst0) dst0[k * HZ + r] = base + sl;
             }
+            MPCC_ROLLED
             for (int o = lane; o < NU * N; o += 32) {
                 const int k = o / NU, j = o - k * NU;
                 const double* L = LIN + (size_t)k * WL_SIZE;
@@ -408,6 +425,7 @@ struct WarpSqp {
     MPCC_HD void issue_stage_copy(int lane, int k, double* SG) const {
         if (k >= 0) {
             double* dst = SG + (k & 1) * SG_SIZE;
+            MPCC_ROLLED
             for (int e = lane; e < SG_SIZE; e += 32) {
                 const double* src;
                 if (e < SG_WP) src = CST + (size_t)k * WC_SIZE + e;
@@ -436,6 +454,7 @@ struct WarpSqp {
         // terminal stage: P_N = Q_N + box W
         W.each([&](int lane) {
             const double* L = LIN + (size_t)N * WL_SIZE;
+            MPCC_ROLLED
             for (int e = lane; e < 256; e += 32) {
                 const int r = e >> 4, c = e & 15;
                 double v = 0;
@@ -460,11 +479,13 @@ struct WarpSqp {
             // F1: start fetching the next stage's inputs; FF = B'Pxx + E'Pwx (8 x 9)
             W.each([&](int lane) {
                 issue_stage_copy(lane, k - 1, SG);
+                MPCC_ROLLED
                 for (int e = lane; e < 72; e += 32) {
                     const int i = e / 9, c = e - i * 9;
                     FF[e] = (i < 7) ? d_bq(i) * Pc[i * 16 + c] + Pc[(9 + i) * 16 + c] : d_bs() * Pc[7 * 16 + c] + d_bv() * Pc[8 * 16 + c];
                 }
                 // F2 (same phase: independent of FF): U = sum_p (w_p g_p) g_p'  in 2 x 2 register blocks
+                MPCC_ROLLED
                 for (int blk = lane; blk < 49; blk += 32) {
                     const int bi = blk / 7, bj = blk - bi * 7;
                     double a00 = 0, a01 = 0, a10 = 0, a11 = 0;
@@ -481,6 +502,7 @@ struct WarpSqp {
             });
             // F3: Mnn (8 x 8), Mnx (8 x 16) and [Mxx 0; 0 Mww] (16 x 16)
             W.each([&](int lane) {
+                MPCC_ROLLED
                 for (int e = lane; e < 64; e += 32) {
                     const int i = e >> 3, j = e & 7;
                     double v;
@@ -494,6 +516,7 @@ struct WarpSqp {
                     if (i == j) { v += RDs[j]; if (j < 7) v += wR[j] + wR[7 + j]; }
                     Mnn[e] = v;
                 }
+                MPCC_ROLLED
                 for (int e = lane; e < 128; e += 32) {
                     const int i = e >> 4, c = e & 15;
                     double v = 0;
@@ -506,6 +529,7 @@ struct WarpSqp {
                     }
                     Mnx[e] = v;
                 }
+                MPCC_ROLLED
                 for (int e = lane; e < 256; e += 32) {
                     const int r = e >> 4, c = e & 15;
                     double v = 0;
@@ -578,6 +602,7 @@ struct WarpSqp {
 #pragma unroll
                 for (int a = 0; a < 4; a++) { Pc[(r0 + a) * 16 + c0] = acc[a][0]; Pc[(r0 + a) * 16 + c0 + 1] = acc[a][1]; }
                 double* F = FACT + (size_t)k * WF_SIZE;
+                MPCC_ROLLED
                 for (int e = lane; e < WF_SIZE; e += 32) F[e] = X[e];  // X and Lam are contiguous in the scratch
                 async_wait<0>();  // the next stage's inputs have landed
             });
@@ -607,6 +632,7 @@ struct WarpSqp {
             issue_factor_copy(lane, N - 1, ring);
             issue_factor_copy(lane, N - 2, ring);
             issue_factor_copy(lane, N - 3, ring);
+            MPCC_ROLLED
             for (int e = lane; e < S * HZ; e += 32) async_copy8(GS_ + e, G + e);
             async_commit();
             if (lane < 16) V[V_D0 + lane] = 0.0;
@@ -722,6 +748,7 @@ struct WarpSqp {
         // feasibility of the boxes (stage 0: xi_0 = 0 must lie inside; others: lo <= hi)
         if (W.any([&](int lane) {
                 bool bad = false;
+                MPCC_ROLLED
                 for (int o = lane; o < S * NX; o += 32) {
                     const int k = o / NX, m = o - k * NX;
                     const double* L = LIN + (size_t)k * WL_SIZE;
@@ -733,6 +760,7 @@ struct WarpSqp {
         // initial point: nu = 0, xi = rollout of the defects (lane = state component), t = max(h - Gz, 1), lam = 1
         const double qn = W.rmax([&](int lane) {
             double q = 0;
+            MPCC_ROLLED
             for (int o = lane; o < S * HZ; o += 32) {
                 const int k = o / HZ, r = o - k * HZ;
                 const double* L = LIN + (size_t)k * WL_SIZE;
@@ -750,6 +778,7 @@ struct WarpSqp {
                 double x = 0;
                 for (int k = 0; k <= N; k++) { VAR[k * HZ + 7] = x; if (k < N) x += d_asv() * VAR[k * HZ + 8] + LIN[(size_t)k * WL_SIZE + WL_b + 7]; }
             }
+            MPCC_ROLLED
             for (int i = lane; i < tot; i += 32) { IT[i] = 1.0; ILAM[i] = 0.0; IW[i] = 0.0; IV[i] = 0.0; IRP[i] = 0.0; IDT[i] = 0.0; IDLAM[i] = 0.0; }
         });
         W.each([&](int lane) {
@@ -796,6 +825,7 @@ struct WarpSqp {
                     });
                     const double nrd = W.rmax([&](int lane) {
                         double nr = 0;
+                        MPCC_ROLLED
                         for (int o = lane; o < NU * N; o += 32) {
                             const int k = o / NU, j = o - k * NU;
                             const double* pn = STEP + (k + 1) * HZ;
@@ -823,7 +853,7 @@ struct WarpSqp {
                     });
                 } else {
                     const double a = fmin(1.0, 0.995 * a_max);
-                    W.each([&](int lane) { for (int o = lane; o < S * HZ; o += 32) VAR[o] += a * STEP[o]; });
+                    W.each([&](int lane) { MPCC_ROLLED for (int o = lane; o < S * HZ; o += 32) VAR[o] += a * STEP[o]; });
                     double* t_ = IT; double* l_ = ILAM;
                     stream_constraints(vec_ids(CV_T, CV_LAM, CV_DT, CV_DLAM), 4, [&](int, int i, int kind, int, int, const double* v, int j, const double*) {
                         const int ts = (kind == 2) ? 32 : 96;
