@@ -101,6 +101,15 @@ MPCC_HD void async_copy8(double* smem_dst, const double* gsrc) {
     *smem_dst = *gsrc;
 #endif
 }
+// 16-byte variant: both addresses 16-byte aligned; copies smem_dst[0..1]
+MPCC_HD void async_copy16(double* smem_dst, const double* gsrc) {
+#if defined(__CUDA_ARCH__)
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+#else
+    smem_dst[0] = gsrc[0]; smem_dst[1] = gsrc[1];
+#endif
+}
 MPCC_HD void async_commit() {
 #if defined(__CUDA_ARCH__)
     asm volatile("cp.async.commit_group;\n" ::: "memory");
@@ -127,9 +136,13 @@ constexpr int SG_GS = 0, SG_WP = 154, SG_Q = 166, SG_RD = 247, SG_WB = 255, SG_W
 constexpr int V_P = 0, V_MN = 16, V_MX = 24, V_KAP = 40, V_D0 = 48, V_D1 = 64, V_RHS = 80, V_DN = 88;  // inside SC_VEC (96)
 constexpr int MAX_SQP_FILTER = 128;
 
+// Everything the 16-byte asynchronous copies touch starts on an even double: the per-constraint vectors have an even stride
+// and the per-instance workspace / per-warp shared block an even size (WL_SIZE, WC_SIZE, the tile bases are even already).
+MPCC_HD size_t cvec_stride(int N) { return ((size_t)(N + 1) * NINEQ + 1) & ~(size_t)1; }
 MPCC_HD size_t warp_ws_doubles(int N) {
     const size_t S = N + 1;
-    return S * (WL_SIZE + WC_SIZE + 8 * NINEQ + HZ /*G*/ + 8 /*KAP*/ + WF_SIZE + 2 * HZ /*persistent step, iterate*/ + 2 * NPOLY /*barrier values*/) + 2 * (MAX_SQP_FILTER + 2);
+    const size_t n = S * (WL_SIZE + WC_SIZE + HZ /*G*/ + 8 /*KAP*/ + WF_SIZE + 2 * HZ /*persistent step, iterate*/ + 2 * NPOLY /*barrier values*/) + 8 * cvec_stride(N) + 2 * (MAX_SQP_FILTER + 2);
+    return (n + 1) & ~(size_t)1;
 }
 // the sweeps keep the gradient (17 S) and kappa (8 S) in the scratch below SC_VEC behind a 4-slot factor ring; longer
 // horizons get a separate block appended after the scratch
@@ -138,7 +151,7 @@ constexpr int XG_ROOM = SC_U;  // the iterate's working copy sits in the factori
 MPCC_HD size_t warp_smem_extra(int N) {
     return ((25 * (N + 1) <= SC_VEC - SW_GK) ? 0 : (size_t)25 * (N + 1)) + ((HZ * (N + 1) <= XG_ROOM) ? 0 : (size_t)HZ * (N + 1));
 }
-MPCC_HD size_t warp_smem_doubles(int N) { return (size_t)2 * (N + 1) * HZ + SC_SIZE + warp_smem_extra(N); }
+MPCC_HD size_t warp_smem_doubles(int N) { return ((size_t)2 * (N + 1) * HZ + SC_SIZE + warp_smem_extra(N) + 1) & ~(size_t)1; }
 
 // isPosdef / isNan of one packed-lower 9 x 9 Hessian block, fully unrolled (static indices: registers).
 // pd is cleared at the first non-positive pivot unless that pivot is NaN (NaN is reported through `nan`).
@@ -197,8 +210,9 @@ struct WarpSqp {
         const size_t S_ = S;
         LIN = gws; gws += S_ * WL_SIZE;
         CST = gws; gws += S_ * WC_SIZE;
-        IT = gws; gws += S_ * NINEQ; ILAM = gws; gws += S_ * NINEQ; IRP = gws; gws += S_ * NINEQ; IW = gws; gws += S_ * NINEQ;
-        IV = gws; gws += S_ * NINEQ; IDT = gws; gws += S_ * NINEQ; IDLAM = gws; gws += S_ * NINEQ; IH = gws; gws += S_ * NINEQ;
+        const size_t VST = cvec_stride(N);
+        IT = gws; gws += VST; ILAM = gws; gws += VST; IRP = gws; gws += VST; IW = gws; gws += VST;
+        IV = gws; gws += VST; IDT = gws; gws += VST; IDLAM = gws; gws += VST; IH = gws; gws += VST;
         G = gws; gws += S_ * HZ; KAP = gws; gws += S_ * 8; FACT = gws; gws += S_ * WF_SIZE; SSTEP = gws; gws += S_ * HZ; GUESS = gws; gws += S_ * HZ; RBFV = gws; gws += S_ * 2 * NPOLY; FILT = gws;
         VAR = sm; STEP = sm + S_ * HZ; SC = sm + 2 * S_ * HZ;
         OR_ = 18 * S; OP_ = 32 * S;
@@ -310,15 +324,20 @@ struct WarpSqp {
     }
     static MPCC_HDNI void issue_tile(int lane, const double* vec0, size_t vec_stride, const double* cst, int op, double* dst, unsigned ids, int na,
                                      int base, int cnt, int ts, int rows) {
+        // pairs of doubles (an odd polytopic tail copies one in-bounds double more than needed)
+        const int half = (cnt + 1) >> 1;
+        MPCC_ROLLED
         for (int a = 0; a < na; a++) {
-            const double* src = vec0 + (size_t)((ids >> (3 * a)) & 7u) * vec_stride + base;
+            const double* src = vec0 + (size_t)((ids >> (3 * a)) & 7u) * vec_stride + base + 2 * lane;
+            double* d = dst + a * ts + 2 * lane;
             MPCC_ROLLED
-            for (int j = lane; j < cnt; j += 32) async_copy8(dst + a * ts + j, src + j);
+            for (int r = half - lane; r > 0; r -= 32, src += 64, d += 64) async_copy16(d, src);
         }
         if (rows) {
-            const double* src = cst + (size_t)(base - op) * 14;
+            const double* src = cst + (size_t)(base - op) * 14 + 2 * lane;
+            double* d = dst + na * ts + 2 * lane;
             MPCC_ROLLED
-            for (int e = lane; e < cnt * 14; e += 32) async_copy8(dst + na * ts + e, src + e);
+            for (int r = cnt * 7 - lane; r > 0; r -= 32, src += 64, d += 64) async_copy16(d, src);
         }
     }
     template <class F>
@@ -326,7 +345,7 @@ struct WarpSqp {
         const int nt1 = (OR_ + 14 * N - 18 + 95) / 96, nt = nt1 + (NPOLY * N + 31) / 32;
         const int s1 = na * 96, s2 = na * 32 + 32 * 14, slot = (s1 > s2) ? s1 : s2;  // <= 608 for na <= 5: three slots stay below SC_TXU
         double* ring = SC;
-        const size_t vstride = (size_t)S * NINEQ;
+        const size_t vstride = cvec_stride(N);
         auto issue = [&](int lane, int t) {
             if (t < nt) {
                 const TileGeom g = tile_geom(t, nt1);
@@ -463,6 +482,8 @@ struct WarpSqp {
                     if (r == c) v += IW[N * 18 + r] + IW[N * 18 + 9 + r];
                 }
                 Pc[e] = v;
+                PM[e] = 0.0;                 // only the structural entries of PM / Mnx are rewritten per stage
+                if (e < 128) Mnx[e] = 0.0;
             }
             issue_stage_copy(lane, N - 1, SG);
             async_wait<0>();
@@ -484,10 +505,11 @@ struct WarpSqp {
                     const int i = e / 9, c = e - i * 9;
                     FF[e] = (i < 7) ? d_bq(i) * Pc[i * 16 + c] + Pc[(9 + i) * 16 + c] : d_bs() * Pc[7 * 16 + c] + d_bv() * Pc[8 * 16 + c];
                 }
-                // F2 (same phase: independent of FF): U = sum_p (w_p g_p) g_p'  in 2 x 2 register blocks
-                MPCC_ROLLED
-                for (int blk = lane; blk < 49; blk += 32) {
-                    const int bi = blk / 7, bj = blk - bi * 7;
+                // F2 (same phase: independent of FF): U = sum_p (w_p g_p) g_p'  in 2 x 2 register blocks, upper triangle + mirror
+                if (lane < 28) {
+                    int bi = 0, t = lane;
+                    while (t >= 7 - bi) { t -= 7 - bi; bi++; }
+                    const int bj = bi + t;
                     double a00 = 0, a01 = 0, a10 = 0, a11 = 0;
 #pragma unroll
                     for (int p = 0; p < NPOLY; p++) {
@@ -498,6 +520,10 @@ struct WarpSqp {
                     }
                     U[(2 * bi) * 14 + 2 * bj] = a00; U[(2 * bi) * 14 + 2 * bj + 1] = a01;
                     U[(2 * bi + 1) * 14 + 2 * bj] = a10; U[(2 * bi + 1) * 14 + 2 * bj + 1] = a11;
+                    if (bi != bj) {
+                        U[(2 * bj) * 14 + 2 * bi] = a00; U[(2 * bj + 1) * 14 + 2 * bi] = a01;
+                        U[(2 * bj) * 14 + 2 * bi + 1] = a10; U[(2 * bj + 1) * 14 + 2 * bi + 1] = a11;
+                    }
                 }
             });
             // F3: Mnn (8 x 8), Mnx (8 x 16) and [Mxx 0; 0 Mww] (16 x 16)
@@ -517,33 +543,35 @@ struct WarpSqp {
                     Mnn[e] = v;
                 }
                 MPCC_ROLLED
-                for (int e = lane; e < 128; e += 32) {
-                    const int i = e >> 4, c = e & 15;
-                    double v = 0;
-                    if (c < 9) {
-                        v = FF[i * 9 + c];
+                for (int e = lane; e < 79; e += 32) {  // structural entries of Mnx: the 8 x 9 block and the rate coupling diagonal
+                    int i, c;
+                    double v;
+                    if (e < 72) {
+                        i = e / 9; c = e - i * 9;
+                        v = FF[e];
                         if (c == 8) v += d_asv() * FF[i * 9 + 7];
                         if (i < 7 && c < 7) v += U[(7 + i) * 14 + c];
-                    } else if (c - 9 == i && k >= 1) {
-                        v = d_cpl(i) - (wR[i] + wR[7 + i]);
+                    } else {
+                        i = e - 72; c = 9 + i;
+                        v = (k >= 1) ? d_cpl(i) - (wR[i] + wR[7 + i]) : 0.0;
                     }
-                    Mnx[e] = v;
+                    Mnx[i * 16 + c] = v;
                 }
                 MPCC_ROLLED
-                for (int e = lane; e < 256; e += 32) {
-                    const int r = e >> 4, c = e & 15;
-                    double v = 0;
-                    if (r < 9 && c < 9) {
-                        v = Pc[e];
+                for (int e = lane; e < 88; e += 32) {  // structural entries of [Mxx 0; 0 Mww]: the 9 x 9 block and 7 diagonal entries
+                    if (e < 81) {
+                        const int r = e / 9, c = e - r * 9;
+                        double v = Pc[r * 16 + c];
                         if (c == 8) v += d_asv() * Pc[r * 16 + 7];
                         if (r == 8) v += d_asv() * (Pc[7 * 16 + c] + ((c == 8) ? d_asv() * Pc[7 * 16 + 7] : 0.0));
-                        v += Qs[r * 9 + c];
+                        v += Qs[e];
                         if (r == c && k >= 1) v += wB[r] + wB[9 + r];
                         if (r < 7 && c < 7) v += U[r * 14 + c];
-                    } else if (r == c && r >= 9 && k >= 1) {
-                        v = wR[r - 9] + wR[7 + r - 9];
+                        PM[r * 16 + c] = v;
+                    } else {
+                        const int j = e - 81;
+                        PM[(9 + j) * 17] = (k >= 1) ? wR[j] + wR[7 + j] : 0.0;
                     }
-                    PM[e] = v;
                 }
             });
             // F4 + F5: every lane c < 24 factors Mnn = Lc Lc' in its own registers (no barriers or shared-memory round trips on
