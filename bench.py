@@ -375,7 +375,7 @@ def run_ours(args):
             ach = flop / (ms * 1e-3) / 1e12
             return {"bound": "fp64", "kernel": kernel, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                     "traffic": traffic.get(kernel), "algorithmic_flops_per_launch": flop, "kernel_ms": float(ms), "peak_source": peak_src, "note": note}
-        roof_mlp = roof_of("k_mlp", mlp_flop, km[2], "dense fp64 contraction (both networks + 7 forward-mode tangents); tcgen05 has no f64 kind, the DFMA pipe is the roof")
+        roof_mlp = roof_of("k_mlp", mlp_flop, km[2], "dense fp64 contraction (both networks + 7 forward-mode tangents) on mma.sync.m8n8k4.f64; tcgen05 has no f64 kind, DMMA and DFMA share one FP64 pipe, which is the roof")
         roof_sqp = roof_of("k_sqp_warp", sqp_flop, km[3], "interior-point / Riccati SQP loop: dependent small factorisations, latency- and DRAM-latency-bound "
                            "(FLOP model x measured interior-point iterations of the last step); its DRAM traffic is in `traffic`")
         roof = dict(roof_sqp if dom == 3 else roof_mlp)

@@ -1,6 +1,7 @@
 // Warp-per-instance SQP kernels (default): see sqp_warp.cuh.
 #include "cycle_args.h"
 #include "sqp_warp.cuh"
+#include <cstdlib>
 
 namespace mpcc {
 
@@ -98,7 +99,13 @@ __global__ void __launch_bounds__(SQPW_WARPS * 32, MPCC_SQPW_MINB) k_solve_ocp_w
 
 
 size_t sqp_warp_ws_doubles(int N) { return warp_ws_doubles(N); }
-size_t sqp_warp_smem_bytes(int N) { return SQPW_WARPS * warp_smem_doubles(N) * sizeof(double); }
+// MPCC_SQPW_SMEM_PAD (bytes, diagnostic): extra dynamic shared memory per CTA, to lower the number of resident CTAs per SM
+// in residency experiments without rebuilding
+static size_t sqp_warp_smem_pad() {
+    static const size_t pad = [] { const char* e = getenv("MPCC_SQPW_SMEM_PAD"); return e ? (size_t)atol(e) : (size_t)0; }();
+    return pad;
+}
+size_t sqp_warp_smem_bytes(int N) { return SQPW_WARPS * warp_smem_doubles(N) * sizeof(double) + sqp_warp_smem_pad(); }
 cudaError_t configure_sqp_warp(int N) {
     cudaError_t e = cudaFuncSetAttribute(k_sqp_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sqp_warp_smem_bytes(N));
     if (e != cudaSuccess) return e;

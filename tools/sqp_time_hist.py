@@ -11,7 +11,7 @@ mpc = M.BatchMPC(B, N); mpc.load_nn(); mpc.set_params(M.load_default_params())
 ee = mpc.eval_robot_data(q_home()[None])[0, 7:10]
 mpc.set_tracks(M.load_track_json(None, ee))
 x0, u0 = synthetic_inputs(B, 0)
-for c in range(8):
+for c in range(14):
     r = mpc.run_cycle(x0, u0, want_horizon=False)
     tt = mpc.compute_time() * 1e3
     t = tt[:, 0]
