@@ -132,7 +132,8 @@ constexpr int SC_P = 0, SC_PM = 256, SC_MNN = 512, SC_MNX = 576, SC_X = 704, SC_
               SC_VEC = 1740, SC_TXU = 1836, SC_DYN = 1854, SC_RED = 1872, SC_SIZE = 2032;  // RED: 5 x 32 per-lane accumulators
 // staged inputs of one stage of the factorisation (two slots, filled by asynchronous copies one stage ahead):
 // polytopic rows, their barrier weights, Q, Rd, box / rate barrier weights
-constexpr int SG_GS = 0, SG_WP = 154, SG_Q = 166, SG_RD = 247, SG_WB = 255, SG_WR = 273, SG_SIZE = 288;
+// (every block but WP starts on an even double in both the source and the slot, so it travels in 16-byte pairs)
+constexpr int SG_GS = 0, SG_Q = 154, SG_RD = 236, SG_WB = 244, SG_WR = 262, SG_WP = 276, SG_SIZE = 288;
 constexpr int V_P = 0, V_MN = 16, V_MX = 24, V_KAP = 40, V_D0 = 48, V_D1 = 64, V_RHS = 80, V_DN = 88;  // inside SC_VEC (96)
 constexpr int MAX_SQP_FILTER = 128;
 
@@ -213,7 +214,8 @@ struct WarpSqp {
         const size_t VST = cvec_stride(N);
         IT = gws; gws += VST; ILAM = gws; gws += VST; IRP = gws; gws += VST; IW = gws; gws += VST;
         IV = gws; gws += VST; IDT = gws; gws += VST; IDLAM = gws; gws += VST; IH = gws; gws += VST;
-        G = gws; gws += S_ * HZ; KAP = gws; gws += S_ * 8; FACT = gws; gws += S_ * WF_SIZE; SSTEP = gws; gws += S_ * HZ; GUESS = gws; gws += S_ * HZ; RBFV = gws; gws += S_ * 2 * NPOLY; FILT = gws;
+        // FACT and G on even offsets (16-byte copies)
+        FACT = gws; gws += S_ * WF_SIZE; G = gws; gws += S_ * HZ; KAP = gws; gws += S_ * 8; SSTEP = gws; gws += S_ * HZ; GUESS = gws; gws += S_ * HZ; RBFV = gws; gws += S_ * 2 * NPOLY; FILT = gws;
         VAR = sm; STEP = sm + S_ * HZ; SC = sm + 2 * S_ * HZ;
         OR_ = 18 * S; OP_ = 32 * S;
         XG = (HZ * S <= XG_ROOM) ? SC : SC + SC_SIZE;
@@ -324,20 +326,24 @@ struct WarpSqp {
     }
     static MPCC_HDNI void issue_tile(int lane, const double* vec0, size_t vec_stride, const double* cst, int op, double* dst, unsigned ids, int na,
                                      int base, int cnt, int ts, int rows) {
-        // pairs of doubles (an odd polytopic tail copies one in-bounds double more than needed)
+        // pairs of doubles (an odd polytopic tail copies one in-bounds double more than needed); a tile holds at most 96
+        // constraints = 48 pairs per vector (two predicated copies per lane, no loop: ~6 instructions per copy instead of
+        // ~18 per loop round) and 32 x 14 coefficient doubles = 224 pairs (seven)
         const int half = (cnt + 1) >> 1;
+        const bool c0 = lane < half, c1 = lane + 32 < half;
         MPCC_ROLLED
         for (int a = 0; a < na; a++) {
             const double* src = vec0 + (size_t)((ids >> (3 * a)) & 7u) * vec_stride + base + 2 * lane;
             double* d = dst + a * ts + 2 * lane;
-            MPCC_ROLLED
-            for (int r = half - lane; r > 0; r -= 32, src += 64, d += 64) async_copy16(d, src);
+            if (c0) async_copy16(d, src);
+            if (c1) async_copy16(d + 64, src + 64);
         }
         if (rows) {
             const double* src = cst + (size_t)(base - op) * 14 + 2 * lane;
             double* d = dst + na * ts + 2 * lane;
-            MPCC_ROLLED
-            for (int r = cnt * 7 - lane; r > 0; r -= 32, src += 64, d += 64) async_copy16(d, src);
+            const int n2 = cnt * 7 - lane;
+#pragma unroll
+            for (int r = 0; r < 7; r++) if (32 * r < n2) async_copy16(d + 64 * r, src + 64 * r);
         }
     }
     template <class F>
@@ -440,21 +446,25 @@ struct WarpSqp {
         });
     }
 
-    // asynchronous fetch of the factorisation inputs of stage k into slot k & 1
+    // asynchronous fetch of the factorisation inputs of stage k into slot k & 1: 138 pairs (polytopic rows 77, Q 41 -- the last
+    // pair carries one unused double --, Rd 4, box weights 9, rate weights 7) + the 11 polytopic weights (odd source offsets)
     MPCC_HD void issue_stage_copy(int lane, int k, double* SG) const {
         if (k >= 0) {
             double* dst = SG + (k & 1) * SG_SIZE;
-            MPCC_ROLLED
-            for (int e = lane; e < SG_SIZE; e += 32) {
-                const double* src;
-                if (e < SG_WP) src = CST + (size_t)k * WC_SIZE + e;
-                else if (e < SG_Q) src = (e - SG_WP < NPOLY) ? IW + OP_ + k * NPOLY + (e - SG_WP) : nullptr;
-                else if (e < SG_RD) src = LIN + (size_t)k * WL_SIZE + WL_Q + (e - SG_Q);
-                else if (e < SG_WB) src = LIN + (size_t)k * WL_SIZE + WL_RD + (e - SG_RD);
-                else if (e < SG_WR) src = IW + k * 18 + (e - SG_WB);
-                else src = (e - SG_WR < 14) ? IW + OR_ + k * 14 + (e - SG_WR) : nullptr;
-                if (src) async_copy8(dst + e, src);
+            const double* L = LIN + (size_t)k * WL_SIZE;
+#pragma unroll
+            for (int r = 0; r < 5; r++) {
+                const int e = lane + 32 * r;
+                const double* src = nullptr;
+                int d = 0;
+                if (e < 77) { src = CST + (size_t)k * WC_SIZE + 2 * e; d = SG_GS + 2 * e; }
+                else if (e < 118) { src = L + WL_Q + 2 * (e - 77); d = SG_Q + 2 * (e - 77); }
+                else if (e < 122) { src = L + WL_RD + 2 * (e - 118); d = SG_RD + 2 * (e - 118); }
+                else if (e < 131) { src = IW + k * 18 + 2 * (e - 122); d = SG_WB + 2 * (e - 122); }
+                else if (e < 138) { src = IW + OR_ + k * 14 + 2 * (e - 131); d = SG_WR + 2 * (e - 131); }
+                if (src) async_copy16(dst + d, src);
             }
+            if (lane < NPOLY) async_copy8(dst + SG_WP + lane, IW + OP_ + k * NPOLY + lane);
         }
         async_commit();
     }
@@ -643,10 +653,10 @@ struct WarpSqp {
     // the gradient is pulled into shared memory in one burst and kappa never leaves it.
     MPCC_HD void issue_factor_copy(int lane, int k, double* ring) const {
         if (k >= 0 && k < N) {
-            const double* F = FACT + (size_t)k * WF_SIZE;
-            double* dst = ring + (k & (SW_RING - 1)) * WF_SIZE;
+            const double* F = FACT + (size_t)k * WF_SIZE + 2 * lane;
+            double* dst = ring + (k & (SW_RING - 1)) * WF_SIZE + 2 * lane;
 #pragma unroll
-            for (int t = 0; t < WF_SIZE / 32; t++) async_copy8(dst + lane + 32 * t, F + lane + 32 * t);
+            for (int t = 0; t < WF_SIZE / 64; t++) async_copy16(dst + 64 * t, F + 64 * t);
         }
         async_commit();
     }
@@ -660,8 +670,13 @@ struct WarpSqp {
             issue_factor_copy(lane, N - 1, ring);
             issue_factor_copy(lane, N - 2, ring);
             issue_factor_copy(lane, N - 3, ring);
-            MPCC_ROLLED
-            for (int e = lane; e < S * HZ; e += 32) async_copy8(GS_ + e, G + e);
+            if (((GS_ - SC) & 1) == 0) {  // pairs; an odd S * HZ copies one unused double (kappa's first slot, written later)
+                MPCC_ROLLED
+                for (int e = lane; 2 * e < S * HZ; e += 32) async_copy16(GS_ + 2 * e, G + 2 * e);
+            } else {
+                MPCC_ROLLED
+                for (int e = lane; e < S * HZ; e += 32) async_copy8(GS_ + e, G + e);
+            }
             async_commit();
             if (lane < 16) V[V_D0 + lane] = 0.0;
             async_wait<0>();
