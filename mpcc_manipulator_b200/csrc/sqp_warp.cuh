@@ -101,6 +101,12 @@ MPCC_HD void async_copy8(double* smem_dst, const double* gsrc) {
     *smem_dst = *gsrc;
 #endif
 }
+#if defined(__CUDA_ARCH__)
+// D (8x8) += A (8x4, row) * B (4x8, col) on the FP64 tensor path.  Lane l holds A[l >> 2][l & 3], B[l & 3][l >> 2], D[l >> 2][2 (l & 3) + {0, 1}].
+__device__ __forceinline__ void warp_dmma884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+#endif
 // 16-byte variant: both addresses 16-byte aligned; copies smem_dst[0..1]
 MPCC_HD void async_copy16(double* smem_dst, const double* gsrc) {
 #if defined(__CUDA_ARCH__)
@@ -515,8 +521,33 @@ struct WarpSqp {
                     const int i = e / 9, c = e - i * 9;
                     FF[e] = (i < 7) ? d_bq(i) * Pc[i * 16 + c] + Pc[(9 + i) * 16 + c] : d_bs() * Pc[7 * 16 + c] + d_bv() * Pc[8 * 16 + c];
                 }
-                // F2 (same phase: independent of FF): U = sum_p (w_p g_p) g_p'  in 2 x 2 register blocks, upper triangle + mirror
-                if (lane < 28) {
+                // F2 (same phase: independent of FF): U = sum_p (w_p g_p) g_p'
+#if defined(__CUDA_ARCH__)
+                {
+                    // (14 x 11)(11 x 14) padded to 16 x 12 x 16: 2 x 2 fragments x 3 k-steps of mma.m8n8k4.f64; as in F6 the A
+                    // fragment of block row m is w times the B fragment of block column m
+                    const int fr = lane >> 2, fq = lane & 3;
+                    double gf[2][3], wf[3];
+#pragma unroll
+                    for (int ks = 0; ks < 3; ks++) {
+                        const int p = ks * 4 + fq;
+                        wf[ks] = (p < NPOLY) ? WP[p] : 0.0;
+#pragma unroll
+                        for (int m = 0; m < 2; m++) { const int a = m * 8 + fr; gf[m][ks] = (p < NPOLY && a < 14) ? GS[p * 14 + a] : 0.0; }
+                    }
+#pragma unroll
+                    for (int mb = 0; mb < 2; mb++)
+#pragma unroll
+                        for (int nb = 0; nb < 2; nb++) {
+                            double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+                            for (int ks = 0; ks < 3; ks++) warp_dmma884(c0, c1, wf[ks] * gf[mb][ks], gf[nb][ks]);
+                            const int a = mb * 8 + fr, b0 = nb * 8 + 2 * fq;
+                            if (a < 14 && b0 < 14) { U[a * 14 + b0] = c0; U[a * 14 + b0 + 1] = c1; }
+                        }
+                }
+#else
+                if (lane < 28) {  // 2 x 2 register blocks, upper triangle + mirror
                     int bi = 0, t = lane;
                     while (t >= 7 - bi) { t -= 7 - bi; bi++; }
                     const int bj = bi + t;
@@ -535,6 +566,7 @@ struct WarpSqp {
                         U[(2 * bj) * 14 + 2 * bi + 1] = a10; U[(2 * bj + 1) * 14 + 2 * bi + 1] = a11;
                     }
                 }
+#endif
             });
             // F3: Mnn (8 x 8), Mnx (8 x 16) and [Mxx 0; 0 Mww] (16 x 16)
             W.each([&](int lane) {
@@ -625,8 +657,28 @@ struct WarpSqp {
                 return !pd;
             });
             if (bad) { ok = false; break; }
-            // F6: P_k = [Mxx 0; 0 Mww] - Lam' Lam  in 4 x 2 register blocks; F7: store the factor record
+            // F6: P_k = [Mxx 0; 0 Mww] - Lam' Lam; F7: store the factor record
             W.each([&](int lane) {
+#if defined(__CUDA_ARCH__)
+                // 16 x 16 += (16 x 8)(8 x 16) as 2 x 2 fragments x 2 k-steps of mma.m8n8k4.f64: the A fragment of block row m
+                // and the B fragment of block column m hold the same Lam entries, so a lane loads 4 doubles and 4 pairs
+                const int fr = lane >> 2, fq = lane & 3;
+                double lf[2][2];
+#pragma unroll
+                for (int m = 0; m < 2; m++)
+#pragma unroll
+                    for (int ks = 0; ks < 2; ks++) lf[m][ks] = Lam[(ks * 4 + fq) * 16 + m * 8 + fr];
+#pragma unroll
+                for (int mb = 0; mb < 2; mb++)
+#pragma unroll
+                    for (int nb = 0; nb < 2; nb++) {
+                        const int o = (mb * 8 + fr) * 16 + nb * 8 + 2 * fq;
+                        double c0 = PM[o], c1 = PM[o + 1];
+                        warp_dmma884(c0, c1, -lf[mb][0], lf[nb][0]);
+                        warp_dmma884(c0, c1, -lf[mb][1], lf[nb][1]);
+                        Pc[o] = c0; Pc[o + 1] = c1;
+                    }
+#else
                 const int r0 = 4 * (lane >> 3), c0 = 2 * (lane & 7);
                 double acc[4][2];
 #pragma unroll
@@ -639,6 +691,7 @@ struct WarpSqp {
                 }
 #pragma unroll
                 for (int a = 0; a < 4; a++) { Pc[(r0 + a) * 16 + c0] = acc[a][0]; Pc[(r0 + a) * 16 + c0 + 1] = acc[a][1]; }
+#endif
                 double* F = FACT + (size_t)k * WF_SIZE;
                 MPCC_ROLLED
                 for (int e = lane; e < WF_SIZE; e += 32) F[e] = X[e];  // X and Lam are contiguous in the scratch
