@@ -173,14 +173,14 @@ MPCC_HD void block9_pd_nan(const double* Qp, bool& pd, bool& nan) {
 #pragma unroll
         for (int t = 0; t < 9; t++) if (t < j) d -= A[sym9(j, t)] * A[sym9(j, t)];
         if (!stop && !(d > 0.0)) { stop = true; if (d == d) pd = false; }
-        const double sd = sqrt(d);
+        const double isd = 1.0 / sqrt(d);  // one division per column (the verdict only needs the pivots' signs)
 #pragma unroll
         for (int i = 0; i < 9; i++)
             if (i > j) {
                 double v = A[sym9(i, j)];
 #pragma unroll
                 for (int t = 0; t < 9; t++) if (t < j) v -= A[sym9(i, t)] * A[sym9(j, t)];
-                A[sym9(i, j)] = v / sd;
+                A[sym9(i, j)] = v * isd;
             }
     }
 }
