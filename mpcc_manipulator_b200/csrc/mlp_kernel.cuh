@@ -12,8 +12,10 @@
 //
 // Mapping.  One persistent CTA per SM walks over tiles of 8 samples = 64 columns.  The activation
 // tile X (256 x 64 doubles, 128 KB) stays in shared memory across all layers of both networks; the
-// weights stream from L2 through a double-buffered 2 x 32 KB shared-memory ring with cp.async, in
-// chunks pre-packed on the host in exactly the order the lanes read them.
+// weights stream from L2 through shared memory with cp.async in chunks pre-packed on the host in exactly
+// the order the lanes read them.  A warp only ever reads the A fragments of its own neurons, so every
+// warp owns a private double-buffered ring (2 x 4 KB) that it fills and waits for by itself: the CTA
+// only synchronises where the activation tile changes hands (twice per layer), not once per chunk.
 // The contraction runs on the FP64 tensor path, mma.sync.m8n8k4.f64 (DMMA): tcgen05 has no f64 kind,
 // and on sm_100 DMMA and DFMA share one pipe of the same peak (tools/probes/fp64_pipes_probe.cu) --
 // what DMMA buys is operand traffic: a warp owns 32 neurons x 64 columns as 4 x 8 fragments and needs
@@ -75,13 +77,13 @@ __device__ __forceinline__ int xslot(int q, int s) { return 8 * (s >> 1) + ((q +
 __device__ __forceinline__ int xl2(int k, int j, int s) { return ((k >> 2) * 4 + j) * 32 + xslot(k & 3, s); }
 
 // one 16-k-step chunk of a 256-neuron layer: the warp's 32 neurons (4 m-fragments) x 64 columns (8 n-fragments).
-//   Wc: chunk as double2 [kb 4][warp 8][m-pair 2][lane 32]   Xs: activation tile, kb0 = first 4-k block of the chunk
+//   Wc: the warp's slice of the chunk as double2 [kb 4][m-pair 2][lane 32]   Xs: activation tile, kb0 = first 4-k block of the chunk
 //   bslot = xslot(lane & 3, lane >> 2): where this lane's B-fragment element sits in a 32-slot row of Xs
-__device__ __forceinline__ void mlp_chunk(const double2* __restrict__ Wc, const double2* __restrict__ Xs, int kb0, int warp, int lane, int bslot,
+__device__ __forceinline__ void mlp_chunk(const double2* __restrict__ Wc, const double2* __restrict__ Xs, int kb0, int lane, int bslot,
                                           double (&acc)[4][8][2]) {
 #pragma unroll
     for (int kb = 0; kb < MLP_KC / 4; kb++) {
-        const double2 a01 = Wc[((kb * 8 + warp) * 2 + 0) * 32 + lane], a23 = Wc[((kb * 8 + warp) * 2 + 1) * 32 + lane];
+        const double2 a01 = Wc[(kb * 2 + 0) * 32 + lane], a23 = Wc[(kb * 2 + 1) * 32 + lane];
         double2 b[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) b[j] = Xs[((kb0 + kb) * 4 + j) * 32 + bslot];
@@ -114,16 +116,18 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp(MlpArgs a) {
 
     int p = 0;    // position in the chunk sequence
     int buf = 0;  // ring slot holding chunk p
+    constexpr int SLICE2 = MLP_CHUNK_D / 2 / 8;  // double2 per warp and chunk (4 KB)
+    double2* Wmine = Wbuf + warp * (2 * SLICE2);  // this warp's two ring slots
     auto prefetch = [&](int chunk, int slot) {
-        const double2* src = reinterpret_cast<const double2*>(a.wpack) + (size_t)chunk * (MLP_CHUNK_D / 2);
-        double2* dst = Wbuf + slot * (MLP_CHUNK_D / 2);
+        const double2* src = reinterpret_cast<const double2*>(a.wpack) + ((size_t)chunk * 8 + warp) * SLICE2;
+        double2* dst = Wmine + slot * SLICE2;
 #pragma unroll
-        for (int i = 0; i < (MLP_CHUNK_D / 2) / MLP_THREADS; i++) cp_async16(dst + tid + i * MLP_THREADS, src + tid + i * MLP_THREADS);
+        for (int i = 0; i < SLICE2 / 32; i++) cp_async16(dst + lane + i * 32, src + lane + i * 32);
         cp_async_commit();
     };
-    auto next_chunk = [&]() {  // chunk p has landed for everyone; start fetching p + 1 into the slot the previous chunk used
+    auto next_chunk = [&]() {  // the warp's slice of chunk p has landed; start fetching p + 1 into the slot the previous chunk used
         cp_async_wait_all();
-        __syncthreads();
+        __syncwarp();
         prefetch((p + 1) % MLP_NCHUNK, buf ^ 1);
     };
     auto advance = [&]() { buf ^= 1; p = (p + 1) % MLP_NCHUNK; };
@@ -153,6 +157,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp(MlpArgs a) {
 #pragma unroll
                 for (int j = 0; j < 4; j++) Xs[xl2(k, j, tx)] = make_double2(v[2 * j], v[2 * j + 1]);
             }
+            __syncthreads();  // X0 is in place
             const int n_hidden = (net == 0) ? 4 : 1;  // layers producing 256 neurons
             for (int layer = 0; layer < n_hidden; layer++) {
                 double acc[4][8][2];
@@ -163,7 +168,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp(MlpArgs a) {
                 const int nch = (layer == 0) ? 2 : 16;
                 for (int ch = 0; ch < nch; ch++) {
                     next_chunk();
-                    mlp_chunk(Wbuf + buf * (MLP_CHUNK_D / 2), Xs, ch * (MLP_KC / 4), warp, lane, bslot, acc);
+                    mlp_chunk(Wmine + buf * SLICE2, Xs, ch * (MLP_KC / 4), lane, bslot, acc);
                     advance();
                 }
                 // bias + ReLU mask, then the tile becomes the next layer's input
@@ -185,10 +190,10 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp(MlpArgs a) {
                             Xs[xl2(row, j, s)] = on ? make_double2(v0, v1) : make_double2(0.0, 0.0);
                         }
                     }
+                __syncthreads();  // the layer's output is in place
             }
             if (net == 0) {
                 // ---- env output layer: 9 x 256 as two m-fragments (rows 0..7, row 8); warp = column kind ----
-                __syncthreads();
                 double o[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};  // [k parity][m-fragment][sample]
                 const double* xb = Xd + ((warp >> 1) * 32 + bslot) * 2 + (warp & 1);
 #pragma unroll 4
@@ -223,10 +228,10 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp(MlpArgs a) {
                 for (int c = 0; c < 8; c++) acc[c][0] = acc[c][1] = 0.0;
                 for (int ch = 0; ch < 4; ch++) {
                     next_chunk();
-                    const double2* Wc = Wbuf + buf * (MLP_CHUNK_D / 2);  // [kb pair 8][warp 8][lane 32] -> {kb even, kb odd}
+                    const double2* Wc = Wmine + buf * SLICE2;  // [kb pair 8][lane 32] -> {kb even, kb odd}
 #pragma unroll 2
                     for (int kp = 0; kp < 8; kp++) {
-                        const double2 a2 = Wc[(kp * 8 + warp) * 32 + lane];
+                        const double2 a2 = Wc[kp * 32 + lane];
 #pragma unroll
                         for (int h = 0; h < 2; h++) {
                             const int kb = ch * 16 + kp * 2 + h;
@@ -290,14 +295,15 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp(MlpArgs a) {
 
 // Host-side packing of both networks' hidden-layer weights into the chunk stream k_mlp consumes (A fragments of
 // mma.m8n8k4: lane l holds neuron l >> 2 of its m-fragment at k-step l & 3 of the 4-k block).
-//   256-neuron layer, chunk = 16 k-steps:  [kb 4][warp 8][m-pair 2][lane 32][e 2]   = W[32 warp + (2 mp + e) 8 + (l >> 2)][k0 + 4 kb + (l & 3)]
-//   self layer 1 (64 neurons), chunk = 64 k-steps: [kb pair 8][warp 8][lane 32][h 2] = W[8 warp + (l >> 2)][64 ch + 4 (2 kp + h) + (l & 3)]
+//   256-neuron layer, chunk = 16 k-steps:  [warp 8][kb 4][m-pair 2][lane 32][e 2]   = W[32 warp + (2 mp + e) 8 + (l >> 2)][k0 + 4 kb + (l & 3)]
+//   self layer 1 (64 neurons), chunk = 64 k-steps: [warp 8][kb pair 8][lane 32][h 2] = W[8 warp + (l >> 2)][64 ch + 4 (2 kp + h) + (l & 3)]
+// (a warp's slice of a chunk is contiguous: 512 doubles)
 // Layer 0 of each net is zero-padded from 30 / 21 encoded inputs to K = 32.
 inline void pack_mlp_weights(const double* const env_W[5], const double* const self_W[3], double* out) {
     auto pack256 = [&](const double* W, int in_dim, int k_pad, double*& o) {
         for (int k0 = 0; k0 < k_pad; k0 += MLP_KC)
-            for (int kb = 0; kb < MLP_KC / 4; kb++)
-                for (int warp = 0; warp < 8; warp++)
+            for (int warp = 0; warp < 8; warp++)
+                for (int kb = 0; kb < MLP_KC / 4; kb++)
                     for (int mp = 0; mp < 2; mp++)
                         for (int l = 0; l < 32; l++)
                             for (int e = 0; e < 2; e++) {
@@ -312,8 +318,8 @@ inline void pack_mlp_weights(const double* const env_W[5], const double* const s
     pack256(env_W[3], 256, 256, o);
     pack256(self_W[0], 21, 32, o);
     for (int ch = 0; ch < 4; ch++)
-        for (int kp = 0; kp < 8; kp++)
-            for (int warp = 0; warp < 8; warp++)
+        for (int warp = 0; warp < 8; warp++)
+            for (int kp = 0; kp < 8; kp++)
                 for (int l = 0; l < 32; l++)
                     for (int h = 0; h < 2; h++) {
                         const int row = 8 * warp + (l >> 2), k = 64 * ch + 4 * (2 * kp + h) + (l & 3);
