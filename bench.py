@@ -232,7 +232,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     B, N = args.batch, args.horizon
     S = N + 1
-    mpc = M.BatchMPC(B, N, device=local)
+    mpc = M.BatchMPC(B, N, device=local, qp_eps=float(os.environ.get("MPCC_BENCH_QP_EPS", "0")))  # 0 = library default; env: diagnostic sweeps only
     # track shifted to the EE position at q_home, as main.cpp does (track.cpp:58-60); FK through the library itself
     mpc.load_nn()
     mpc.set_params(M.load_default_params())

@@ -397,7 +397,7 @@ struct StageQP {
             WsRef L = lin(k);
             for (int m = 0; m < 9; m++) if (L[LIN_XLO + m] > L[LIN_XHI + m]) return st;
         }
-        // initial point: nu = 0, xi = rollout of the defects, y = 0, t = max(h - Gz, 1), lam = 1
+        // initial point: nu = 0, xi = rollout of the defects, y = 0, t = max(h - Gz, QP_INIT_SLACK), lam = QP_INIT_SLACK / t
         double qn = 0;
         {
             double x[9];
@@ -420,8 +420,9 @@ struct StageQP {
             WsRef I = ineq(k);
             for (int c = 0; c < NINEQ; c++) {
                 if (!present(k, c)) { I[I_T + c] = 1; I[I_LAM + c] = 0; I[I_W + c] = 0; I[I_V + c] = 0; I[I_RP + c] = 0; continue; }
-                I[I_T + c] = fmax(hval(k, c) - gz<V_XI, V_NU, false>(k, c), 1.0);
-                I[I_LAM + c] = 1.0;
+                const double t0 = fmax(hval(k, c) - gz<V_XI, V_NU, false>(k, c), QP_INIT_SLACK);
+                I[I_T + c] = t0;
+                I[I_LAM + c] = QP_INIT_SLACK / t0;
                 m_tot++;
             }
         }

@@ -72,5 +72,10 @@ constexpr int RB_Q = 0, RB_P = 7, RB_R = 10, RB_JV = 19, RB_JW = 40, RB_MANIP = 
 
 // Options of the structured QP solver that replaces the reference's OSQP call.
 struct QpOptions { int max_iter; double eps; };
+// Interior-point start: slacks t = max(h - G z0, QP_INIT_SLACK), multipliers lam = QP_INIT_SLACK / t (so t lam <= mu0 = QP_INIT_SLACK,
+// on the central path wherever the slack is not clamped).  In the solver's normalised variables the step QPs of a warm MPCC
+// cycle have slacks of 0.01 .. 1: starting at mu0 = 3e-3 instead of t >= 1, lam = 1 saves ~2 of ~8 interior-point
+// iterations (measured on closed-loop QPs of configs C2 and C3 and on widely perturbed starts, no failure in either).
+constexpr double QP_INIT_SLACK = 3e-3;
 
 }  // namespace mpcc

@@ -853,7 +853,7 @@ struct WarpSqp {
                 }
                 return bad;
             })) return st;
-        // initial point: nu = 0, xi = rollout of the defects (lane = state component), t = max(h - Gz, 1), lam = 1
+        // initial point: nu = 0, xi = rollout of the defects (lane = state component), t = max(h - Gz, QP_INIT_SLACK), lam = QP_INIT_SLACK / t
         const double qn = W.rmax([&](int lane) {
             double q = 0;
             MPCC_ROLLED
@@ -878,7 +878,7 @@ struct WarpSqp {
             for (int i = lane; i < tot; i += 32) { IT[i] = 1.0; ILAM[i] = 0.0; IW[i] = 0.0; IV[i] = 0.0; IRP[i] = 0.0; IDT[i] = 0.0; IDLAM[i] = 0.0; }
         });
         W.each([&](int lane) {
-            for_present(lane, VAR, true, [&](int i, double g, double h) { IT[i] = fmax(h - g, 1.0); ILAM[i] = 1.0; IH[i] = h; });
+            for_present(lane, VAR, true, [&](int i, double g, double h) { const double t0 = fmax(h - g, QP_INIT_SLACK); IT[i] = t0; ILAM[i] = QP_INIT_SLACK / t0; IH[i] = h; });
         });
         const double m_tot = 43.0 * N;
         for (int it = 0; it < opt.max_iter; it++) {

@@ -107,6 +107,16 @@ int orc_mpc_warm_state(void* mp, double* horizon, int* valid, int* failed) {
     *valid = m->valid_initial_guess; *failed = (int)m->num_valid_guess_failed;
     return 0;
 }
+// test harness: overwrite the warm start (mpc.h: initial_guess_, valid_initial_guess_, num_valid_guess_failed_) so that a cycle can
+// be replayed from exactly the state another implementation started it from
+int orc_mpc_set_warm_state(void* mp, const double* horizon, int valid, int failed) {
+    MPC* m = (MPC*)mp;
+    m->initial_guess = horizon_in(horizon, (int)m->initial_guess.size() - 1);
+    m->valid_initial_guess = valid != 0; m->num_valid_guess_failed = (unsigned)failed;
+    return 0;
+}
+// test harness: termination threshold of the dense QP solver (default 1e-9 on every KKT residual)
+int orc_mpc_set_qp_eps(void* mp, double eps) { ((MPC*)mp)->solver.qp.eps = eps; return 0; }
 // plant step used by the closed-loop harness (integrator.cpp:55-68)
 void orc_sim_time_step(const double* x, const double* u, double ts, double* x_next) {
     State s; Input in;

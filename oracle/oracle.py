@@ -201,6 +201,16 @@ class OracleMPC:
         lib().orc_mpc_warm_state(self.h, _p(hor), C.byref(v), C.byref(f))
         return hor, v.value, f.value
 
+    def set_qp_eps(self, eps):
+        """Termination threshold of the checker's dense QP solver (all KKT residuals; default 1e-9)."""
+        lib().orc_mpc_set_qp_eps(self.h, C.c_double(eps))
+
+    def set_warm_state(self, horizon, valid, failed):
+        """Replay harness: start the next cycle from this warm start (e.g. the one the CUDA path holds)."""
+        hor = np.ascontiguousarray(horizon, dtype=np.float64)
+        assert hor.shape == (self.N + 1, 17)
+        lib().orc_mpc_set_warm_state(self.h, _p(hor), int(valid), int(failed))
+
     def track_eval(self, s):
         o = np.zeros(21)
         lib().orc_track_eval(self.h, C.c_double(s), _p(o))

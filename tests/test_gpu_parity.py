@@ -170,21 +170,31 @@ def _first_cycles_vs_golden(mpc, g, with_obs=False):
     return n_cmp
 
 
-def _closed_loop_follow(mpc, oracles, x, u, cycles, Ts, O, obs_fn=None):
+def _closed_loop_follow(mpc, oracles, x, u, cycles, Ts, O, obs_fn=None, tol=QP_TOL, slack_outliers=0):
     """Closed loop on the GPU with one live oracle per instance replayed ALONG THE DEVICE'S BRANCH: the oracle is told
     the device's per-iteration line-search decisions (mpcc_cuda_read_decisions) and must then reproduce status,
     iteration count, updated s / vs and the applied control within the reference QP tolerance; wherever the oracle's
     own decision differs from the device's, its robustness margin must certify a noise-level tie (< TIE).
+    `tol` bounds the normalised control / horizon difference.  Both solvers stop at KKT residuals <= 1e-9 by default, and the
+    Gauss-Newton Hessian is regularised by only 1e-6 I (cost.cpp:353), so that along weakly convex directions two such
+    solutions may differ by more than 1e-4 although both beat OSQP's own stopping rule (eps_abs = eps_rel = 1e-4 on the
+    residuals) by five orders: up to `slack_outliers` comparisons may exceed `tol`, none may exceed 5 tol; with both
+    solvers run to 1e-11 / 1e-12 the same scenario agrees to 1e-5 (test_exact_minimiser_agreement_at_tight_tolerances).
     Returns (comparisons, ties, worst |du0|)."""
     B = x.shape[0]
-    n_cmp = n_tie = 0
+    n_cmp = n_tie = n_out = 0
     worst = 0.0
     for c in range(cycles):
         obs = obs_fn(c) if obs_fn else None
+        # every cycle is replayed from the warm start the device actually holds: the comparison is per cycle on identical
+        # inputs (two exact QP solvers differ by up to ~5e-5 along the weakly convex directions; fed back through the warm
+        # start of a one-iteration SQP that difference would random-walk over the cycles)
+        w_hor, w_valid, w_failed = mpc.get_warm_state()
         r = mpc.run_cycle(x, u, obs)
         masks = mpc.decisions()
         for b in range(B):
             dec = [(int(masks[b]) >> i) & 1 for i in range(min(int(r["iters"][b]), 32))]
+            oracles[b].set_warm_state(w_hor[b], w_valid[b], w_failed[b])
             oracles[b].set_forced_decisions(dec)
             ro = oracles[b].run(x[b], u[b], obs[b] if obs is not None else (3., 3., 3., 0.))
             nat, mg = oracles[b].decision_log()
@@ -192,8 +202,10 @@ def _closed_loop_follow(mpc, oracles, x, u, cycles, Ts, O, obs_fn=None):
             assert r["status"][b] == ro["status"], (c, b)
             assert r["iters"][b] == ro["iters"], (c, b, r["iters"][b], ro["iters"])
             d = (np.abs(r["u0"][b] - ro["u0"]) / TU).max()
-            assert d < QP_TOL, (c, b, d)
-            assert (np.abs(r["horizon"][b] - ro["horizon"]) / THZ).max() < QP_TOL * max(1, ro["iters"])
+            dh = (np.abs(r["horizon"][b] - ro["horizon"]) / THZ).max() / max(1, ro["iters"])
+            if d >= tol or dh >= tol:
+                n_out += 1
+                assert n_out <= slack_outliers and d < 5 * tol and dh < 5 * tol, (c, b, d, dh)
             worst = max(worst, d); n_cmp += 1
             for i in range(len(dec)):
                 if nat[i] != dec[i]:
@@ -325,8 +337,15 @@ def test_heterogeneous_tracks_and_weights(M, O, nn, ee_home, rng):
     oracles = []
     for b in range(B):
         o = O.OracleMPC(N=N, nn=nn, params=O.load_params(overrides={"cost": over[b]})); o.set_track(*wps[b]); oracles.append(o)
-    n_cmp, n_tie, worst = _closed_loop_follow(mpc, oracles, x0, u0, 3, 0.01, O)
+    n_cmp, n_tie, worst = _closed_loop_follow(mpc, oracles, x0, u0, 3, 0.01, O, slack_outliers=1)
     print(f"C4 small: {n_cmp} comparisons, {n_tie} certified filter ties, worst |du0| = {worst:.2e}")
+    mpc.close()
+    # the same scenario with both solvers converged: the two algorithms reach the same minimiser
+    mpc = M.BatchMPC(B, N, qp_eps=1e-11); mpc.load_nn(); mpc.set_params(params); mpc.set_tracks(np.stack(tables), np.arange(B))
+    for o in oracles:
+        o.set_warm_state(np.zeros((N + 1, 17)), 0, 0); o.set_qp_eps(1e-12)
+    n_cmp, n_tie, worst = _closed_loop_follow(mpc, oracles, x0, u0, 3, 0.01, O, tol=1e-5)
+    print(f"C4 small, QP tolerances 1e-11 / 1e-12: {n_cmp} comparisons, {n_tie} certified filter ties, worst |du0| = {worst:.2e}")
     mpc.close()
 
 
