@@ -259,7 +259,7 @@ def run_ours(args):
         """device-resident closed-loop step: cycle -> (gather) -> plant"""
         nonlocal x, xn
         mpc.run_cycle_device(x.data_ptr(), u.data_ptr())
-        launches["n"] += 5
+        launches["n"] += 6  # k_prologue, k_kin, k_mlp, k_order, k_sqp_warp x 2 (exclusive-SM launch + main launch); == mpcc_cuda_get_stats()[0]
         with torch.cuda.stream(stream):
             if world > 1:
                 # the path's only collective: gather the applied controls and per-instance status / iterations (NCCL)

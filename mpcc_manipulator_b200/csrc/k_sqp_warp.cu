@@ -7,6 +7,10 @@ namespace mpcc {
 
 // Launch order: instances that took many SQP iterations in one of the last four cycles go first, so that the long
 // tail of the batch starts at time zero (longest-processing-time-first; affects scheduling only, never results).
+// The first order[B] of them (>= 15 iterations lately: in practice the MAX_ITER "stragglers", which keep coming back
+// for a while) are solved by a second, small launch of the same kernel on a high-priority stream whose CTAs ask for so
+// much shared memory that each gets an SM of its own: a straggler's ~100 latency-bound evaluations and its first QP
+// run ~1.5x faster without nine other warps on the SM, and it is the stragglers that bound the kernel in those cycles.
 __global__ void k_order(const int32_t* __restrict__ hist, int32_t* __restrict__ order, int B) {
     __shared__ int cnt[16], base[16];
     if (threadIdx.x < 16) cnt[threadIdx.x] = 0;
@@ -19,7 +23,7 @@ __global__ void k_order(const int32_t* __restrict__ hist, int32_t* __restrict__ 
     };
     for (int b = threadIdx.x; b < B; b += blockDim.x) atomicAdd(&cnt[key(b)], 1);
     __syncthreads();
-    if (threadIdx.x == 0) { int s = 0; for (int i = 0; i < 16; i++) { base[i] = s; s += cnt[i]; } }
+    if (threadIdx.x == 0) { order[B] = cnt[0]; int s = 0; for (int i = 0; i < 16; i++) { base[i] = s; s += cnt[i]; } }  // order[B]: instances with >= 15 iterations lately
     __syncthreads();
     for (int b = threadIdx.x; b < B; b += blockDim.x) order[atomicAdd(&base[key(b)], 1)] = b;
 }
@@ -32,11 +36,17 @@ __global__ void k_order(const int32_t* __restrict__ hist, int32_t* __restrict__ 
 #define MPCC_SQPW_MINB 5
 #endif
 constexpr int SQPW_WARPS = MPCC_SQPW_WARPS;  // warps (instances) per CTA
-__global__ void __launch_bounds__(SQPW_WARPS * 32, MPCC_SQPW_MINB) k_sqp_warp(CycleArgs a, double* wws, size_t ws_per, size_t sm_per) {
+constexpr int SQPW_EXCL_CTAS = 8;            // CTAs of the exclusive launch (one SM each)
+// excl: 1 = exclusive launch (the first slots only), 0 = main launch (skips them), -1 = single launch (everything)
+__global__ void __launch_bounds__(SQPW_WARPS * 32, MPCC_SQPW_MINB) k_sqp_warp(CycleArgs a, double* wws, size_t ws_per, size_t sm_per, int excl) {
     extern __shared__ __align__(16) double sqpw_smem[];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int slot = blockIdx.x * SQPW_WARPS + wid;
     if (slot >= a.B) return;  // whole warps leave together
+    if (excl >= 0) {
+        const int n_excl = min(a.order[a.B], SQPW_EXCL_CTAS * SQPW_WARPS);
+        if ((excl == 1) != (slot < n_excl)) return;
+    }
     const int b = a.order[slot];
     const Params& P = a.params[a.params_per_instance ? b : 0];
     const TrackTable& T = a.tracks[a.track_id[b]];
@@ -106,14 +116,38 @@ static size_t sqp_warp_smem_pad() {
     return pad;
 }
 size_t sqp_warp_smem_bytes(int N) { return SQPW_WARPS * warp_smem_doubles(N) * sizeof(double) + sqp_warp_smem_pad(); }
+// shared memory request of the exclusive launch: leaves no room for a CTA of the main launch on the same SM
+static size_t sqp_warp_excl_smem_bytes(int N) {
+    const size_t normal = sqp_warp_smem_bytes(N), want = (size_t)227 * 1024 - normal;  // 227 KB = per-SM limit on sm_100
+    return want > normal ? want : normal;
+}
 cudaError_t configure_sqp_warp(int N) {
-    cudaError_t e = cudaFuncSetAttribute(k_sqp_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sqp_warp_smem_bytes(N));
+    cudaError_t e = cudaFuncSetAttribute(k_sqp_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sqp_warp_excl_smem_bytes(N));
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_solve_ocp_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sqp_warp_smem_bytes(N));
 }
-void launch_sqp_warp(const CycleArgs& a, double* wws, cudaStream_t s) {
-    k_order<<<1, 1024, 0, s>>>(a.hist, a.order, a.B);
-    k_sqp_warp<<<(a.B + SQPW_WARPS - 1) / SQPW_WARPS, SQPW_WARPS * 32, sqp_warp_smem_bytes(a.N), s>>>(a, wws, warp_ws_doubles(a.N), warp_smem_doubles(a.N));
+void launch_sqp_warp(const CycleArgs& a, double* wws, cudaStream_t s, cudaStream_t aux, cudaEvent_t ev_pre, cudaEvent_t ev_order, cudaEvent_t ev_aux) {
+    static const bool no_excl = getenv("MPCC_SQPW_NO_EXCL") != nullptr;  // diagnostic: everything in the main launch
+    if (no_excl) aux = nullptr;
+    const int grid = (a.B + SQPW_WARPS - 1) / SQPW_WARPS;
+    if (!aux) {
+        k_order<<<1, 1024, 0, s>>>(a.hist, a.order, a.B);
+        k_sqp_warp<<<grid, SQPW_WARPS * 32, sqp_warp_smem_bytes(a.N), s>>>(a, wws, warp_ws_doubles(a.N), warp_smem_doubles(a.N), -1);
+        return;
+    }
+    // The exclusive launch must get its SMs BEFORE the main launch fills the machine (a 180 KB CTA never fits next to
+    // resident 44 KB CTAs): it follows k_order in the auxiliary stream, so it starts the moment the order exists, while
+    // the main launch waits for the same order across streams.
+    cudaEventRecord(ev_pre, s);                    // RobotData and the previous cycle's history are complete
+    cudaStreamWaitEvent(aux, ev_pre, 0);
+    k_order<<<1, 1024, 0, aux>>>(a.hist, a.order, a.B);
+    cudaEventRecord(ev_order, aux);
+    const int gx = grid < SQPW_EXCL_CTAS ? grid : SQPW_EXCL_CTAS;
+    k_sqp_warp<<<gx, SQPW_WARPS * 32, sqp_warp_excl_smem_bytes(a.N), aux>>>(a, wws, warp_ws_doubles(a.N), warp_smem_doubles(a.N), 1);
+    cudaEventRecord(ev_aux, aux);
+    cudaStreamWaitEvent(s, ev_order, 0);
+    k_sqp_warp<<<grid, SQPW_WARPS * 32, sqp_warp_smem_bytes(a.N), s>>>(a, wws, warp_ws_doubles(a.N), warp_smem_doubles(a.N), 0);
+    cudaStreamWaitEvent(s, ev_aux, 0);
 }
 void launch_solve_ocp_warp(const CycleArgs& a, double* wws, double* guess, const double* rb, const double* cur_u, int n, double* steps, double* alphas,
                            int32_t* qp_ok, int max_log, int32_t* n_logged, cudaStream_t s) {

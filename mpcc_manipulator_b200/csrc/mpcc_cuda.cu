@@ -173,6 +173,8 @@ struct mpcc_cuda_handle {
     int64_t launches = 0;
     bool profiling = false;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // prologue | kin | mlp | sqp boundaries
+    cudaStream_t aux = nullptr;                 // high-priority stream of the exclusive-SM straggler launch
+    cudaEvent_t ev_pre = nullptr, ev_order = nullptr, ev_aux = nullptr;
     std::vector<double> h_params;  // host copy of set 0 (validation)
     std::vector<void*> allocs;
 
@@ -244,6 +246,14 @@ int mpcc_cuda_create(const mpcc_cuda_config* cfg, mpcc_cuda_handle** out) {
     h->num_sms = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     for (auto& e : h->ev) CK(cudaEventCreate(&e));
+    {
+        int lo = 0, hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CK(cudaStreamCreateWithPriority(&h->aux, cudaStreamNonBlocking, hi));
+        CK(cudaEventCreateWithFlags(&h->ev_pre, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_order, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_aux, cudaEventDisableTiming));
+    }
     const size_t B = h->B, S = h->S, HN = S * HZ;
     cudaError_t ae = cudaSuccess;
     auto A = [&](cudaError_t r) { if (ae == cudaSuccess) ae = r; };
@@ -256,7 +266,7 @@ int mpcc_cuda_create(const mpcc_cuda_config* cfg, mpcc_cuda_handle** out) {
     A(h->alloc(&h->d_qs, h->NS * DOF)); A(h->alloc(&h->d_rb, h->NS * RB_DOUBLES));
     A(h->alloc(&h->d_flags, B));
     A(h->alloc(&h->d_u_out, B * NU)); A(h->alloc(&h->d_horizon, B * HN));
-    A(h->alloc(&h->d_status, B)); A(h->alloc(&h->d_iters, B)); A(h->alloc(&h->d_ok, B)); A(h->alloc(&h->d_qp_iters, B)); A(h->alloc(&h->d_qp_fail, B)); A(h->alloc(&h->d_accept, B)); A(h->alloc(&h->d_sqp_ns, 4 * B)); A(h->alloc(&h->d_hist, B)); A(h->alloc(&h->d_order, B));
+    A(h->alloc(&h->d_status, B)); A(h->alloc(&h->d_iters, B)); A(h->alloc(&h->d_ok, B)); A(h->alloc(&h->d_qp_iters, B)); A(h->alloc(&h->d_qp_fail, B)); A(h->alloc(&h->d_accept, B)); A(h->alloc(&h->d_sqp_ns, 4 * B)); A(h->alloc(&h->d_hist, B)); A(h->alloc(&h->d_order, B + 1));
     A(h->alloc(&h->d_wpack, (size_t)MLP_NCHUNK * MLP_CHUNK_D)); A(h->alloc(&h->d_bias, MLP_BIAS_TOTAL));
     A(h->alloc(&h->d_w_out_env, 9 * 256)); A(h->alloc(&h->d_w_out_self, 64));
     if (ae != cudaSuccess) { mpcc_cuda_destroy(h); return fail(MPCC_ERR_CUDA, std::string("device allocation failed: ") + cudaGetErrorString(ae)); }
@@ -278,6 +288,10 @@ int mpcc_cuda_destroy(mpcc_cuda_handle* h) {
     for (void* p : h->allocs) cudaFree(p);
     if (h->d_params) cudaFree(h->d_params);
     if (h->d_tracks) cudaFree(h->d_tracks);
+    if (h->aux) cudaStreamDestroy(h->aux);
+    if (h->ev_pre) cudaEventDestroy(h->ev_pre);
+    if (h->ev_order) cudaEventDestroy(h->ev_order);
+    if (h->ev_aux) cudaEventDestroy(h->ev_aux);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return MPCC_OK;
@@ -473,7 +487,7 @@ int mpcc_cuda_run_cycle_device(mpcc_cuda_handle* h, double* d_x0, const double* 
     if (rc) return rc;
     if (prof) cudaEventRecord(h->ev[3], h->stream);
     if (h->cfg.sqp_kernel == 1) launch_sqp_thread(a, h->stream);
-    else { launch_sqp_warp(a, h->d_wws, h->stream); h->launches++; }  // + the launch-order kernel
+    else { launch_sqp_warp(a, h->d_wws, h->stream, h->aux, h->ev_pre, h->ev_order, h->ev_aux); h->launches += 2; }  // + the launch-order kernel, + the exclusive launch
     h->launches++;
     if (prof) cudaEventRecord(h->ev[4], h->stream);
     CK(cudaGetLastError());

@@ -1031,9 +1031,17 @@ struct WarpSqp {
                 // one dependent global load at a time inside stage_eval
                 double rbl[RB_DOUBLES];
                 {
+                    // (the joint angles are not read -- the evaluation point carries them -- and the Jacobians only by the
+                    //  full linearisation: 101 / 143 of the 150 doubles)
                     const double* src = rb + (size_t)k * rb_stage;
-#pragma unroll 10
-                    for (int e = 0; e < RB_DOUBLES; e++) rbl[e] = src[(size_t)e * rb_stride];
+#pragma unroll 12
+                    for (int e = RB_P; e < RB_JV; e++) rbl[e] = src[(size_t)e * rb_stride];
+                    if (FULL) {
+#pragma unroll 21
+                        for (int e = RB_JV; e < RB_MANIP; e++) rbl[e] = src[(size_t)e * rb_stride];
+                    }
+#pragma unroll 30
+                    for (int e = RB_MANIP; e < RB_DOUBLES; e++) rbl[e] = src[(size_t)e * rb_stride];
                 }
                 RbView rv{rbl, 1};
                 // the relaxed-barrier values of the polytopic rows are constant over the cycle: computed by the first

@@ -388,7 +388,7 @@ def test_instrumentation_and_counters(M, O, ee_home):
     qi, qf = mpc.qp_counters()
     st = mpc.stats()
     assert st["qp_iters"] == int(qi.sum()) and st["qp_fail"] == int(qf.sum()) and st["sqp_iters"] == int(r["iters"].sum())
-    assert st["launches"] == 5 and st["solved"] == B
+    assert st["launches"] == 6 and st["solved"] == B  # prologue, kin, mlp, order, sqp (exclusive + main launch)
     masks = mpc.decisions()
     assert np.all((masks & 1) == 1)  # the first trial of the first iteration meets an empty filter: always accepted
     mpc.close()
