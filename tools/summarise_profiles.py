@@ -23,16 +23,26 @@ def launches():
         ms = v / 1e6 if unit in ("ns", "nsecond") else v / 1e3 if unit in ("us", "usecond") else v
         a = agg.setdefault(r["Kernel Name"], [0, 0.0]); a[0] += 1; a[1] += ms
     per_cycle = {k: v for k, v in agg.items() if any(c in k for c in CYCLE)}
-    n_cycles = max(v[0] for k, v in per_cycle.items() if "k_sqp_warp" in k)
-    cyc_ms = sum(v[1] / v[0] * (v[0] / n_cycles if "k_kin" not in k and "k_mlp" not in k else 1) for k, v in per_cycle.items())
+    n_cycles = max(v[0] for k, v in per_cycle.items() if "k_order" in k)
+    def ms_per_cycle(k, v):  # k_kin / k_mlp also run once outside the cycles (probes): use their mean; k_sqp_warp runs twice per cycle
+        return v[1] / v[0] if ("k_kin" in k or "k_mlp" in k) else v[1] / n_cycles
+    cyc_ms = sum(ms_per_cycle(k, v) for k, v in per_cycle.items())
     lines = ["# Round 1 - ncu launch list (final build of the round)", "",
              "Command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline` (B = 4096, N = 20), run after the same command exited 0 without ncu.",
-             "Per-launch times are cold-cache and serialised: compare SHARES with the live CUDA-event numbers of bench.py (profiles/bench_r1_single_gpu.json: `kernels_ms`, `roofline.kernel_share_of_step`).", "",
-             "| kernel | launches | mean ms | share of cycle |", "|---|---|---|---|"]
+             "Per-launch times are cold-cache and serialised: compare SHARES with the live CUDA-event numbers of bench.py (profiles/bench_r1_single_gpu.json: `kernels_ms`, `roofline.kernel_share_of_step`).",
+             "`k_sqp_warp` is launched twice per cycle (exclusive-SM launch for predicted stragglers, often empty, + main launch): its row is per cycle.", "",
+             "| kernel | launches | ms per cycle (mean per launch outside the cycle) | share of cycle |", "|---|---|---|---|"]
     for k, (n, tot) in agg.items():
-        share = f"{100 * (tot / n) / cyc_ms:.2f}%" if k in per_cycle else "(outside the cycle)"
-        lines.append(f"| `{k[:70]}` | {n} | {tot / n:.3f} | {share} |")
-    lines += ["", f"Kernels of one control cycle (sum of means): {cyc_ms:.2f} ms under ncu.  The first cycles after `reset()` are cold starts (every instance runs several SQP iterations), which is why `k_sqp_warp`'s mean here is above the closed-loop average of bench.py."]
+        if k in per_cycle: lines.append(f"| `{k[:70]}` | {n} | {ms_per_cycle(k, (n, tot)):.3f} | {100 * ms_per_cycle(k, (n, tot)) / cyc_ms:.2f}% |")
+        else: lines.append(f"| `{k[:70]}` | {n} | {tot / n:.3f} | (outside the cycle) |")
+    lines += ["", f"Kernels of one control cycle: {cyc_ms:.2f} ms under ncu ({n_cycles} cycles captured).  The first cycles after `reset()` are cold starts (every instance runs several SQP iterations), which is why `k_sqp_warp`'s time here is above the closed-loop average of bench.py."]
+    try:
+        live = json.loads((OUT / "plain.log").read_text().strip().splitlines()[-1])
+        lines += ["", "Live CUDA-event shares of the SAME command run without ncu just before (timed cycles only): "
+                  + ", ".join(f"{k} {100 * v:.1f}%" for k, v in live["roofline"]["kernel_share_of_step"].items())
+                  + f" of {live['ms_per_step']:.2f} ms per step.  (The ncu list also contains the untimed warm-up cycles 0-2, which are cold starts, and serialises the two SQP launches.)"]
+    except Exception:
+        pass
     (PROF / "r1_launches.md").write_text("\n".join(lines) + "\n")
 
 KEEP = ["dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "gpu__time_duration.sum",
