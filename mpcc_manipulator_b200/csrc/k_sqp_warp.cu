@@ -36,9 +36,14 @@ __global__ void k_order(const int32_t* __restrict__ hist, int32_t* __restrict__ 
 #define MPCC_SQPW_MINB 5
 #endif
 constexpr int SQPW_WARPS = MPCC_SQPW_WARPS;  // warps (instances) per CTA
+#ifdef MPCC_SQPW_MAXNREG
+#define SQPW_BOUNDS __maxnreg__(MPCC_SQPW_MAXNREG)
+#else
+#define SQPW_BOUNDS __launch_bounds__(SQPW_WARPS * 32, MPCC_SQPW_MINB)
+#endif
 constexpr int SQPW_EXCL_CTAS = 8;            // CTAs of the exclusive launch (one SM each)
 // excl: 1 = exclusive launch (the first slots only), 0 = main launch (skips them), -1 = single launch (everything)
-__global__ void __launch_bounds__(SQPW_WARPS * 32, MPCC_SQPW_MINB) k_sqp_warp(CycleArgs a, double* wws, size_t ws_per, size_t sm_per, int excl) {
+__global__ void SQPW_BOUNDS k_sqp_warp(CycleArgs a, double* wws, size_t ws_per, size_t sm_per, int excl) {
     extern __shared__ __align__(16) double sqpw_smem[];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int slot = blockIdx.x * SQPW_WARPS + wid;
@@ -86,7 +91,7 @@ __global__ void __launch_bounds__(SQPW_WARPS * 32, MPCC_SQPW_MINB) k_sqp_warp(Cy
     }
 }
 // solveOCP probe, one warp per instance: AoS guess / RobotData, optional iteration log
-__global__ void __launch_bounds__(SQPW_WARPS * 32, MPCC_SQPW_MINB) k_solve_ocp_warp(CycleArgs a, double* wws, size_t ws_per, size_t sm_per, double* guess, const double* rb,
+__global__ void SQPW_BOUNDS k_solve_ocp_warp(CycleArgs a, double* wws, size_t ws_per, size_t sm_per, double* guess, const double* rb,
                                                                     const double* cur_u_all, int n, double* steps, double* alphas, int32_t* qp_ok, int max_log, int32_t* n_logged) {
     extern __shared__ __align__(16) double sqpw_smem[];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
