@@ -63,7 +63,7 @@ typedef struct {
     int32_t qp_max_iter;  /* interior-point iteration cap of the structured QP solver (0 -> 60) */
     double qp_eps;        /* its residual tolerance (0 -> 1e-9) */
     int32_t sqp_kernel;   /* 0: default (warp-cooperative when available), 1: one thread per instance */
-    int32_t reserved;
+    int32_t reserved;     /* bit 0 (diagnostic): 1 = no exclusive-SM launch for recent long runners (scheduling only, same results) */
 } mpcc_cuda_config;
 
 typedef struct mpcc_cuda_handle mpcc_cuda_handle;

@@ -104,9 +104,9 @@ def fp64_peak(device=0):
 class BatchMPC:
     """Batch of independent mpcc::MPC objects on one GPU (reference cpp/include/MPC/mpc.h:58-101)."""
 
-    def __init__(self, batch, horizon=10, Ts=0.01, device=0, qp_max_iter=0, qp_eps=0.0, sqp_kernel=0):
+    def __init__(self, batch, horizon=10, Ts=0.01, device=0, qp_max_iter=0, qp_eps=0.0, sqp_kernel=0, flags=0):
         self.B, self.N, self.S, self.Ts = int(batch), int(horizon), int(horizon) + 1, float(Ts)
-        cfg = Config(self.B, self.N, self.Ts, device, qp_max_iter, qp_eps, sqp_kernel, 0)
+        cfg = Config(self.B, self.N, self.Ts, device, qp_max_iter, qp_eps, sqp_kernel, flags)  # flags -> mpcc_cuda_config.reserved
         self.h = C.c_void_p()
         _check(lib().mpcc_cuda_create(C.byref(cfg), C.byref(self.h)))
 

@@ -132,7 +132,7 @@ cudaError_t configure_sqp_warp(int N) {
     return cudaFuncSetAttribute(k_solve_ocp_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sqp_warp_smem_bytes(N));
 }
 void launch_sqp_warp(const CycleArgs& a, double* wws, cudaStream_t s, cudaStream_t aux, cudaEvent_t ev_pre, cudaEvent_t ev_order, cudaEvent_t ev_aux) {
-    static const bool no_excl = getenv("MPCC_SQPW_NO_EXCL") != nullptr;  // diagnostic: everything in the main launch
+    static const bool no_excl = getenv("MPCC_SQPW_NO_EXCL") != nullptr;  // diagnostic (as mpcc_cuda_config.reserved bit 0): everything in the main launch
     if (no_excl) aux = nullptr;
     const int grid = (a.B + SQPW_WARPS - 1) / SQPW_WARPS;
     if (!aux) {

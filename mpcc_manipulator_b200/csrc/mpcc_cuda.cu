@@ -487,7 +487,7 @@ int mpcc_cuda_run_cycle_device(mpcc_cuda_handle* h, double* d_x0, const double* 
     if (rc) return rc;
     if (prof) cudaEventRecord(h->ev[3], h->stream);
     if (h->cfg.sqp_kernel == 1) launch_sqp_thread(a, h->stream);
-    else { launch_sqp_warp(a, h->d_wws, h->stream, h->aux, h->ev_pre, h->ev_order, h->ev_aux); h->launches += 2; }  // + the launch-order kernel, + the exclusive launch
+    else { launch_sqp_warp(a, h->d_wws, h->stream, (h->cfg.reserved & 1) ? nullptr : h->aux, h->ev_pre, h->ev_order, h->ev_aux); h->launches += (h->cfg.reserved & 1) ? 1 : 2; }  // + the launch-order kernel (+ the exclusive launch)
     h->launches++;
     if (prof) cudaEventRecord(h->ev[4], h->stream);
     CK(cudaGetLastError());

@@ -409,3 +409,27 @@ def test_thread_per_instance_kernel_agrees_with_warp_kernel(M, O, ee_home, rng):
     assert np.median(err[same]) < 1e-9           # same branch, same arithmetic up to reduction order
     assert (err[same] < QP_TOL).sum() >= same.sum() - 2 and err.max() < 0.05   # a tie inside the back-tracking may still split one or two
     a.close(); b.close()
+
+
+def test_exclusive_sm_launch_changes_scheduling_only(M, O, ee_home):
+    """The instances with >= 15 SQP iterations in one of the last four cycles are solved by a second launch of the same
+    kernel on SMs of their own (k_sqp_warp.cu).  Same per-instance code, so a handle with that launch disabled
+    (mpcc_cuda_config.reserved bit 0) must give bit-identical results, cycle after cycle, also in the cycles in which the
+    MAX_ITER stragglers of the start-up transient recur."""
+    B, N = 2048, 20
+    rng = np.random.default_rng(3)
+    a = make_mpc(M, B, N, ee_home)
+    b = M.BatchMPC(B, N, flags=1); b.setup_default(init_position=ee_home)
+    x = np.tile(np.r_[O.Q_HOME, 0., 0.], (B, 1)); x[:, :7] += rng.uniform(-0.05, 0.05, (B, 7)); u = np.zeros((B, 8))
+    long_runs = recurrences = 0
+    seen = np.zeros(B, bool)
+    for c in range(9):
+        ra, rb_ = a.run_cycle(x, u, want_horizon=False), b.run_cycle(x, u, want_horizon=False)
+        assert np.array_equal(ra["status"], rb_["status"]) and np.array_equal(ra["iters"], rb_["iters"]) and np.array_equal(ra["u0"], rb_["u0"])
+        assert np.array_equal(ra["x0"], rb_["x0"]) and np.array_equal(a.decisions(), b.decisions())
+        lr = ra["iters"] >= 15
+        long_runs += int(lr.sum()); recurrences += int((lr & seen).sum()); seen |= lr
+        u = ra["u0"]; x = a.sim_time_step(ra["x0"], u, 0.01)
+    assert long_runs > 0 and recurrences > 0   # the exclusive launch did have work, including long runs (not only quick ones)
+    assert a.stats()["launches"] == 6 and b.stats()["launches"] == 5
+    a.close(); b.close()

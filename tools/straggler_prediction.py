@@ -16,5 +16,7 @@ for c in range(24):
     prev = np.max(np.stack(hist[-4:]), axis=0) if hist else np.zeros(B, int)
     pred = prev >= 15
     print(f"cycle {c}: stragglers {len(s)}, of which predicted {int(pred[s].sum())}; predicted set size {int(pred.sum())}; straggler ms {np.round(t[s], 1)} predicted? {pred[s].astype(int)}")
+    if len(s) and hist:
+        print("      their iteration counts in the previous cycles:", [[int(h[i]) for h in hist[-3:]] for i in s], "| population share with >= 3 iterations last cycle:", float((hist[-1] >= 3).mean()))
     hist.append(it)
     u0 = r["u0"]; x0 = mpc.sim_time_step(r["x0"], u0)
