@@ -358,7 +358,7 @@ def run_ours(args):
         names = ["k_prologue", "k_kin", "k_mlp", "k_sqp_warp"]
         dom = int(np.argmax(km))
         peak = M.fp64_peak(local)
-        peak_src = ("FP64 FMA microbenchmark measured in this run (mpcc_cuda_fp64_peak); MEASURED_PEAKS.json holds no FP64 figure; "
+        peak_src = ("FP64 microbenchmark measured in this run (mpcc_cuda_fp64_peak: larger of the DFMA and the mma.m8n8k4.f64 figure, one shared pipe); MEASURED_PEAKS.json holds no FP64 figure; "
                     "nominal 148 SM x 64 FMA/clk x 1.965 GHz = %.1f" % NOMINAL_FP64_TFLOPS)
         traffic = {}
         try:
@@ -371,13 +371,13 @@ def run_ours(args):
         kernels = {n: round(float(t), 4) for n, t in zip(names, km)}
         share = {n: round(float(t / step_ms.mean()), 4) for n, t in zip(names, km)}
 
-        def roof_of(kernel, flop, ms, note):
+        def roof_of(kernel, flop, ms, note, bound):
             ach = flop / (ms * 1e-3) / 1e12
-            return {"bound": "fp64", "kernel": kernel, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+            return {"bound": bound, "pipe": "fp64", "kernel": kernel, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                     "traffic": traffic.get(kernel), "algorithmic_flops_per_launch": flop, "kernel_ms": float(ms), "peak_source": peak_src, "note": note}
-        roof_mlp = roof_of("k_mlp", mlp_flop, km[2], "dense fp64 contraction (both networks + 7 forward-mode tangents) on mma.sync.m8n8k4.f64; tcgen05 has no f64 kind, DMMA and DFMA share one FP64 pipe, which is the roof")
+        roof_mlp = roof_of("k_mlp", mlp_flop, km[2], "dense fp64 contraction (both networks + 7 forward-mode tangents) on mma.sync.m8n8k4.f64; tcgen05 has no f64 kind, DMMA and DFMA share one FP64 pipe, which is the roof", "tensor")
         roof_sqp = roof_of("k_sqp_warp", sqp_flop, km[3], "interior-point / Riccati SQP loop: dependent small factorisations, latency- and DRAM-latency-bound "
-                           "(FLOP model x measured interior-point iterations of the last step); its DRAM traffic is in `traffic`")
+                           "(FLOP model x measured interior-point iterations of the last step); its DRAM traffic is in `traffic`", "latency (reported against the fp64 pipe)")
         roof = dict(roof_sqp if dom == 3 else roof_mlp)
         roof["dominant_kernel"] = names[dom]
         roof["kernel_share_of_step"] = share

@@ -131,7 +131,8 @@ int mpcc_cuda_sim_time_step_device(mpcc_cuda_handle* h, const double* d_x, const
  * ms4 = durations of [prologue, kinematics, networks, SQP] of the last cycle (waits for that cycle). */
 int mpcc_cuda_set_profiling(mpcc_cuda_handle* h, int32_t on);
 int mpcc_cuda_get_kernel_times(mpcc_cuda_handle* h, double* ms4);
-/* measured FP64 FMA throughput of a device (the roofline denominator of this path), best of 5 bursts */
+/* measured FP64 throughput of a device (the roofline denominator of this path): best of 5 bursts of DFMA chains and of
+ * mma.sync.m8n8k4.f64 chains (one shared pipe; the larger figure is returned) */
 int mpcc_cuda_fp64_peak(int32_t device, double* tflops);
 
 /* ---- per-function evaluators (each runs the same device code the cycle uses; n <= batch*(N+1)) ---- */

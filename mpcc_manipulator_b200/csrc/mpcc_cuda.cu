@@ -728,7 +728,7 @@ int mpcc_cuda_get_kernel_times(mpcc_cuda_handle* h, double* ms4) {
     return MPCC_OK;
 }
 
-// FP64 DFMA peak of the device: 8 independent FMA chains per thread, enough CTAs to fill every SM
+// FP64 peak of the device (the larger of the DFMA and the DMMA figure; one shared pipe): 8 independent FMA chains per thread, enough CTAs to fill every SM
 __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters) {
     double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
     const double m = 1.0000001, c = 1e-9;
@@ -741,6 +741,23 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters) {
     }
     double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
     if (s == 123.456) out[0] = s;  // keep the chains alive
+}
+// the same pipe driven by the tensor instruction the MLP kernel uses (mma.sync.m8n8k4.f64): 8 independent accumulator pairs
+__global__ void __launch_bounds__(256) k_fp64_peak_mma(double* out, int iters) {
+    double c[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) c[i] = i * 1e-3;
+    const double x = 0.5 + threadIdx.x * 1e-6, y = 0.25;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) dmma884(c[2 * j], c[2 * j + 1], x, y);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) s += c[i];
+    if (s == 123.456) out[0] = s;
 }
 int mpcc_cuda_fp64_peak(int32_t device, double* tflops) {
     if (!tflops) return fail(MPCC_ERR_INVALID, "null argument");
@@ -763,6 +780,15 @@ int mpcc_cuda_fp64_peak(int32_t device, double* tflops) {
         CK(cudaEventElapsedTime(&ms, e0, e1));
         double fl = 2.0 * 64.0 * iters * 256.0 * grid;
         double tf = fl / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+        // tensor instruction: 64 mma per thread and iteration, 256 MAC per warp-wide mma = 8 per lane
+        CK(cudaEventRecord(e0));
+        k_fp64_peak_mma<<<grid, 256>>>(d, iters / 8);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        fl = 2.0 * 64.0 * 8.0 * (iters / 8) * 256.0 * grid;
+        tf = fl / (ms * 1e-3) / 1e12;
         if (tf > best) best = tf;
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
