@@ -76,6 +76,10 @@ struct QpOptions { int max_iter; double eps; };
 // on the central path wherever the slack is not clamped).  In the solver's normalised variables the step QPs of a warm MPCC
 // cycle have slacks of 0.01 .. 1: starting at mu0 = 3e-3 instead of t >= 1, lam = 1 saves ~2 of ~8 interior-point
 // iterations (measured on closed-loop QPs of configs C2 and C3 and on widely perturbed starts, no failure in either).
-constexpr double QP_INIT_SLACK = 3e-3;
+// Sweep on the bench workload (k_sqp_warp, ms): 1e-2 8.15 | 3e-3 7.96 | 1e-3 8.78 | 5e-4 10.6.
+#ifndef MPCC_QP_INIT_SLACK
+#define MPCC_QP_INIT_SLACK 3e-3
+#endif
+constexpr double QP_INIT_SLACK = MPCC_QP_INIT_SLACK;
 
 }  // namespace mpcc
