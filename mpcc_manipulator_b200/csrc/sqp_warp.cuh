@@ -14,11 +14,14 @@
 //
 // Work distribution:
 //   * stage linearisation / trial evaluation: lane = stage (stage_eval is independent per stage);
-//   * per-constraint and per-variable passes of the interior-point iteration: flat index over (stage, item),
-//     one loop per constraint type (box / rate / polytopic) so that a round does not diverge;
+//   * per-constraint passes of the interior-point iteration: tiles of the flat per-constraint vectors streamed through a
+//     shared-memory ring by asynchronous copies, one generic tile loop for all passes (stream_constraints);
 //   * Riccati factorisation and the two vector sweeps: sequential in the stage; inside a stage the 32 lanes work
-//     on the 8x8 / 8x16 / 16x16 / 14x14 blocks in this warp's shared-memory scratch with register blocking;
-//     the factor is stored as L^-1 and Lam = L^-1 Mnx so that both sweeps are pure mat-vecs.
+//     on the 8x8 / 8x16 / 16x16 / 14x14 blocks in this warp's shared-memory scratch (the two dense products on
+//     mma.m8n8k4.f64, the 8x8 Cholesky replicated in registers); the factor is stored as L^-1 and Lam = L^-1 Mnx so
+//     that both sweeps are pure mat-vecs.
+// Code size is a first-order concern: with ten warps per SM in different phases the interior-point iteration was bound
+// by instruction fetch until its code was made compact (one copy of every pass, rolled lane loops).
 // Memory: the iterate, the QP point and the Newton step live in shared memory; the per-stage QP blocks, the
 // per-constraint interior-point vectors and the Riccati factors live in a per-instance CONTIGUOUS global
 // workspace (every warp access is a run of consecutive doubles).
