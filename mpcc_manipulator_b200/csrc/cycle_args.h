@@ -43,7 +43,8 @@ size_t sqp_warp_ws_doubles(int N);    // global workspace per instance
 size_t sqp_warp_smem_bytes(int N);    // dynamic shared memory per CTA
 cudaError_t configure_sqp_warp(int N);
 // aux != nullptr: the instances with many recent SQP iterations go to an exclusive-SM launch on `aux` (see k_sqp_warp.cu)
-void launch_sqp_warp(const CycleArgs& a, double* wws, cudaStream_t s, cudaStream_t aux, cudaEvent_t ev_pre, cudaEvent_t ev_order, cudaEvent_t ev_aux);
+// hint: two pinned host ints written by k_order (how transient the batch is), or nullptr
+void launch_sqp_warp(const CycleArgs& a, double* wws, cudaStream_t s, cudaStream_t aux, cudaEvent_t ev_pre, cudaEvent_t ev_order, cudaEvent_t ev_aux, int32_t* hint);
 void launch_solve_ocp_warp(const CycleArgs& a, double* wws, double* guess, const double* rb, const double* cur_u, int n, double* steps, double* alphas,
                            int32_t* qp_ok, int max_log, int32_t* n_logged, cudaStream_t s);
 

@@ -175,6 +175,7 @@ struct mpcc_cuda_handle {
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // prologue | kin | mlp | sqp boundaries
     cudaStream_t aux = nullptr;                 // high-priority stream of the exclusive-SM straggler launch
     cudaEvent_t ev_pre = nullptr, ev_order = nullptr, ev_aux = nullptr;
+    int32_t* hint = nullptr;                    // pinned host memory: [n(>= 2 iterations last cycle), n(>= 15 lately)], written by k_order
     std::vector<double> h_params;  // host copy of set 0 (validation)
     std::vector<void*> allocs;
 
@@ -253,6 +254,8 @@ int mpcc_cuda_create(const mpcc_cuda_config* cfg, mpcc_cuda_handle** out) {
         CK(cudaEventCreateWithFlags(&h->ev_pre, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&h->ev_order, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&h->ev_aux, cudaEventDisableTiming));
+        CK(cudaHostAlloc((void**)&h->hint, 2 * sizeof(int32_t), cudaHostAllocPortable));
+        h->hint[0] = h->B; h->hint[1] = 0;  // the first cycle is a cold start
     }
     const size_t B = h->B, S = h->S, HN = S * HZ;
     cudaError_t ae = cudaSuccess;
@@ -289,6 +292,7 @@ int mpcc_cuda_destroy(mpcc_cuda_handle* h) {
     if (h->d_params) cudaFree(h->d_params);
     if (h->d_tracks) cudaFree(h->d_tracks);
     if (h->aux) cudaStreamDestroy(h->aux);
+    if (h->hint) cudaFreeHost(h->hint);
     if (h->ev_pre) cudaEventDestroy(h->ev_pre);
     if (h->ev_order) cudaEventDestroy(h->ev_order);
     if (h->ev_aux) cudaEventDestroy(h->ev_aux);
@@ -448,6 +452,7 @@ int mpcc_cuda_reset(mpcc_cuda_handle* h) {
     CK(cudaSetDevice(h->cfg.device));
     CK(cudaMemsetAsync(h->d_flags, 0, (size_t)h->B * sizeof(WarmFlags), h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    if (h->hint) h->hint[0] = h->B;  // a cold start is a transient: every instance needs several SQP iterations
     return MPCC_OK;
 }
 
@@ -487,7 +492,7 @@ int mpcc_cuda_run_cycle_device(mpcc_cuda_handle* h, double* d_x0, const double* 
     if (rc) return rc;
     if (prof) cudaEventRecord(h->ev[3], h->stream);
     if (h->cfg.sqp_kernel == 1) launch_sqp_thread(a, h->stream);
-    else { launch_sqp_warp(a, h->d_wws, h->stream, (h->cfg.reserved & 1) ? nullptr : h->aux, h->ev_pre, h->ev_order, h->ev_aux); h->launches += (h->cfg.reserved & 1) ? 1 : 2; }  // + the launch-order kernel (+ the exclusive launch)
+    else { launch_sqp_warp(a, h->d_wws, h->stream, (h->cfg.reserved & 1) ? nullptr : h->aux, h->ev_pre, h->ev_order, h->ev_aux, h->hint); h->launches += (h->cfg.reserved & 1) ? 1 : 2; }  // + the launch-order kernel (+ the exclusive launch)
     h->launches++;
     if (prof) cudaEventRecord(h->ev[4], h->stream);
     CK(cudaGetLastError());
