@@ -148,7 +148,8 @@ void launch_sqp_warp(const CycleArgs& a, double* wws, cudaStream_t s, cudaStream
     const int grid = (a.B + SQPW_WARPS - 1) / SQPW_WARPS;
     // hint (pinned host memory, written by k_order, read here without synchronising -- it may be a cycle old, it only
     // selects a build): [0] instances with >= 2 SQP iterations in their last cycle, [1] instances with >= 15 lately
-    const bool transient = hint && (((volatile int32_t*)hint)[0] * 32 >= a.B || ((volatile int32_t*)hint)[1] > 0);
+    // (the recent long runners themselves go to the exclusive launch, which always uses the 255-register build)
+    const bool transient = hint && ((volatile int32_t*)hint)[0] * 32 >= a.B;
     auto main_launch = [&](int excl) {
         if (transient) k_sqp_warp_r255<<<grid, SQPW_WARPS * 32, sqp_warp_smem_bytes(a.N), s>>>(a, wws, warp_ws_doubles(a.N), warp_smem_doubles(a.N), excl);
         else k_sqp_warp<<<grid, SQPW_WARPS * 32, sqp_warp_smem_bytes(a.N), s>>>(a, wws, warp_ws_doubles(a.N), warp_smem_doubles(a.N), excl);
