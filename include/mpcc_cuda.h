@@ -62,7 +62,7 @@ typedef struct {
     int32_t device;       /* CUDA device ordinal */
     int32_t qp_max_iter;  /* interior-point iteration cap of the structured QP solver (0 -> 60) */
     double qp_eps;        /* its residual tolerance (0 -> 1e-9) */
-    int32_t sqp_kernel;   /* 0: default (warp-cooperative when available), 1: one thread per instance */
+    int32_t sqp_kernel;   /* must be 0 (one SQP kernel ships: a warp per instance) */
     int32_t reserved;     /* bit 0 (diagnostic): 1 = no exclusive-SM launch for recent long runners (scheduling only, same results) */
 } mpcc_cuda_config;
 
@@ -93,7 +93,7 @@ int mpcc_fit_track(int32_t n, const double* X, const double* Y, const double* Z,
 int mpcc_fit_tracks(int32_t n_tracks, int32_t n, const double* X, const double* Y, const double* Z, const double* R, double* tables_out, int32_t n_threads);
 int mpcc_load_track_json(const char* track_path, const double* init_position3 /* nullable */, double* table_out);
 /* tables: n_tracks x MPCC_TRACK_DOUBLES; track_of_instance: batch indices or NULL (all instances use track 0).
- * Invalidates every warm start (MPC::setTrack, mpc.cpp:192-197). */
+ * Invalidates every warm start (valid_initial_guess_ = false; the failure counter keeps its value: MPC::setTrack, mpc.cpp:192-197). */
 int mpcc_cuda_set_tracks(mpcc_cuda_handle* h, const double* tables, int32_t n_tracks, const int32_t* track_of_instance);
 
 /* forget all warm starts (valid_initial_guess_ = false, num_valid_guess_failed_ = 0) */

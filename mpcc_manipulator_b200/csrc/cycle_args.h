@@ -34,10 +34,6 @@ struct CycleArgs {
 };
 
 
-// one thread per instance (k_sqp_thread.cu)
-void launch_sqp_thread(const CycleArgs& a, cudaStream_t s);
-void launch_solve_ocp_thread(const CycleArgs& a, double* guess, const double* rb, const double* cur_u, int n, double* steps, double* alphas,
-                             int32_t* qp_ok, int max_log, int32_t* n_logged, cudaStream_t s);
 // one warp per instance (k_sqp_warp.cu)
 size_t sqp_warp_ws_doubles(int N);    // global workspace per instance
 size_t sqp_warp_smem_bytes(int N);    // dynamic shared memory per CTA

@@ -42,7 +42,7 @@ constexpr int OFF_LIN = 0, OFF_VAR = LIN_SIZE, OFF_INEQ = OFF_VAR + V_SIZE, OFF_
 
 MPCC_HD int qp_workspace_doubles(int N) { return (N + 1) * STAGE_WS; }
 
-struct QpStats { int ok; int iters; double res_dual, res_prim, gap; };
+struct QpStats { int ok; int iters; double res_dual, res_prim, gap; int infeasible = 0; };  // infeasible: stopped by a primal-infeasibility certificate
 
 // normalised dynamics constants
 struct DynConst {

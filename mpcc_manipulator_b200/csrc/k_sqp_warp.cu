@@ -135,12 +135,16 @@ static size_t sqp_warp_excl_smem_bytes(int N) {
     const size_t normal = sqp_warp_smem_bytes(N), want = (size_t)227 * 1024 - normal;  // 227 KB = per-SM limit on sm_100
     return want > normal ? want : normal;
 }
-cudaError_t configure_sqp_warp(int N) {
-    cudaError_t e = cudaFuncSetAttribute(k_sqp_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sqp_warp_smem_bytes(N));
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the FUNCTION on the device, not to a handle: handles of different
+// horizons live side by side (mpcc::MPC at N = 10 next to an N = 20 batch), so the limits are set once to the worst case
+// (the launches themselves ask only for what their horizon needs, which is what decides the residency).
+cudaError_t configure_sqp_warp(int) {
+    const int main_limit = (int)sqp_warp_smem_bytes(MAX_N), excl_limit = 227 * 1024;
+    cudaError_t e = cudaFuncSetAttribute(k_sqp_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, main_limit);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_sqp_warp_r255, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sqp_warp_excl_smem_bytes(N));
+    e = cudaFuncSetAttribute(k_sqp_warp_r255, cudaFuncAttributeMaxDynamicSharedMemorySize, excl_limit);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_solve_ocp_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sqp_warp_smem_bytes(N));
+    return cudaFuncSetAttribute(k_solve_ocp_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, main_limit);
 }
 void launch_sqp_warp(const CycleArgs& a, double* wws, cudaStream_t s, cudaStream_t aux, cudaEvent_t ev_pre, cudaEvent_t ev_order, cudaEvent_t ev_aux, int32_t* hint) {
     static const bool no_excl = getenv("MPCC_SQPW_NO_EXCL") != nullptr;  // diagnostic (as mpcc_cuda_config.reserved bit 0): everything in the main launch

@@ -115,6 +115,10 @@ __global__ void k_warm_io(double* warm_soa, double* hor_aos, int B, int HN, int 
     if (to_aos) hor_aos[i] = warm_soa[(size_t)e * B + b];
     else warm_soa[(size_t)e * B + b] = hor_aos[i];
 }
+__global__ void k_invalidate_warm(WarmFlags* fl, int B) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) fl[b].valid = 0;
+}
 // Integrator::simTimeStep (integrator.cpp:55-68): (int)(ts/1e-3) RK4 steps of the (linear) model
 __global__ void k_sim_step(const double* x, const double* u, double ts, int B, double* xn) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -178,6 +182,16 @@ struct mpcc_cuda_handle {
     int32_t* hint = nullptr;                    // pinned host memory: [n(>= 2 iterations last cycle), n(>= 15 lately)], written by k_order
     std::vector<double> h_params;  // host copy of set 0 (validation)
     std::vector<void*> allocs;
+    // grow-only device arena of the per-call probes / bindings (solveOCP at 100 Hz must not cudaMalloc per call)
+    char* scratch = nullptr; size_t scratch_bytes = 0;
+    cudaError_t need_scratch(size_t bytes) {
+        if (bytes <= scratch_bytes) return cudaSuccess;
+        if (scratch) { cudaStreamSynchronize(stream); cudaFree(scratch); scratch = nullptr; scratch_bytes = 0; }
+        bytes = (bytes + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
+        cudaError_t e = cudaMalloc((void**)&scratch, bytes);
+        if (e == cudaSuccess) scratch_bytes = bytes;
+        return e;
+    }
 
     template <class T>
     cudaError_t alloc(T** p, size_t count) {
@@ -227,11 +241,13 @@ extern "C" {
 
 const char* mpcc_cuda_last_error(void) { return g_err.c_str(); }
 
+static int create_impl(mpcc_cuda_handle* h, const mpcc_cuda_config* cfg);
 int mpcc_cuda_create(const mpcc_cuda_config* cfg, mpcc_cuda_handle** out) {
     if (!cfg || !out) return fail(MPCC_ERR_INVALID, "null argument");
     if (cfg->batch < 1) return fail(MPCC_ERR_INVALID, "batch must be >= 1");
     if (cfg->horizon < 2 || cfg->horizon > MAX_N) return fail(MPCC_ERR_INVALID, "horizon must be in [2, 64]");
     if (!(cfg->Ts > 0)) return fail(MPCC_ERR_INVALID, "Ts must be positive");
+    if (cfg->sqp_kernel != 0) return fail(MPCC_ERR_INVALID, "sqp_kernel must be 0: the library ships one SQP kernel (warp per instance)");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) return fail(MPCC_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
@@ -239,6 +255,12 @@ int mpcc_cuda_create(const mpcc_cuda_config* cfg, mpcc_cuda_handle** out) {
     CK(cudaSetDevice(cfg->device));
     mpcc_cuda_handle* h = new mpcc_cuda_handle();
     h->cfg = *cfg;
+    const int rc = create_impl(h, cfg);
+    if (rc != MPCC_OK) { const std::string keep = g_err; mpcc_cuda_destroy(h); g_err = keep; return rc; }  // nothing of a half-built handle leaks
+    *out = h;
+    return MPCC_OK;
+}
+static int create_impl(mpcc_cuda_handle* h, const mpcc_cuda_config* cfg) {
     if (h->cfg.qp_max_iter <= 0) h->cfg.qp_max_iter = 60;
     if (!(h->cfg.qp_eps > 0)) h->cfg.qp_eps = 1e-9;
     h->B = cfg->batch; h->N = cfg->horizon; h->S = cfg->horizon + 1; h->NS = (size_t)h->B * h->S;
@@ -272,14 +294,13 @@ int mpcc_cuda_create(const mpcc_cuda_config* cfg, mpcc_cuda_handle** out) {
     A(h->alloc(&h->d_status, B)); A(h->alloc(&h->d_iters, B)); A(h->alloc(&h->d_ok, B)); A(h->alloc(&h->d_qp_iters, B)); A(h->alloc(&h->d_qp_fail, B)); A(h->alloc(&h->d_accept, B)); A(h->alloc(&h->d_sqp_ns, 4 * B)); A(h->alloc(&h->d_hist, B)); A(h->alloc(&h->d_order, B + 1));
     A(h->alloc(&h->d_wpack, (size_t)MLP_NCHUNK * MLP_CHUNK_D)); A(h->alloc(&h->d_bias, MLP_BIAS_TOTAL));
     A(h->alloc(&h->d_w_out_env, 9 * 256)); A(h->alloc(&h->d_w_out_self, 64));
-    if (ae != cudaSuccess) { mpcc_cuda_destroy(h); return fail(MPCC_ERR_CUDA, std::string("device allocation failed: ") + cudaGetErrorString(ae)); }
+    if (ae != cudaSuccess) return fail(MPCC_ERR_CUDA, std::string("device allocation failed: ") + cudaGetErrorString(ae));
     std::vector<double> dummy(B * 4);
     for (size_t b = 0; b < B; b++) { dummy[4 * b] = 3; dummy[4 * b + 1] = 3; dummy[4 * b + 2] = 3; dummy[4 * b + 3] = 0; }  // mpc.cpp:97-100
     CK(cudaMemcpyAsync(h->d_obs_dummy, dummy.data(), dummy.size() * 8, cudaMemcpyHostToDevice, h->stream));
     CK(cudaFuncSetAttribute(k_mlp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_SMEM_BYTES));
     CK(configure_sqp_warp(h->N));
     CK(cudaStreamSynchronize(h->stream));
-    *out = h;
     return MPCC_OK;
 }
 
@@ -289,6 +310,7 @@ int mpcc_cuda_destroy(mpcc_cuda_handle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (cudaEvent_t e : h->ev) if (e) cudaEventDestroy(e);
     for (void* p : h->allocs) cudaFree(p);
+    if (h->scratch) cudaFree(h->scratch);
     if (h->d_params) cudaFree(h->d_params);
     if (h->d_tracks) cudaFree(h->d_tracks);
     if (h->aux) cudaStreamDestroy(h->aux);
@@ -401,6 +423,7 @@ int mpcc_load_params_json(const char* model_path, const char* cost_path, const c
 
 int mpcc_fit_track(int32_t n, const double* X, const double* Y, const double* Z, const double* R, double* table_out) {
     if (!X || !Y || !Z || !R || !table_out) return fail(MPCC_ERR_INVALID, "null argument");
+    if (n < 3) return fail(MPCC_ERR_INVALID, "a track needs at least 3 waypoints");
     try {
         Waypoints w;
         w.X.assign(X, X + n); w.Y.assign(Y, Y + n); w.Z.assign(Z, Z + n); w.R.assign(R, R + (size_t)9 * n);
@@ -413,7 +436,7 @@ int mpcc_fit_track(int32_t n, const double* X, const double* Y, const double* Z,
 
 // Bulk track ingestion for heterogeneous batches (configuration C4): n_tracks independent fits on the host cores.
 int mpcc_fit_tracks(int32_t n_tracks, int32_t n, const double* X, const double* Y, const double* Z, const double* R, double* tables_out, int32_t n_threads) {
-    if (!X || !Y || !Z || !R || !tables_out || n_tracks < 1 || n < 2) return fail(MPCC_ERR_INVALID, "bad argument");
+    if (!X || !Y || !Z || !R || !tables_out || n_tracks < 1 || n < 3) return fail(MPCC_ERR_INVALID, "bad argument (n_tracks >= 1, at least 3 waypoints per track)");
     unsigned hw = std::thread::hardware_concurrency();
     int nt = n_threads > 0 ? n_threads : (int)(hw ? hw : 1);
     if (nt > n_tracks) nt = n_tracks;
@@ -472,7 +495,12 @@ int mpcc_cuda_set_tracks(mpcc_cuda_handle* h, const double* tables, int32_t n_tr
     CK(cudaStreamSynchronize(h->stream));
     h->n_tracks = n_tracks;
     h->have_track = true;
-    return mpcc_cuda_reset(h);
+    // MPC::setTrack (mpc.cpp:192-197) clears valid_initial_guess_ only; num_valid_guess_failed_ keeps counting
+    k_invalidate_warm<<<(h->B + 255) / 256, 256, 0, h->stream>>>(h->d_flags, h->B);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->hint) h->hint[0] = h->B;
+    return MPCC_OK;
 }
 
 int mpcc_cuda_run_cycle_device(mpcc_cuda_handle* h, double* d_x0, const double* d_u0, const double* d_obs) {
@@ -491,8 +519,8 @@ int mpcc_cuda_run_cycle_device(mpcc_cuda_handle* h, double* d_x0, const double* 
     rc = launch_robot_data(h, obs, h->S, prof);
     if (rc) return rc;
     if (prof) cudaEventRecord(h->ev[3], h->stream);
-    if (h->cfg.sqp_kernel == 1) launch_sqp_thread(a, h->stream);
-    else { launch_sqp_warp(a, h->d_wws, h->stream, (h->cfg.reserved & 1) ? nullptr : h->aux, h->ev_pre, h->ev_order, h->ev_aux, h->hint); h->launches += (h->cfg.reserved & 1) ? 1 : 2; }  // + the launch-order kernel (+ the exclusive launch)
+    launch_sqp_warp(a, h->d_wws, h->stream, (h->cfg.reserved & 1) ? nullptr : h->aux, h->ev_pre, h->ev_order, h->ev_aux, h->hint);
+    h->launches += (h->cfg.reserved & 1) ? 1 : 2;  // + the launch-order kernel (+ the exclusive launch)
     h->launches++;
     if (prof) cudaEventRecord(h->ev[4], h->stream);
     CK(cudaGetLastError());
@@ -676,23 +704,27 @@ int mpcc_cuda_solve_ocp(mpcc_cuda_handle* h, double* guess, const double* rb, co
     if (max_log > 0 && (!alphas || !n_logged)) return fail(MPCC_ERR_INVALID, "log arrays missing");
     CK(cudaSetDevice(h->cfg.device));
     const size_t HN = (size_t)h->S * HZ;
-    double *d_g = nullptr, *d_rb = nullptr, *d_cu = nullptr, *d_steps = nullptr, *d_alphas = nullptr;
-    int32_t *d_qpok = nullptr, *d_nl = nullptr;
+    // buffers carved from the handle's grow-only arena: no allocation (and no implicit device synchronisation) per call
     const int ml = max_log > 0 ? max_log : 1;
-    CK(cudaMalloc((void**)&d_g, n * HN * 8));
-    CK(cudaMalloc((void**)&d_rb, (size_t)n * h->S * RB_DOUBLES * 8));
-    CK(cudaMalloc((void**)&d_cu, (size_t)n * NU * 8));
-    if (steps && max_log > 0) CK(cudaMalloc((void**)&d_steps, (size_t)n * ml * HN * 8));
-    CK(cudaMalloc((void**)&d_alphas, (size_t)n * ml * 8));
-    CK(cudaMalloc((void**)&d_qpok, (size_t)n * ml * 4));
-    CK(cudaMalloc((void**)&d_nl, (size_t)n * 4));
+    const bool want_steps = steps && max_log > 0;
+    auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t b_g = up(n * HN * 8), b_rb = up((size_t)n * h->S * RB_DOUBLES * 8), b_cu = up((size_t)n * NU * 8), b_steps = want_steps ? up((size_t)n * ml * HN * 8) : 0,
+                 b_al = up((size_t)n * ml * 8), b_ok = up((size_t)n * ml * 4), b_nl = up((size_t)n * 4);
+    CK(h->need_scratch(b_g + b_rb + b_cu + b_steps + b_al + b_ok + b_nl));
+    char* sp = h->scratch;
+    double* d_g = (double*)sp; sp += b_g;
+    double* d_rb = (double*)sp; sp += b_rb;
+    double* d_cu = (double*)sp; sp += b_cu;
+    double* d_steps = want_steps ? (double*)sp : nullptr; sp += b_steps;
+    double* d_alphas = (double*)sp; sp += b_al;
+    int32_t* d_qpok = (int32_t*)sp; sp += b_ok;
+    int32_t* d_nl = (int32_t*)sp;
     CK(cudaMemcpyAsync(d_g, guess, n * HN * 8, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(d_rb, rb, (size_t)n * h->S * RB_DOUBLES * 8, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(d_cu, cur_u, (size_t)n * NU * 8, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemsetAsync(d_nl, 0, (size_t)n * 4, h->stream));
     CycleArgs a = make_args(h, h->d_x0, h->d_u0, h->d_obs_dummy);
-    if (h->cfg.sqp_kernel == 1) launch_solve_ocp_thread(a, d_g, d_rb, d_cu, n, d_steps, d_alphas, d_qpok, max_log, d_nl, h->stream);
-    else launch_solve_ocp_warp(a, h->d_wws, d_g, d_rb, d_cu, n, d_steps, d_alphas, d_qpok, max_log, d_nl, h->stream);
+    launch_solve_ocp_warp(a, h->d_wws, d_g, d_rb, d_cu, n, d_steps, d_alphas, d_qpok, max_log, d_nl, h->stream);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(guess, d_g, n * HN * 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(status, h->d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
@@ -703,7 +735,6 @@ int mpcc_cuda_solve_ocp(mpcc_cuda_handle* h, double* guess, const double* rb, co
         CK(cudaMemcpyAsync(n_logged, d_nl, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
     }
     CK(cudaStreamSynchronize(h->stream));
-    cudaFree(d_g); cudaFree(d_rb); cudaFree(d_cu); cudaFree(d_steps); cudaFree(d_alphas); cudaFree(d_qpok); cudaFree(d_nl);
     return MPCC_OK;
 }
 

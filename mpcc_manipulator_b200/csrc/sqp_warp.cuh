@@ -400,16 +400,20 @@ struct WarpSqp {
     }
 
     // ---- gradient of the step QP: G <- H z + f + G'(IV); dst0 (shared) <- same with multipliers ILAM ----
-    MPCC_HD void gradient(double* dst0) const {
+    // cost == false: the cost terms H z + f are left out (dst0 <- G' ILAM alone: the infeasibility certificate)
+    MPCC_HD void gradient(double* dst0, bool cost = true) const {
         W.each([&](int lane) {
             MPCC_ROLLED
             for (int o = lane; o < NX * S; o += 32) {
                 const int k = o / NX, r = o - k * NX;
                 const double* L = LIN + (size_t)k * WL_SIZE;
                 const double* z = VAR + k * HZ;
-                double base = L[WL_q + r];
+                double base = 0.0;
+                if (cost) {
+                    base = L[WL_q + r];
 #pragma unroll
-                for (int c = 0; c < NX; c++) base += L[WL_Q + r * 9 + c] * z[c];
+                    for (int c = 0; c < NX; c++) base += L[WL_Q + r * 9 + c] * z[c];
+                }
                 double sv = IV[k * 18 + 9 + r] - IV[k * 18 + r];
                 double sl = dst0 ? ILAM[k * 18 + 9 + r] - ILAM[k * 18 + r] : 0.0;
                 if (k < N && r < DOF) {
@@ -429,11 +433,11 @@ struct WarpSqp {
                 const int k = o / NU, j = o - k * NU;
                 const double* L = LIN + (size_t)k * WL_SIZE;
                 const double* z = VAR + k * HZ + NX;
-                double base = L[WL_RD + j] * z[j] + L[WL_r + j];
+                double base = cost ? L[WL_RD + j] * z[j] + L[WL_r + j] : 0.0;
                 double sv = 0, sl = 0;
                 if (j < DOF) {
-                    if (k >= 1) base += d_cpl(j) * z[j - HZ];
-                    if (k <= N - 2) base += d_cpl(j) * z[j + HZ];
+                    if (cost && k >= 1) base += d_cpl(j) * z[j - HZ];
+                    if (cost && k <= N - 2) base += d_cpl(j) * z[j + HZ];
                     const int ir = OR_ + k * 14;
                     sv = IV[ir + 7 + j] - IV[ir + j];
                     if (dst0) sl = ILAM[ir + 7 + j] - ILAM[ir + j];
@@ -453,6 +457,61 @@ struct WarpSqp {
                 if (dst0) dst0[k * HZ + NX + j] = base + sl;
             }
         });
+    }
+
+    // costates of the xi-stationarity recursion p_N = g_N, p_k = g_k + A' p_{k+1}, in place on the xi part of STEP (which holds g);
+    // returns the inf-norm of the nu-stationarity residual g_nu,k + B' p_{k+1}
+    MPCC_HDNI double costate_residual() const {
+        W.each([&](int lane) {
+            if (lane < 8) for (int k = N - 1; k >= 1; k--) STEP[k * HZ + lane] += STEP[(k + 1) * HZ + lane];
+        });
+        W.each([&](int lane) {
+            if (lane == 8) for (int k = N - 1; k >= 1; k--) STEP[k * HZ + 8] += STEP[(k + 1) * HZ + 8] + d_asv() * STEP[(k + 1) * HZ + 7];
+        });
+        return W.rmax([&](int lane) {
+            double nr = 0;
+            MPCC_ROLLED
+            for (int o = lane; o < NU * N; o += 32) {
+                const int k = o / NU, j = o - k * NU;
+                const double* pn = STEP + (k + 1) * HZ;
+                const double btp = (j < 7) ? d_bq(j) * pn[j] : d_bs() * pn[7] + d_bv() * pn[8];
+                nr = fmax(nr, fabs(STEP[k * HZ + NX + j] + btp));
+            }
+            return nr;
+        });
+    }
+
+    // Primal infeasibility certificate (Farkas; the counterpart of OSQP's primal-infeasibility test, which makes the reference's
+    // solveQP return PrimalInfeasible quickly, osqp_interface.cpp:495-497): for multipliers lam >= 0 and the costates p of
+    // G' lam (recursion above), every z that satisfies the dynamics has lam' G z = r' nu + sum_k p_{k+1}' b_k with r the
+    // nu-stationarity residual.  If r vanishes (relative to |lam|) and sum_k p_{k+1}' b_k - h' lam > 0, no such z has G z <= h.
+    // The diverging multipliers of an interior-point run on an infeasible QP converge to such a ray.  Tested only on
+    // iterations that follow a short step (the hot path never gets here); tolerance eps_inf relative to |lam|_inf.
+    MPCC_HDNI bool primal_infeasible(double eps_inf) const {
+        double* RED = SC + SC_RED;
+        W.each([&](int lane) { RED[lane] = 0.0; RED[32 + lane] = 0.0; });
+        stream_constraints(vec_ids(CV_LAM, CV_H), 2, [&](int lane, int, int kind, int, int, const double* v, int j, const double*) {
+            const int ts = (kind == 2) ? 32 : 96;
+            const double lam = v[j], h = v[ts + j];
+            RED[lane] = fmax(RED[lane], lam);
+            RED[32 + lane] += lam * h;
+        });
+        const double lmax = W.rmax([&](int lane) { return RED[lane]; });
+        const double hl = W.rsum([&](int lane) { return RED[32 + lane]; });
+        if (!(lmax > 0.0) || !(lmax < 1e300)) return false;
+        gradient(STEP, false);  // STEP <- G' lam  (G, the gradient with the predictor multipliers, is recomputed by the next pass)
+        const double nr = costate_residual();
+        const double c = W.rsum([&](int lane) {
+            double a = 0;
+            MPCC_ROLLED
+            for (int o = lane; o < NX * N; o += 32) { const int k = o / NX, r = o - k * NX; a += STEP[(k + 1) * HZ + r] * LIN[(size_t)k * WL_SIZE + WL_b + r]; }
+            return a;
+        });
+#if defined(MPCC_QP_TRACE) && !defined(__CUDA_ARCH__)
+        fprintf(stderr, "          certificate: |lam| %.3e  r/|lam| %.3e  (c - h'lam)/|lam| %.3e\n", lmax, nr / lmax, (c - hl) / lmax);
+#endif
+        // rigorous for every z with |nu|_1 <= 1e4 (normalised input steps are O(1)): lam'(G z - h) = r'nu + c - h'lam > 0
+        return (c - hl) >= eps_inf * lmax && nr * 1e4 <= (c - hl);
     }
 
     // asynchronous fetch of the factorisation inputs of stage k into slot k & 1: 138 pairs (polytopic rows 77, Q 41 -- the last
@@ -841,7 +900,7 @@ struct WarpSqp {
     // ---- interior-point loop; on success VAR holds the step (xi = exact rollout of nu) ----
     MPCC_HD QpStats solve() const {
         QpStats st;
-        st.ok = 0; st.iters = 0; st.res_dual = 0; st.res_prim = 0; st.gap = 0;
+        st.ok = 0; st.iters = 0; st.res_dual = 0; st.res_prim = 0; st.gap = 0; st.infeasible = 0;
         const int tot = S * NINEQ;
         double* RED = SC + SC_RED;
         // feasibility of the boxes (stage 0: xi_0 = 0 must lie inside; others: lo <= hi)
@@ -880,10 +939,12 @@ struct WarpSqp {
             MPCC_ROLLED
             for (int i = lane; i < tot; i += 32) { IT[i] = 1.0; ILAM[i] = 0.0; IW[i] = 0.0; IV[i] = 0.0; IRP[i] = 0.0; IDT[i] = 0.0; IDLAM[i] = 0.0; }
         });
+        const double s0 = QP_INIT_SLACK;
         W.each([&](int lane) {
-            for_present(lane, VAR, true, [&](int i, double g, double h) { const double t0 = fmax(h - g, QP_INIT_SLACK); IT[i] = t0; ILAM[i] = QP_INIT_SLACK / t0; IH[i] = h; });
+            for_present(lane, VAR, true, [&](int i, double g, double h) { const double t0 = fmax(h - g, s0); IT[i] = t0; ILAM[i] = s0 / t0; IH[i] = h; });
         });
         const double m_tot = 43.0 * N;
+        double a_prev = 1.0;  // step length of the previous iteration
         for (int it = 0; it < opt.max_iter; it++) {
             // residuals, barrier weights, predictor v = lam rp / t
             W.each([&](int lane) { RED[lane] = 0.0; RED[32 + lane] = 0.0; });
@@ -904,6 +965,8 @@ struct WarpSqp {
             const double nrp = W.rmax([&](int lane) { return RED[lane]; });
             const double sum_tl = W.rsum([&](int lane) { return RED[32 + lane]; });
             const double mu = sum_tl / m_tot;
+            // a short step announces trouble: test the multipliers for a Farkas ray before spending the remaining iterations
+            if (it >= 2 && a_prev < 0.01 && nrp > opt.eps && primal_infeasible(1e-8)) { st.iters = it; st.res_prim = nrp; st.gap = mu; st.infeasible = 1; break; }
             // Two passes over ONE copy of gradient / sweeps / step lengths (the loop is kept rolled on purpose: code footprint).
             //   pass 0: Lagrangian gradient and residual test, factorisation, affine (predictor) step, centring parameter
             //   pass 1: corrector right-hand side, combined step, update
@@ -915,25 +978,11 @@ struct WarpSqp {
             for (int pass = 0; pass < 2; pass++) {
                 gradient(pass == 0 ? STEP : nullptr);  // G <- gradient of this pass; pass 0: STEP <- Lagrangian gradient (scratch until the step is computed)
                 if (pass == 0) {
-                    // costates: in-place suffix recursion p_k = g_k + A' p_{k+1} on the xi part of STEP
-                    W.each([&](int lane) {
-                        if (lane < 8) for (int k = N - 1; k >= 1; k--) STEP[k * HZ + lane] += STEP[(k + 1) * HZ + lane];
-                    });
-                    W.each([&](int lane) {
-                        if (lane == 8) for (int k = N - 1; k >= 1; k--) STEP[k * HZ + 8] += STEP[(k + 1) * HZ + 8] + d_asv() * STEP[(k + 1) * HZ + 7];
-                    });
-                    const double nrd = W.rmax([&](int lane) {
-                        double nr = 0;
-                        MPCC_ROLLED
-                        for (int o = lane; o < NU * N; o += 32) {
-                            const int k = o / NU, j = o - k * NU;
-                            const double* pn = STEP + (k + 1) * HZ;
-                            const double btp = (j < 7) ? d_bq(j) * pn[j] : d_bs() * pn[7] + d_bv() * pn[8];
-                            nr = fmax(nr, fabs(STEP[k * HZ + NX + j] + btp));
-                        }
-                        return nr;
-                    });
+                    const double nrd = costate_residual();
                     st.iters = it; st.res_dual = nrd; st.res_prim = nrp; st.gap = mu;
+#if defined(MPCC_QP_TRACE) && !defined(__CUDA_ARCH__)
+                    fprintf(stderr, "  ipm %2d  rd %.3e  rp %.3e  mu %.3e\n", it, nrd, nrp, mu);
+#endif
                     if (nrd <= opt.eps * (1.0 + qn) && nrp <= opt.eps && mu <= opt.eps) { st.ok = 1; stop = true; break; }
                     if (!(nrd == nrd) || !(mu == mu)) { stop = true; break; }
                     if (!factor()) { stop = true; break; }
@@ -952,6 +1001,10 @@ struct WarpSqp {
                     });
                 } else {
                     const double a = fmin(1.0, 0.995 * a_max);
+                    a_prev = a;
+#if defined(MPCC_QP_TRACE) && !defined(__CUDA_ARCH__)
+                    fprintf(stderr, "          alpha %.3e\n", a);
+#endif
                     W.each([&](int lane) { MPCC_ROLLED for (int o = lane; o < S * HZ; o += 32) VAR[o] += a * STEP[o]; });
                     double* t_ = IT; double* l_ = ILAM;
                     stream_constraints(vec_ids(CV_T, CV_LAM, CV_DT, CV_DLAM), 4, [&](int, int i, int kind, int, int, const double* v, int j, const double*) {

@@ -394,23 +394,6 @@ def test_instrumentation_and_counters(M, O, ee_home):
     mpc.close()
 
 
-def test_thread_per_instance_kernel_agrees_with_warp_kernel(M, O, ee_home, rng):
-    """sqp_kernel = 1 (one thread per instance, the direct compilation of dev_sqp.cuh) against the default warp kernel."""
-    B, N = 16, 10
-    a = make_mpc(M, B, N, ee_home)
-    b = M.BatchMPC(B, N, sqp_kernel=1); b.setup_default(init_position=ee_home)
-    x0 = np.tile(np.r_[O.Q_HOME, 0., 0.], (B, 1)); x0[:, :7] += rng.uniform(-0.05, 0.05, (B, 7)); u0 = np.zeros((B, 8))
-    ra, rb_ = a.run_cycle(x0, u0), b.run_cycle(x0, u0)
-    assert np.array_equal(ra["status"], rb_["status"])
-    # a filter tie may split the two formulations (different rounding): compare the instances that took the same branch
-    same = (ra["iters"] == rb_["iters"]) & (a.decisions() == b.decisions())
-    assert same.sum() >= B // 2
-    err = (np.abs(ra["u0"] - rb_["u0"]) / TU).max(axis=1)
-    assert np.median(err[same]) < 1e-9           # same branch, same arithmetic up to reduction order
-    assert (err[same] < QP_TOL).sum() >= same.sum() - 2 and err.max() < 0.05   # a tie inside the back-tracking may still split one or two
-    a.close(); b.close()
-
-
 def test_exclusive_sm_launch_changes_scheduling_only(M, O, ee_home):
     """The instances with >= 15 SQP iterations in one of the last four cycles are solved by a second launch of the same
     kernel on SMs of their own (k_sqp_warp.cu).  Same per-instance code, so a handle with that launch disabled

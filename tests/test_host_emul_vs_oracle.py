@@ -2,6 +2,8 @@
 oracle.  These are the same inline functions the CUDA kernels call; the GPU tier repeats the comparisons on
 the device through the C ABI.  Tolerances: linearisations 1e-9 relative (north_star), QP/SQP steps within the
 reference QP solver's tolerance (OSQP eps_abs = 1e-4, osqp_interface.cpp:623)."""
+from pathlib import Path
+
 import numpy as np
 import pytest
 
@@ -312,3 +314,35 @@ def test_warp_sqp_loop_vs_oracle(O, nn, emu, track_wp, setup, rng, N):
             assert np.abs(step_to_flat(a["steps"][i], N) - b["steps"][i]).max() < 1e-4
             assert nat[i] == int(a["alphas"][i] == 1.0) or mg[i] < 1e-6
         assert a["accept_mask"] == sum(int(x == 1.0) << i for i, x in enumerate(a["alphas"]))
+
+
+def test_primal_infeasibility_certificate(O, nn, track_wp):
+    """A QP of the latency configuration (N = 40, eps_prim = 0.01; instance 3, cycle 13 of the C5 closed loop) whose
+    constraints are inconsistent by 3e-4: the reference's OSQP would report PrimalInfeasible (osqp_interface.cpp:495-497);
+    the interior point used to burn all 60 iterations on it.  The Farkas test on the diverging multipliers stops it early.
+    Independent confirmation: an LP phase 1 (scipy HiGHS) on the ORACLE's flat constraint matrix has a positive optimum,
+    and the oracle's dense solver fails on the same QP."""
+    from scipy.optimize import linprog
+    g = np.load(Path(__file__).resolve().parent / "golden" / "infeasible_qp_n40.npz")
+    N = 40
+    emu = Emul()
+    p = O.load_params(overrides={"sqp": {"eps_prim": 0.01}}); pf = flat_params(p)
+    table = emu.fit_track(*track_wp)
+    for rev in (False, True):
+        ok, step, it, res = emu.warp_solve_qp(pf, table, p["Ts"], N, g["warm"], g["rb"], g["u"], reverse=rev)
+        assert not ok and it < 30, (ok, it)
+    o = O.OracleMPC(N=N, nn=nn, params=p); o.set_track(*track_wp)
+    qp = o.build_qp(g["warm"], g["rb"], g["u"])
+    A, lo, hi = qp["A"], qp["l"] - qp["c"], qp["u"] - qp["c"]
+    okd, _, _ = O.solve_qp_dense(qp["P"], qp["q"], A, lo, hi)
+    assert not okd
+    keep = np.abs(A).sum(1) > 0
+    A, lo, hi = A[keep], lo[keep], hi[keep]
+    n = A.shape[1]
+    fu, fl = hi < 1e20, lo > -1e20
+    Aub = np.vstack([np.c_[A[fu], -np.ones(fu.sum())], np.c_[-A[fl], -np.ones(fl.sum())]])
+    r = linprog(np.r_[np.zeros(n), 1.0], A_ub=Aub, b_ub=np.r_[hi[fu], -lo[fl]], bounds=[(None, None)] * n + [(0, None)], method="highs")
+    assert r.status == 0 and r.fun > 1e-5   # smallest uniform violation of l <= A z <= u is positive: infeasible
+    # the whole SQP cycle on it: the QP fails, the step stays zero, the reference's loop then reports SOLVED (quirk 10)
+    r2 = emu.warp_solve_ocp(pf, table, p["Ts"], N, g["warm"], g["rb"], g["u"])
+    assert r2["status"] == 0 and r2["iters"] == 1 and r2["qp_ok"][0] == 0 and r2["qp_iters"] < 30
