@@ -90,6 +90,25 @@ inline bool cholesky_inplace(double* a, int n, int ld) {
     }
     return true;
 }
+// Eigen::LLT's verdict (info() != NumericalIssue): false at the first pivot x <= 0; NaN pivots are not flagged.
+inline bool llt_no_numerical_issue(double* a, int n, int ld) {
+    for (int j = 0; j < n; j++) {
+        double* aj = a + (size_t)j * ld;
+        double d = aj[j];
+        for (int k = 0; k < j; k++) d -= aj[k] * aj[k];
+        if (d <= 0.0) return false;
+        d = std::sqrt(d);
+        aj[j] = d;
+        double inv = 1.0 / d;
+        for (int i = j + 1; i < n; i++) {
+            double* ai = a + (size_t)i * ld;
+            double s = ai[j];
+            for (int k = 0; k < j; k++) s -= ai[k] * aj[k];
+            ai[j] = s * inv;
+        }
+    }
+    return true;
+}
 // Solve L L^T x = b in place (L lower, row-major).
 inline void cholesky_solve(const double* L, int n, int ld, double* x) {
     for (int i = 0; i < n; i++) {

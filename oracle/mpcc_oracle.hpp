@@ -1309,9 +1309,10 @@ struct Solver {
             auto a0 = std::chrono::high_resolution_clock::now();
             setCost(initial_guess, &obj, &grad_obj, &Hess);
             setConstraints(initial_guess, &jac, &constr, &l, &u);
-            {  // isPosdef (:810-817): dense LLT
+            {  // isPosdef (:810-817): Eigen::LLT reports NumericalIssue only at a pivot x <= 0 (Eigen/src/Cholesky/LLT.h,
+               // llt_inplace::unblocked: `if (x <= RealScalar(0)) return k;`), so a NaN pivot passes and the NaN test below decides
                 Mat tmp = Hess;
-                if (!cholesky_inplace(tmp.a.data(), N_var, N_var)) { *status = NON_PD_HESSIAN; break; }
+                if (!llt_no_numerical_issue(tmp.a.data(), N_var, N_var)) { *status = NON_PD_HESSIAN; break; }
             }
             if (isNan(Hess)) { *status = NAN_HESSIAN; break; }
             auto a1 = std::chrono::high_resolution_clock::now();

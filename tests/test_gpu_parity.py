@@ -299,6 +299,121 @@ def test_full_size_batch_properties(M, O, ee_home):
     small.close()
 
 
+def test_full_size_batch_sampled_against_oracle(M, O, nn, ee_home, track_wp):
+    """BASELINE configs[1] at full size: 64 instances sampled from the 4096 x N=20 batch, three closed-loop cycles, each
+    compared with the oracle along the device's branch (status, iterations, s / vs, control, horizon)."""
+    B, N, n_s = 4096, 20, 64
+    rng = np.random.default_rng(0)
+    mpc = make_mpc(M, B, N, ee_home)
+    x = np.tile(np.r_[O.Q_HOME, 0., 0.], (B, 1)); x[:, :7] += rng.uniform(-0.05, 0.05, (B, 7)); u = np.zeros((B, 8))
+    idx = np.sort(rng.choice(B, n_s, replace=False))
+    oracles = {}
+    for b in idx:
+        o = O.OracleMPC(N=N, nn=nn); o.set_track(*track_wp); oracles[b] = o
+    n_cmp = n_tie = n_out = 0
+    worst = 0.0
+    for c in range(3):
+        w_hor, w_valid, w_failed = mpc.get_warm_state()
+        r = mpc.run_cycle(x, u)
+        masks = mpc.decisions()
+        for b in idx:
+            o = oracles[b]
+            dec = [(int(masks[b]) >> i) & 1 for i in range(min(int(r["iters"][b]), 32))]
+            o.set_warm_state(w_hor[b], w_valid[b], w_failed[b]); o.set_forced_decisions(dec)
+            ro = o.run(x[b], u[b])
+            nat, mg = o.decision_log()
+            assert np.abs(r["x0"][b] - ro["x0"]).max() < 1e-9
+            assert r["status"][b] == ro["status"] and r["iters"][b] == ro["iters"], (c, b)
+            d = (np.abs(r["u0"][b] - ro["u0"]) / TU).max()
+            dh = (np.abs(r["horizon"][b] - ro["horizon"]) / THZ).max() / max(1, ro["iters"])
+            if d >= QP_TOL or dh >= QP_TOL:
+                n_out += 1
+                assert n_out <= 2 and d < 5 * QP_TOL and dh < 5 * QP_TOL, (c, b, d, dh)
+            worst = max(worst, d); n_cmp += 1
+            for i in range(len(dec)):
+                if nat[i] != dec[i]:
+                    assert mg[i] < TIE, (c, b, i, mg[i]); n_tie += 1
+        u = r["u0"]; x = mpc.sim_time_step(r["x0"], u, 0.01)
+    print(f"C2 full size, 64 sampled: {n_cmp} comparisons, {n_tie} certified ties, {n_out} termination-slack outliers, worst |du0|/Tu = {worst:.2e}")
+    assert n_cmp == 3 * n_s
+    mpc.close()
+
+
+def test_closed_loop_latency_config_n40(M, O, nn, ee_home, track_wp):
+    """Configuration C5 in small: N = 40, eps_prim = 0.01 (several SQP iterations per cycle), 6 instances, 5 closed-loop cycles."""
+    B, N = 6, 40
+    rng = np.random.default_rng(3)
+    mpc = M.BatchMPC(B, N); mpc.load_nn()
+    mpc.set_params(M.load_default_params(overrides={"sqp.eps_prim": 0.01}))
+    mpc.set_tracks(M.load_track_json(None, ee_home))
+    po = O.load_params(overrides={"sqp": {"eps_prim": 0.01}})
+    oracles = []
+    for b in range(B):
+        o = O.OracleMPC(N=N, nn=nn, params=po); o.set_track(*track_wp); oracles.append(o)
+    x = np.tile(np.r_[O.Q_HOME, 0., 0.], (B, 1)); x[:, :7] += rng.uniform(-0.05, 0.05, (B, 7)); u = np.zeros((B, 8))
+    n_cmp, n_tie, worst = _closed_loop_follow(mpc, oracles, x, u, 5, 0.01, O, slack_outliers=2)
+    print(f"C5 small (N=40): {n_cmp} comparisons, {n_tie} certified filter ties, worst |du0| = {worst:.2e}")
+    assert n_cmp == 5 * B
+    mpc.close()
+
+
+def test_infeasible_qp_is_cut_short_on_the_device(M, O, ee_home):
+    """The committed infeasible N = 40 QP (tests/golden/infeasible_qp_n40.npz; infeasibility proven by an LP in the CPU tier):
+    solveOCP through the C ABI reports the reference's outcome (QP failed, zero step, SOLVED after one iteration)."""
+    g = np.load(G / "infeasible_qp_n40.npz")
+    mpc = M.BatchMPC(2, 40); mpc.load_nn()
+    mpc.set_params(M.load_default_params(overrides={"sqp.eps_prim": 0.01}))
+    mpc.set_tracks(M.load_track_json(None, ee_home))
+    r = mpc.solve_ocp(np.stack([g["warm"]] * 2), np.stack([g["rb"]] * 2), np.stack([g["u"]] * 2), max_log=4, want_steps=True)
+    assert np.all(r["status"] == 0) and np.all(r["iters"] == 1) and np.all(r["n_logged"] == 1)
+    assert np.abs(r["steps"][:, 0]).max() == 0.0 and np.abs(r["horizon"] - g["warm"][None]).max() == 0.0
+    mpc.close()
+
+
+def test_c1_free_running_to_the_end_of_the_track(M, O, nn, ee_home, track_wp):
+    """Configuration C1 (main.cpp:100-179) FREE-RUNNING: the GPU (B = 1) and the oracle each close their own loop from q_home
+    with no per-cycle re-seeding and no forced decisions, until the harness's own end condition (main.cpp:174: EE within
+    1e-2 of the end point and |s - L| < 1e-2): through the deceleration ramp (cost.cpp:133-134) to the s -> L clamp.
+    The two loops are not bit-identical (noise-level filter ties flip a line-search decision now and then, DESIGN.md 4;
+    the lock-step tests certify each such tie), so the comparison is a stated envelope over the whole lap:
+    path parameter within 2e-3 m, joint angles within 5e-3 rad, applied joint velocities within 0.5 rad/s (the host-compiled
+    product code against the same oracle shows 4e-4 / 2e-3 / 0.2); same number of cycles to the end within 2 %; no failed cycle."""
+    N = 10
+    mpc = make_mpc(M, 1, N, ee_home)
+    o = O.OracleMPC(N=N, nn=nn); o.set_track(*track_wp)
+    L = o.track_length
+    end_point = o.track_eval(L)["pos"]
+    xa = np.r_[O.Q_HOME, 0., 0.][None]; ua = np.zeros((1, 8))
+    xb = xa[0].copy(); ub = np.zeros(8)
+    ds = dq = du = 0.0
+    bad_a = bad_b = 0
+    end_a = end_b = None
+    vs_max = 0.0
+    for c in range(3000):
+        if end_a is None:
+            ra = mpc.run_cycle(xa, ua); bad_a += int(ra["ok"][0] == 0)
+            ua = ra["u0"]; xa = mpc.sim_time_step(ra["x0"], ua, 0.01)
+            if np.linalg.norm(end_point - O.fk(xa[0, :7])[0]) < 1e-2 and abs(xa[0, 7] - L) < 1e-2:
+                end_a = c
+        if end_b is None:
+            rb_ = o.run(xb, ub); bad_b += int(not rb_["ok"])
+            ub = rb_["u0"]; xb = O.sim_time_step(rb_["x0"], ub, 0.01)
+            if np.linalg.norm(end_point - O.fk(xb[:7])[0]) < 1e-2 and abs(xb[7] - L) < 1e-2:
+                end_b = c
+        if end_a is None and end_b is None:
+            ds = max(ds, abs(xa[0, 7] - xb[7])); dq = max(dq, np.abs(xa[0, :7] - xb[:7]).max()); du = max(du, np.abs(ua[0, :7] - ub[:7]).max())
+            vs_max = max(vs_max, xa[0, 8])
+        if end_a is not None and end_b is not None:
+            break
+    print(f"C1 free-running: end reached after {end_a} (GPU) / {end_b} (oracle) cycles, L = {L:.4f}, max |ds| = {ds:.2e}, max |dq| = {dq:.2e}, "
+          f"max |du| = {du:.2e}, failed cycles gpu/oracle = {bad_a}/{bad_b}, final vs = {xa[0, 8]:.3f} (max {vs_max:.3f})")
+    assert end_a is not None and end_b is not None and abs(end_a - end_b) <= 0.02 * end_b
+    assert ds < 2e-3 and dq < 5e-3 and du < 0.5
+    assert bad_a == bad_b == 0
+    assert xa[0, 8] < 0.5 * vs_max          # the deceleration ramp was driven through
+    mpc.close()
+
+
 def test_warm_start_state_roundtrip_and_failure_policy(M, O, ee_home):
     """MPC's persistent members: warm start shift, invalidation on a projection jump (mpc.cpp:117-121)."""
     B, N = 4, 10
@@ -316,7 +431,76 @@ def test_warm_start_state_roundtrip_and_failure_policy(M, O, ee_home):
     r1 = mpc.run_cycle(x1, r["u0"])
     _, v3, f3 = mpc.get_warm_state()
     assert np.all(r1["status"] == 0)
+    # the jumped instance regenerated its guess (num_valid_guess_failed_++ in the prologue, mpc.cpp:117-121), solved, and the
+    # epilogue then set valid = true / failed = 0 (mpc.cpp:140-144); projection pulled s back near the path point
+    assert np.all(v3 == 1) and np.all(f3 == 0)
+    assert abs(r1["x0"][0, 7] - x1[0, 7]) > 0.4 and np.abs(r1["x0"][1:, 7] - x1[1:, 7]).max() < 1e-3
+    assert r1["iters"][0] >= r1["iters"][1:].max()      # a regenerated (cold) guess needs at least as many SQP iterations
+    assert np.abs(r1["horizon"][0, 0, :9] - r1["x0"][0]).max() == 0.0
     mpc.close()
+
+
+def test_failure_policy_through_the_kernels(M, O, nn, ee_home, track_wp):
+    """Status policy of runMPC_ (mpc.cpp:140-188) exercised through k_prologue / k_sqp_warp, not the host emulation:
+    MAX_ITER_EXCEEDED invalidates the warm start, counts failures, returns true only while failed < 5; NON_PD_HESSIAN and
+    NAN_HESSIAN abort the loop, return false and fall back to the x0 horizon with zero inputs."""
+    B, N = 4, 10
+    x0 = np.tile(np.r_[O.Q_HOME, 0., 0.], (B, 1)); u0 = np.zeros((B, 8))
+    # (a) MAX_ITER_EXCEEDED: eps_prim so small that alpha |step| never gets below it, max_iter = 3
+    mpc = M.BatchMPC(B, N); mpc.load_nn()
+    mpc.set_params(M.load_default_params(overrides={"sqp.eps_prim": 1e-13, "sqp.max_iter": 3}))
+    mpc.set_tracks(M.load_track_json(None, ee_home))
+    po = O.load_params(overrides={"sqp": {"eps_prim": 1e-13, "max_iter": 3}})
+    o = O.OracleMPC(N=N, nn=nn, params=po); o.set_track(*track_wp)
+    x = x0.copy(); u = u0.copy()
+    xo, uo = x0[0].copy(), u0[0].copy()
+    for c in range(6):
+        r = mpc.run_cycle(x, u)
+        ro = o.run(xo, uo)
+        _, v, f = mpc.get_warm_state()
+        assert np.all(r["status"] == 1) and ro["status"] == 1 and np.all(r["iters"] == 3)
+        assert np.all(v == 0) and np.all(f == c + 1)
+        assert np.all(r["ok"] == (1 if c + 1 < 5 else 0)) and bool(ro["ok"]) == (c + 1 < 5)
+        # fallback horizon: every stage = x0 (updated s, vs), inputs zero (mpc.cpp:171-181 via generateNewInitialGuess semantics)
+        assert np.abs(r["horizon"][:, :, :9] - r["x0"][:, None, :]).max() == 0.0 and np.abs(r["horizon"][:, :, 9:]).max() == 0.0
+        assert np.abs(r["u0"]).max() == 0.0 and np.abs(ro["u0"]).max() == 0.0
+        x = mpc.sim_time_step(r["x0"], r["u0"]); xo = O.sim_time_step(ro["x0"], ro["u0"], 0.01)
+    mpc.close()
+    # (b) NON_PD_HESSIAN: a negative input weight makes the input block of the Hessian indefinite (osqp_interface.cpp:454-462)
+    mpc = M.BatchMPC(B, N); mpc.load_nn()
+    mpc.set_params(M.load_default_params(overrides={"cost.rdq": -1.0}))
+    mpc.set_tracks(M.load_track_json(None, ee_home))
+    o = O.OracleMPC(N=N, nn=nn, params=O.load_params(overrides={"cost": {"rdq": -1.0}})); o.set_track(*track_wp)
+    r = mpc.run_cycle(x0, u0); ro = o.run(x0[0], u0[0])
+    assert np.all(r["status"] == 11) and ro["status"] == 11 and np.all(r["ok"] == 0) and not ro["ok"]
+    _, v, f = mpc.get_warm_state()
+    assert np.all(v == 0) and np.all(f == 1)
+    mpc.close()
+    # (c) NAN_HESSIAN: a NaN weight poisons the Hessian (osqp_interface.cpp:464-473)
+    mpc = M.BatchMPC(B, N); mpc.load_nn()
+    mpc.set_params(M.load_default_params(overrides={"cost.qVs": float("nan")}))
+    mpc.set_tracks(M.load_track_json(None, ee_home))
+    o = O.OracleMPC(N=N, nn=nn, params=O.load_params(overrides={"cost": {"qVs": float("nan")}})); o.set_track(*track_wp)
+    r = mpc.run_cycle(x0, u0); ro = o.run(x0[0], u0[0])
+    # Eigen's LLT flags only pivots x <= 0, so a NaN Hessian passes isPosdef and is caught by isNan: NAN_HESSIAN (10)
+    assert ro["status"] == 10 and np.all(r["status"] == 10) and np.all(r["ok"] == 0)
+    mpc.close()
+
+
+def test_two_handles_with_different_horizons(M, O, ee_home):
+    """cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the kernel, not to a handle: an N = 10 and an N = 40 handle
+    alive at the same time must both keep cycling, created in either order."""
+    x = lambda B: np.tile(np.r_[O.Q_HOME, 0., 0.], (B, 1))
+    for order in ((10, 40), (40, 10)):
+        a = make_mpc(M, 4, order[0], ee_home)
+        b = make_mpc(M, 4, order[1], ee_home)
+        ref_a = a.run_cycle(x(4), np.zeros((4, 8)))["u0"]
+        ref_b = b.run_cycle(x(4), np.zeros((4, 8)))["u0"]
+        for _ in range(3):
+            a.reset(); b.reset()
+            assert np.array_equal(a.run_cycle(x(4), np.zeros((4, 8)))["u0"], ref_a)
+            assert np.array_equal(b.run_cycle(x(4), np.zeros((4, 8)))["u0"], ref_b)
+        a.close(); b.close()
 
 
 def test_heterogeneous_tracks_and_weights(M, O, nn, ee_home, rng):
