@@ -217,6 +217,228 @@ class DevPtr:
         self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 3, "strides": None}
 
 
+# params record offsets (include/mpcc_cuda.h): model7 | cost12 | ...
+P_COST = 7
+P_QC, P_QL, P_QVS, P_QORI = P_COST + 0, P_COST + 2, P_COST + 3, P_COST + 4
+
+CONFIGS = {
+    # name: (batch per GPU, horizon, description)
+    "c2": (4096, 20, "C2 (BASELINE configs[1]): 4096 Panda instances per GPU, q0 = q_home + U(-0.05,0.05) seeded, default track.json, N=20, closed loop"),
+    "c3": (4096, 20, "C3 (BASELINE configs[2]): 4096 instances per GPU, N=20, live moving obstacle (env-collision rows active), tol_envcol=1, tol_sing=0.018, v_des=0.1; "
+                     "fixed-base Panda (the reference has no mobile-base model, SURVEY F4)"),
+    "c4": (8192, 20, "C4 (BASELINE configs[3]): heterogeneous batch, 8192 instances per GPU (65536 on 8), per-instance track.py-family spline (fitted on the device) "
+                     "and per-instance cost weights qC/qL/qOri/qVs, N=20"),
+    "c5": (64, 40, "C5 (BASELINE configs[4]): latency mode, 64 instances, N=40, eps_prim=0.01 (several SQP iterations per cycle), per-cycle latency through the host-buffer call"),
+}
+
+
+def setup_config(M, name, B, N, local, rank):
+    """Build the handle and the synthetic closed-loop start of one BASELINE configuration."""
+    over = None
+    if name == "c3":
+        over = {"model.tol_envcol": 1.0, "model.tol_sing": 0.018, "model.desired_ee_velocity": 0.1}
+    if name == "c5":
+        over = {"sqp.eps_prim": 0.01}
+    mpc = M.BatchMPC(B, N, device=local, qp_eps=float(os.environ.get("MPCC_BENCH_QP_EPS", "0")))  # 0 = library default; env: diagnostic sweeps only
+    mpc.load_nn()
+    base = M.load_default_params(overrides=over)
+    seed = {"c2": 0, "c3": 1, "c4": 2, "c5": 3}[name] + 1000 * rank
+    rng = np.random.default_rng(seed)
+    x0 = np.tile(np.r_[q_home(), 0.0, 0.0], (B, 1))
+    x0[:, :7] += rng.uniform(-0.05, 0.05, (B, 7))
+    u0 = np.zeros((B, 8))
+    obs = None
+    info = {}
+    if name == "c4":
+        P = np.tile(base, (B, 1))
+        P[:, P_QC] = rng.uniform(200, 1000, B); P[:, P_QL] = rng.uniform(50, 200, B); P[:, P_QORI] = rng.uniform(10, 100, B); P[:, P_QVS] = rng.uniform(5, 40, B)
+        mpc.set_params(P)
+    else:
+        mpc.set_params(base)
+    # tracks start at the EE position at q_home, as main.cpp does (track.cpp:58-60); FK through the library itself
+    ee = mpc.eval_robot_data(q_home()[None])[0, 7:10]
+    if name == "c4":
+        t = np.linspace(np.pi / 2, 5 * np.pi / 2, 100)
+        a, b, c = rng.uniform(1.5, 3, B), rng.uniform(1.5, 3, B), rng.uniform(0, 2.5, B)
+        X = 0.1 * a[:, None] * np.sin(t)[None]; Y = 0.1 * b[:, None] * np.sin(2 * t)[None]; Z = 0.1 * c[:, None] * np.cos(t)[None]
+        X = X - X[:, :1] + ee[0]; Y = Y - Y[:, :1] + ee[1]; Z = Z - Z[:, :1] + ee[2]
+        R = np.tile(np.diag([1.0, -1.0, -1.0]).ravel(), (B, 100, 1))
+        t0 = time.perf_counter()
+        mpc.fit_tracks_device(X, Y, Z, R, np.arange(B))     # ArcLengthSpline::fitSpline for every instance, on the device
+        info["track_fit_ms"] = 1e3 * (time.perf_counter() - t0)
+        x0[:, :7] = q_home()[None] + rng.uniform(-0.03, 0.03, (B, 7))
+    else:
+        mpc.set_tracks(M.load_track_json(None, ee))
+    if name == "c3":
+        obs = np.c_[np.array([0.48, 0.218, 0.521]) + rng.uniform(-0.05, 0.05, (B, 3)), np.full(B, 5.0)]
+    return mpc, x0, u0, obs, info
+
+
+def measure(M, name, args, steps, warmup, world, rank, local, dist, full):
+    """Closed-loop measurement of one configuration on this rank's GPU.
+    Returns the device-resident timing (`value`), the end-to-end timing through the host-buffer call (`e2e`) and, with `full`,
+    per-kernel times / stats for the roofline."""
+    import torch
+    import ctypes as C
+    from mpcc_manipulator_b200 import capi
+    B, N, desc = CONFIGS[name]
+    if name == args.config:
+        B = args.batch or B; N = args.horizon or N
+    S = N + 1
+    Ts = 0.01
+    mpc, x_host, u_host, obs_host, info = setup_config(M, name, B, N, local, rank)
+    dev = f"cuda:{local}"
+    if world > 1:
+        # the library's own communicator (NCCL bound at run time): rank 0 creates the id, torch.distributed only carries it
+        uid = torch.from_numpy(M.comm_unique_id() if rank == 0 else np.zeros(128, np.uint8)).to(dev)
+        dist.broadcast(uid, 0)
+        mpc.comm_init(uid.cpu().numpy(), rank, world)
+    stream = torch.cuda.ExternalStream(mpc.stream, device=local)
+    p_u, p_hor, p_st, p_it, p_ok = mpc.result_pointers()
+    with torch.cuda.stream(stream):
+        x = torch.from_numpy(x_host).to(dev)
+        xn = torch.empty_like(x)
+        u = torch.from_numpy(u_host).to(dev)
+        obs = torch.from_numpy(obs_host).to(dev) if obs_host is not None else None
+        u_out = torch.as_tensor(DevPtr(p_u, (B, 8), "<f8"), device=dev)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    stream.synchronize()
+    launches = {"n": 0}
+
+    def step():
+        """device-resident closed-loop step: cycle -> (enqueue the gather on the side stream) -> plant step"""
+        nonlocal x, xn
+        mpc.run_cycle_device(x.data_ptr(), u.data_ptr(), obs.data_ptr() if obs is not None else None)
+        if world > 1:
+            mpc.gather_results()   # the path's only collective: u0 / status / iterations of every rank (NCCL all-gather, off the critical path)
+        launches["n"] += mpc.launch_count()
+        with torch.cuda.stream(stream):
+            u.copy_(u_out)
+            if obs is not None:
+                obs[:, 2] += 0.05 * Ts     # obstacle moving at 0.05 m/s in z (python/main_w_sim.py:126-129)
+        mpc.sim_time_step_device(x.data_ptr(), u.data_ptr(), xn.data_ptr())
+        launches["n"] += 1
+        x, xn = xn, x
+
+    for _ in range(warmup):
+        step()
+    mpc.synchronize()
+    mpc.set_profiling(True)
+    sampler = ClockSampler(local) if (full and rank == 0) else None
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    if sampler:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    ktimes = np.zeros((steps, 4))
+    stats_acc = {}
+    qp_iters_acc = 0
+    launches["n"] = 0
+    t_wall0 = time.perf_counter()
+    for i in range(steps):
+        with torch.cuda.stream(stream):
+            flush.zero_()  # L2 flush between timed iterations (outside the event pair)
+            ev[i][0].record(stream)
+        step()
+        with torch.cuda.stream(stream):
+            ev[i][1].record(stream)
+        ktimes[i] = mpc.kernel_times()
+        if full or i == steps - 1:
+            stats_acc = mpc.stats()
+            qp_iters_acc += stats_acc["qp_iters"]
+    mpc.synchronize()
+    if world > 1:
+        gathered = mpc.read_gathered()   # waits for the last enqueued gather: the timed region ends with every rank's results everywhere
+        assert gathered["u0"].shape[0] == world * B
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if sampler else None
+    step_ms = np.array([a.elapsed_time(b) for a, b in ev])
+    total_ms = float(step_ms.sum())
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms_max = float(t.item())
+    else:
+        total_ms_max = total_ms
+    value = world * B * steps / (total_ms_max * 1e-3)
+    mpc.set_profiling(False)
+
+    # ---- e2e: HOST buffers through mpcc_cuda_run_cycle (pinned), copies inside the timed region, MPCReturn complete
+    #      (u0, the whole mpc_horizon, status, iterations, ok) and, on several GPUs, the gather read back on the host ----
+    hx = torch.empty((B, 9), dtype=torch.float64).pin_memory(); hu = torch.empty((B, 8), dtype=torch.float64).pin_memory()
+    huo = torch.empty((B, 8), dtype=torch.float64).pin_memory(); hhor = torch.empty((B, S, 17), dtype=torch.float64).pin_memory()
+    hobs = torch.from_numpy(obs_host.copy()).pin_memory() if obs_host is not None else None
+    hst = torch.empty(B, dtype=torch.int32).pin_memory(); hit = torch.empty(B, dtype=torch.int32).pin_memory(); hok = torch.empty(B, dtype=torch.int32).pin_memory()
+    mpc.reset()   # same closed loop from the same start as the device-resident measurement
+    hx.copy_(torch.from_numpy(x_host)); hu.copy_(torch.from_numpy(u_host))
+    gu = np.zeros((world * B, 8)); gs = np.zeros(world * B, np.int32); gi = np.zeros(world * B, np.int32)
+
+    def e2e_step():
+        rc = capi.lib().mpcc_cuda_run_cycle(mpc.h, C.c_void_p(hx.data_ptr()), C.c_void_p(hu.data_ptr()), C.c_void_p(hobs.data_ptr()) if hobs is not None else None,
+                                            C.c_void_p(huo.data_ptr()), C.c_void_p(hhor.data_ptr()), C.c_void_p(hst.data_ptr()), C.c_void_p(hit.data_ptr()), C.c_void_p(hok.data_ptr()))
+        if rc != 0:
+            raise RuntimeError(capi.lib().mpcc_cuda_last_error().decode())
+        if world > 1:
+            mpc.gather_results()
+            capi._check(capi.lib().mpcc_cuda_read_gathered(mpc.h, capi._p(gu), capi._p(gs), capi._p(gi)))
+        # host-side plant step (exact for the linear model; integrator.cpp:55-68), next cycle's inputs
+        xs, us = hx.numpy(), huo.numpy()
+        xs[:, :7] += Ts * us[:, :7]
+        xs[:, 7] += Ts * xs[:, 8] + 0.5 * Ts * Ts * us[:, 7]
+        xs[:, 8] += Ts * us[:, 7]
+        hu.copy_(huo)
+        if hobs is not None:
+            hobs[:, 2] += 0.05 * Ts
+
+    e2e_steps = steps if name == "c5" else max(3, min(steps, 20))
+    for _ in range(warmup):
+        e2e_step()
+    if world > 1:
+        dist.barrier()
+    lat = np.zeros(e2e_steps)
+    iters_max = np.zeros(e2e_steps, int)
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        ta = time.perf_counter()
+        e2e_step()
+        lat[i] = (time.perf_counter() - ta) * 1e3
+        iters_max[i] = int(hit.max())
+    t_e2e = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_e2e = float(t.item())
+    e2e_val = world * B * e2e_steps / t_e2e
+    h2d = B * (9 + 8) * 8 + (B * 4 * 8 if hobs is not None else 0)
+    d2h = B * 9 * 8 + B * 8 * 8 + B * S * 17 * 8 + 3 * B * 4 + (world * B * 72 if world > 1 else 0)
+    res = {"name": name, "workload": desc, "B": B, "N": N, "value": value, "ms_per_step": total_ms_max / steps, "step_ms": step_ms, "ktimes": ktimes,
+           "stats": stats_acc, "qp_iters_mean": qp_iters_acc / max(1, steps if full else 1), "launches": launches["n"], "clocks": clocks, "t_wall": t_wall,
+           "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                   "api": "mpcc_cuda_run_cycle (host buffers, pinned; u0 + full mpc_horizon + status/iters/ok copied back"
+                          + ("; + mpcc_cuda_gather_results / read_gathered over NCCL" if world > 1 else "") + ")",
+                   "latency_ms": {"p50": float(np.percentile(lat, 50)), "p90": float(np.percentile(lat, 90)), "p99": float(np.percentile(lat, 99)), "max": float(lat.max())},
+                   "max_sqp_iters_per_cycle": {"p50": int(np.percentile(iters_max, 50)), "p99": int(np.percentile(iters_max, 99)), "max": int(iters_max.max())}},
+           "info": info}
+    mpc.close()
+    return res
+
+
+def summary_of(r):
+    """compact record of a secondary configuration for the JSON line"""
+    sm = r["step_ms"]
+    return {"workload": r["workload"], "batch_per_gpu": r["B"], "horizon": r["N"], "value": r["value"], "unit": UNIT, "ms_per_step": r["ms_per_step"],
+            "device_step_ms": {"p50": float(np.percentile(sm, 50)), "p99": float(np.percentile(sm, 99)), "max": float(sm.max())},
+            "e2e": r["e2e"], "kernels_ms": {n: round(float(t), 4) for n, t in zip(KERNEL_NAMES, r["ktimes"].mean(axis=0))},
+            "last_step_stats": r["stats"], **r["info"]}
+
+
+KERNEL_NAMES = ["k_prologue", "k_kin", "k_mlp", "k_sqp_warp"]
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -230,157 +452,51 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    B, N = args.batch, args.horizon
-    S = N + 1
-    mpc = M.BatchMPC(B, N, device=local, qp_eps=float(os.environ.get("MPCC_BENCH_QP_EPS", "0")))  # 0 = library default; env: diagnostic sweeps only
-    # track shifted to the EE position at q_home, as main.cpp does (track.cpp:58-60); FK through the library itself
-    mpc.load_nn()
-    mpc.set_params(M.load_default_params())
-    ee = mpc.eval_robot_data(q_home()[None])[0, 7:10]
-    mpc.set_tracks(M.load_track_json(None, ee))
-
-    stream = torch.cuda.ExternalStream(mpc.stream, device=local)
-    x_host, u_host = synthetic_inputs(B, seed=rank)
-    p_u, p_hor, p_st, p_it, p_ok = mpc.result_pointers()
-    with torch.cuda.stream(stream):
-        x = torch.from_numpy(x_host).cuda(non_blocking=False)
-        xn = torch.empty_like(x)
-        u = torch.from_numpy(u_host).cuda()
-        u_out = torch.as_tensor(DevPtr(p_u, (B, 8), "<f8"), device=f"cuda:{local}")
-        st_out = torch.as_tensor(DevPtr(p_st, (B,), "<i4"), device=f"cuda:{local}")
-        it_out = torch.as_tensor(DevPtr(p_it, (B,), "<i4"), device=f"cuda:{local}")
-        flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")  # > 126 MB L2
-    launches = {"n": 0}
-    gathered = {}
-    from mpcc_manipulator_b200.sharding import ResultGatherer
-    gatherer = ResultGatherer(B, world, f"cuda:{local}") if world > 1 else None
-
-    def step():
-        """device-resident closed-loop step: cycle -> (gather) -> plant"""
-        nonlocal x, xn
-        mpc.run_cycle_device(x.data_ptr(), u.data_ptr())
-        launches["n"] += 6  # k_prologue, k_kin, k_mlp, k_order, k_sqp_warp x 2 (exclusive-SM launch + main launch); == mpcc_cuda_get_stats()[0]
-        with torch.cuda.stream(stream):
-            if world > 1:
-                # the path's only collective: gather the applied controls and per-instance status / iterations (NCCL)
-                gathered["u0"], gathered["status"], gathered["iters"] = gatherer(u_out, st_out, it_out, dist)
-            u.copy_(u_out)
-        mpc.sim_time_step_device(x.data_ptr(), u.data_ptr(), xn.data_ptr())
-        launches["n"] += 1
-        x, xn = xn, x
-
-    for _ in range(args.warmup):
-        step()
-    mpc.synchronize()
-    mpc.set_profiling(True)
-    sampler = ClockSampler(local)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    if rank == 0:
-        sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    ktimes = np.zeros((args.steps, 4))
-    stats_acc = {}
-    launches["n"] = 0
-    t_wall0 = time.perf_counter()
-    for i in range(args.steps):
-        with torch.cuda.stream(stream):
-            flush.zero_()  # L2 flush between timed iterations (outside the event pair)
-            ev[i][0].record(stream)
-        step()
-        with torch.cuda.stream(stream):
-            ev[i][1].record(stream)
-        ktimes[i] = mpc.kernel_times()
-        if i == args.steps - 1:
-            st = mpc.stats()
-            stats_acc = st
-    mpc.synchronize()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t_wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop() if rank == 0 else None
-    step_ms = np.array([a.elapsed_time(b) for a, b in ev])
-    total_ms = float(step_ms.sum())
-    if world > 1:
-        t = torch.tensor([total_ms], dtype=torch.float64, device=f"cuda:{local}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms_max = float(t.item())
-    else:
-        total_ms_max = total_ms
-    value = world * B * args.steps / (total_ms_max * 1e-3)
-    mpc.set_profiling(False)
-
-    # ---- e2e: HOST buffers through mpcc_cuda_run_cycle (pinned), copies inside the timed region ----
-    import ctypes as C
-    from mpcc_manipulator_b200 import capi
-    hx = torch.empty((B, 9), dtype=torch.float64).pin_memory(); hu = torch.empty((B, 8), dtype=torch.float64).pin_memory()
-    huo = torch.empty((B, 8), dtype=torch.float64).pin_memory()
-    hst = torch.empty(B, dtype=torch.int32).pin_memory(); hit = torch.empty(B, dtype=torch.int32).pin_memory(); hok = torch.empty(B, dtype=torch.int32).pin_memory()
-    # same closed loop from the same start as the device-resident measurement: forget the warm starts, replay the warm-up
-    mpc.reset()
-    hx.copy_(torch.from_numpy(x_host)); hu.copy_(torch.from_numpy(u_host))
-    Ts = 0.01
-
-    def e2e_step():
-        rc = capi.lib().mpcc_cuda_run_cycle(mpc.h, C.c_void_p(hx.data_ptr()), C.c_void_p(hu.data_ptr()), None, C.c_void_p(huo.data_ptr()), None,
-                                            C.c_void_p(hst.data_ptr()), C.c_void_p(hit.data_ptr()), C.c_void_p(hok.data_ptr()))
-        if rc != 0:
-            raise RuntimeError(capi.lib().mpcc_cuda_last_error().decode())
-        # host-side plant step (exact for the linear model; integrator.cpp:55-68), next cycle's inputs
-        xs, us = hx.numpy(), huo.numpy()
-        xs[:, :7] += Ts * us[:, :7]
-        xs[:, 7] += Ts * xs[:, 8] + 0.5 * Ts * Ts * us[:, 7]
-        xs[:, 8] += Ts * us[:, 7]
-        hu.copy_(huo)
-
-    e2e_steps = max(3, min(args.steps, 20))
-    for _ in range(args.warmup):
-        e2e_step()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    t_e2e = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([t_e2e], dtype=torch.float64, device=f"cuda:{local}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_e2e = float(t.item())
-    e2e_val = world * B * e2e_steps / t_e2e
-    h2d = B * (9 + 8) * 8
-    d2h = B * (9 + 8) * 8 + 3 * B * 4
+    r = measure(M, args.config, args, args.steps, args.warmup, world, rank, local, dist, full=True)
+    B, N, S = r["B"], r["N"], r["N"] + 1
+    # secondary BASELINE configurations, short runs, reported inside the same JSON line (the driver only runs the default command)
+    secondary = {}
+    if args.config == "c2" and not args.no_secondary:
+        names = ["c3", "c4", "c5"] if world == 1 else ["c4"]
+        for nm in names:
+            st, wu = (300, 20) if nm == "c5" else (10, 3)
+            secondary[nm] = summary_of(measure(M, nm, args, st, wu, world, rank, local, dist, full=False))
 
     out = None
     if rank == 0:
+        step_ms, ktimes, stats_acc = r["step_ms"], r["ktimes"], r["stats"]
         km = ktimes.mean(axis=0)
-        names = ["k_prologue", "k_kin", "k_mlp", "k_sqp_warp"]
+        names = KERNEL_NAMES
         dom = int(np.argmax(km))
         peak = M.fp64_peak(local)
         peak_src = ("FP64 microbenchmark measured in this run (mpcc_cuda_fp64_peak: larger of the DFMA and the mma.m8n8k4.f64 figure, one shared pipe); MEASURED_PEAKS.json holds no FP64 figure; "
                     "nominal 148 SM x 64 FMA/clk x 1.965 GHz = %.1f" % NOMINAL_FP64_TFLOPS)
+        # DRAM traffic per launch: ncu --set full captures of STEADY-STATE launches, committed with their capture conditions;
+        # reported as captured (bytes per launch), never divided by this run's kernel time
         traffic = {}
         try:
             traffic = json.loads((ROOT / "profiles" / "dram_traffic.json").read_text())
         except Exception:
             pass
         mlp_flop = B * S * MLP_FLOP_PER_STAGE
-        qp_iters_step = float(stats_acc.get("qp_iters", 0))
-        sqp_flop = qp_iters_step * N * QP_FLOP_PER_STAGE_ITER
+        sqp_flop = r["qp_iters_mean"] * N * QP_FLOP_PER_STAGE_ITER
         kernels = {n: round(float(t), 4) for n, t in zip(names, km)}
         share = {n: round(float(t / step_ms.mean()), 4) for n, t in zip(names, km)}
 
         def roof_of(kernel, flop, ms, note, bound):
             ach = flop / (ms * 1e-3) / 1e12
+            tr = traffic.get(kernel)
             return {"bound": bound, "pipe": "fp64", "kernel": kernel, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                    "traffic": traffic.get(kernel), "algorithmic_flops_per_launch": flop, "kernel_ms": float(ms), "peak_source": peak_src, "note": note}
+                    "traffic": tr.get("dram_bytes_per_launch") if isinstance(tr, dict) else tr, "traffic_capture": tr if isinstance(tr, dict) else None,
+                    "algorithmic_flops_per_launch": flop, "kernel_ms": float(ms), "peak_source": peak_src, "note": note}
         roof_mlp = roof_of("k_mlp", mlp_flop, km[2], "dense fp64 contraction (both networks + 7 forward-mode tangents) on mma.sync.m8n8k4.f64; tcgen05 has no f64 kind, DMMA and DFMA share one FP64 pipe, which is the roof", "tensor")
-        roof_sqp = roof_of("k_sqp_warp", sqp_flop, km[3], "interior-point / Riccati SQP loop: dependent small factorisations, latency- and DRAM-latency-bound "
-                           "(FLOP model x measured interior-point iterations of the last step); its DRAM traffic is in `traffic`", "latency (reported against the fp64 pipe)")
+        roof_sqp = roof_of("k_sqp_warp", sqp_flop, km[3], "interior-point / Riccati SQP loop: dependent small factorisations, latency-bound "
+                           "(FLOP model x measured interior-point iterations, mean over the timed steps)", "latency (reported against the fp64 pipe)")
         roof = dict(roof_sqp if dom == 3 else roof_mlp)
         roof["dominant_kernel"] = names[dom]
         roof["kernel_share_of_step"] = share
+        whole = (B * S * (MLP_FLOP_PER_STAGE + KIN_FLOP_PER_STAGE)) / (step_ms.mean() * 1e-3) / 1e12
+        roof["whole_cycle"] = {"achieved": whole, "frac": whole / peak, "note": "fixed algorithmic FLOPs of the cycle (networks + kinematics, SURVEY 8d) / mean step time"}
         hbm_peak = None
         try:
             hbm_peak = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"]
@@ -389,18 +505,18 @@ def run_ours(args):
         alg_bytes = B * ((9 + 8 + 4) * 8 + 2 * (17 * N + 9) * 8 + 64 + 16)
         roof["hbm"] = {"algorithmic_bytes_per_step": alg_bytes, "achieved_gbs": alg_bytes / (step_ms.mean() * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                        "note": "arithmetic intensity ~1e4 FLOP/B: HBM fraction is tiny by construction (SURVEY 8d)"}
-        if traffic.get(names[dom]) and hbm_peak:
-            roof["hbm"]["dominant_kernel_dram_gbs"] = traffic[names[dom]] / (km[dom] * 1e-3) / 1e9
-        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-               "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-               "config": {"workload": "C2 (BASELINE configs[1]): 4096 Panda instances per GPU, q0 = q_home + U(-0.05,0.05) seeded, default track.json, N=20, closed loop",
-                          "batch_per_gpu": B, "horizon": N, "l2": "flushed (256 MiB memset) between timed steps", "parallelism": f"dp{world} (instances sharded, all_gather of u0/status only)"},
-               "latency_ms": {"p50": float(np.percentile(step_ms, 50)), "p99": float(np.percentile(step_ms, 99)), "max": float(step_ms.max())},
-               "clocks": clocks, "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                                         "api": "mpcc_cuda_run_cycle (host buffers, pinned)"},
-               "gpu_launches": launches["n"], "kernels_ms": kernels, "roofline": roof, "roofline_mlp": roof_mlp, "roofline_sqp": roof_sqp,
-               "last_step_stats": stats_acc, "wall_s_timed_region": t_wall}
-    mpc.close()
+        out = {"metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": r["workload"], "name": args.config,
+                          "batch_per_gpu": B, "horizon": N, "l2": "flushed (256 MiB memset) between timed steps",
+                          "parallelism": f"dp{world} (instances sharded; all-gather of u0/status/iters only, NCCL on a side stream through mpcc_cuda_gather_results)"},
+               "latency_ms": {"p50": float(np.percentile(step_ms, 50)), "p99": float(np.percentile(step_ms, 99)), "max": float(step_ms.max()),
+                              "what": "device time of one closed-loop step of the whole batch (CUDA events)"},
+               "clocks": r["clocks"], "e2e": r["e2e"],
+               "gpu_launches": r["launches"], "kernels_ms": kernels, "roofline": roof, "roofline_mlp": roof_mlp, "roofline_sqp": roof_sqp,
+               "last_step_stats": stats_acc, "wall_s_timed_region": r["t_wall"]}
+        if secondary:
+            out["secondary_configs"] = secondary
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -416,17 +532,21 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=4096)
-    ap.add_argument("--horizon", type=int, default=20)
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS), help="BASELINE configuration (SURVEY 8d); c2 is the metric's")
+    ap.add_argument("--batch", type=int, default=0, help="instances per GPU (0: the configuration's own)")
+    ap.add_argument("--horizon", type=int, default=0, help="N (0: the configuration's own)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the short C3 / C4 / C5 runs that the default (c2) line carries")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-worker", action="store_true")
     ap.add_argument("--worker-id", type=int, default=0)
     ap.add_argument("--per", type=int, default=2)
     args = ap.parse_args()
     if args.cpu_worker:
+        args.horizon = args.horizon or 20
         return cpu_worker_main(args)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
+        args.horizon = args.horizon or CONFIGS[args.config][1]
         return run_reference(args)
     return run_ours(args)
 

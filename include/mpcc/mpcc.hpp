@@ -109,12 +109,19 @@ public:
     BatchMPC(int batch, int horizon, double Ts, const PathToJson& path, const ParamValue& pv = ParamValue(), int device = 0) : B_(batch), N_(horizon), Ts_(Ts), path_(path) {
         mpcc_cuda_config cfg{}; cfg.batch = batch; cfg.horizon = horizon; cfg.Ts = Ts; cfg.device = device;
         check(mpcc_cuda_create(&cfg, &h_));
-        setParam(pv);
+        ctor_pv_ = pv;
+        auto p = loadParams(path_, pv); check(mpcc_cuda_set_params(h_, p.data(), 1));   // MPC(Ts, path, param_value), mpc.cpp:36-52
     }
     ~BatchMPC() { if (h_) mpcc_cuda_destroy(h_); }
     BatchMPC(const BatchMPC&) = delete; BatchMPC& operator=(const BatchMPC&) = delete;
     void loadNetworks(const std::string& self_path, const std::string& env_path) { check(mpcc_cuda_load_nn(h_, self_path.c_str(), env_path.c_str())); }
-    void setParam(const ParamValue& pv) { auto p = loadParams(path_, pv); check(mpcc_cuda_set_params(h_, p.data(), 1)); }
+    // MPC::setParam on a live object (mpc.cpp:204-209, osqp_interface.cpp:95-100): the "param" and "cost" maps take
+    // effect (file values + this map), bounds are rebuilt from the file, the normalisation and SQP parameters keep their
+    // construction-time values, and the interface's own rddq stays the file's.  Warm starts are kept (main.cpp:103-106).
+    void setParam(const ParamValue& pv) {
+        ParamValue live; live.param = pv.param; live.cost = pv.cost; live.normalization = ctor_pv_.normalization; live.sqp = ctor_pv_.sqp;
+        auto p = loadParams(path_, live); check(mpcc_cuda_set_params(h_, p.data(), 1));
+    }
     void setParams(const std::vector<ParamValue>& per_instance) {
         std::vector<double> all; for (auto& pv : per_instance) { auto p = loadParams(path_, pv); all.insert(all.end(), p.begin(), p.end()); }
         check(mpcc_cuda_set_params(h_, all.data(), (int32_t)per_instance.size()));
@@ -174,7 +181,7 @@ public:
     int horizon() const { return N_; }
     mpcc_cuda_handle* handle() { return h_; }
 private:
-    int B_, N_; double Ts_; PathToJson path_;
+    int B_, N_; double Ts_; PathToJson path_; ParamValue ctor_pv_;
     mpcc_cuda_handle* h_ = nullptr;
     std::vector<double> track_len_;
 };

@@ -96,6 +96,15 @@ int mpcc_load_track_json(const char* track_path, const double* init_position3 /*
  * Invalidates every warm start (valid_initial_guess_ = false; the failure counter keeps its value: MPC::setTrack, mpc.cpp:192-197). */
 int mpcc_cuda_set_tracks(mpcc_cuda_handle* h, const double* tables, int32_t n_tracks, const int32_t* track_of_instance);
 
+/* Track ingestion on the DEVICE (ArcLengthSpline::fitSpline, arc_length_spline.cpp:213-253, one thread per track): host
+ * waypoints X, Y, Z [n_tracks][n], R [n_tracks][n][9] in; the fitted tables become the handle's tracks (equivalent to
+ * mpcc_fit_tracks + mpcc_cuda_set_tracks).  mpcc_cuda_get_tracks copies the first n_tracks installed tables back to the host. */
+int mpcc_cuda_fit_tracks(mpcc_cuda_handle* h, int32_t n_tracks, int32_t n, const double* X, const double* Y, const double* Z, const double* R,
+                         const int32_t* track_of_instance);
+int mpcc_cuda_get_tracks(mpcc_cuda_handle* h, double* tables_out, int32_t n_tracks);
+/* Table from the 100 knots of an already fitted ArcLengthSpline (s, X, Y, Z [100], R [100][9]): no fit / resample pass. */
+int mpcc_track_from_knots(const double* s, const double* X, const double* Y, const double* Z, const double* R, double* table_out);
+
 /* forget all warm starts (valid_initial_guess_ = false, num_valid_guess_failed_ = 0) */
 int mpcc_cuda_reset(mpcc_cuda_handle* h);
 
@@ -163,9 +172,26 @@ int mpcc_cuda_read_qp_counters(mpcc_cuda_handle* h, int32_t* qp_iters, int32_t* 
  * replay the oracle along the same branch when a decision hinges on solver noise. */
 int mpcc_cuda_read_decisions(mpcc_cuda_handle* h, int32_t* accept_mask);
 
+/* ---- multi-GPU (one process and one handle per GPU; the caller shards the batch: instances are independent) ----
+ * The path's only exchange is the gather of the per-instance results.  The library owns a NCCL communicator
+ * (bound at run time, libnccl.so.2): rank 0 calls mpcc_cuda_comm_unique_id() and hands the 128 bytes to every rank by
+ * whatever means the application has (MPI, a file, torch.distributed); every rank then calls mpcc_cuda_comm_init().
+ * world == 1 needs no NCCL.  mpcc_cuda_gather_results() ENQUEUES, behind the current cycle and without blocking the host or
+ * the next cycle, an all-gather of [u0 (8 doubles) | status, iters (2 x int32)] of every instance of every rank on a side
+ * stream (double-buffered); mpcc_cuda_read_gathered() waits for the most recent one and unpacks it into host arrays
+ * u_all [world*B][8], status_all / iters_all [world*B] (rank-major; any may be NULL).  mpcc_cuda_gathered_pointer(): the
+ * packed device buffer [world*B][9] of the most recent gather and the stream it is ordered on. */
+int mpcc_cuda_comm_unique_id(uint8_t* id128);
+int mpcc_cuda_comm_init(mpcc_cuda_handle* h, const uint8_t* id128, int32_t rank, int32_t world);
+int mpcc_cuda_gather_results(mpcc_cuda_handle* h);
+int mpcc_cuda_read_gathered(mpcc_cuda_handle* h, double* u_all, int32_t* status_all, int32_t* iters_all);
+int mpcc_cuda_gathered_pointer(mpcc_cuda_handle* h, double** d_packed, void** stream);
+
 /* counters of the last cycle: [0] kernels launched, [1] total SQP iterations, [2] total QP (IPM) iterations,
  * [3] QP failures, [4] instances SOLVED, [5] instances with ok == 1 */
 int mpcc_cuda_get_stats(mpcc_cuda_handle* h, int64_t* stats6);
+/* kernels (and collectives) enqueued by the last cycle; host-side counter, does not synchronise */
+int64_t mpcc_cuda_launch_count(mpcc_cuda_handle* h);
 
 #ifdef __cplusplus
 }

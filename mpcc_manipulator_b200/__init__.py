@@ -5,4 +5,4 @@ host classes under ``csrc/host``.  This Python package is a thin ctypes binding 
 ``bench.py``; it contains no numerical code and has no CPU fallback: importing :mod:`.capi` raises if the
 library has not been built (``python -c "import __graft_entry__ as g; g.build()"``).
 """
-from .capi import BatchMPC, load_default_params, fit_track, fit_tracks, load_track_json, default_assets, fp64_peak, LIB_PATH  # noqa: F401
+from .capi import BatchMPC, load_default_params, fit_track, fit_tracks, load_track_json, track_from_knots, comm_unique_id, default_assets, fp64_peak, LIB_PATH  # noqa: F401

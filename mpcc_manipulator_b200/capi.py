@@ -18,6 +18,8 @@ EXPORTS = [
     "mpcc_cuda_get_warm_state", "mpcc_cuda_set_warm_state", "mpcc_cuda_sim_time_step", "mpcc_cuda_eval_robot_data", "mpcc_cuda_eval_stage",
     "mpcc_cuda_eval_track", "mpcc_cuda_solve_ocp", "mpcc_cuda_get_stats", "mpcc_cuda_sim_time_step_device", "mpcc_cuda_set_profiling",
     "mpcc_cuda_get_kernel_times", "mpcc_cuda_fp64_peak", "mpcc_cuda_read_decisions", "mpcc_fit_tracks", "mpcc_cuda_read_qp_counters", "mpcc_cuda_read_compute_time",
+    "mpcc_cuda_fit_tracks", "mpcc_cuda_get_tracks", "mpcc_track_from_knots",
+    "mpcc_cuda_comm_unique_id", "mpcc_cuda_comm_init", "mpcc_cuda_gather_results", "mpcc_cuda_read_gathered", "mpcc_cuda_gathered_pointer", "mpcc_cuda_launch_count",
 ]
 
 
@@ -38,6 +40,8 @@ def lib():
         _lib = C.CDLL(str(LIB_PATH))
         _lib.mpcc_cuda_last_error.restype = C.c_char_p
         _lib.mpcc_cuda_stream.restype = C.c_void_p
+        _lib.mpcc_cuda_launch_count.restype = C.c_int64
+        _lib.mpcc_cuda_launch_count.argtypes = [C.c_void_p]
     return _lib
 
 
@@ -85,6 +89,22 @@ def fit_tracks(X, Y, Z, R, n_threads=0):
     t = np.zeros((nt, TRACK_DOUBLES))
     _check(lib().mpcc_fit_tracks(nt, n, _p(X), _p(Y), _p(Z), _p(R), _p(t), n_threads))
     return t
+
+
+def track_from_knots(s, X, Y, Z, R):
+    """Table of an already fitted ArcLengthSpline from its 100 knots (no fit / resample pass)."""
+    t = np.zeros(TRACK_DOUBLES)
+    s, X, Y, Z, R = _f64(s), _f64(X), _f64(Y), _f64(Z), _f64(R)
+    assert len(s) == 100 and R.size == 900
+    _check(lib().mpcc_track_from_knots(_p(s), _p(X), _p(Y), _p(Z), _p(R), _p(t)))
+    return t
+
+
+def comm_unique_id():
+    """128-byte NCCL unique id (rank 0 creates it; the application hands it to every rank)."""
+    buf = np.zeros(128, np.uint8)
+    _check(lib().mpcc_cuda_comm_unique_id(_p(buf)))
+    return buf
 
 
 def load_track_json(path=None, init_position=None):
@@ -136,6 +156,36 @@ class BatchMPC:
         n = 1 if tables.ndim == 1 else tables.shape[0]
         ids = None if track_of_instance is None else np.ascontiguousarray(track_of_instance, dtype=np.int32)
         _check(lib().mpcc_cuda_set_tracks(self.h, _p(tables), n, _p(ids)))
+
+    def fit_tracks_device(self, X, Y, Z, R, track_of_instance=None):
+        """ArcLengthSpline::fitSpline on the device for n_tracks tracks (X, Y, Z [n_tracks][n], R [n_tracks][n][9]); installs them."""
+        X, Y, Z, R = _f64(X), _f64(Y), _f64(Z), _f64(R)
+        if X.ndim == 1:
+            X, Y, Z, R = X[None], Y[None], Z[None], R[None]
+        nt, n = X.shape
+        ids = None if track_of_instance is None else np.ascontiguousarray(track_of_instance, dtype=np.int32)
+        _check(lib().mpcc_cuda_fit_tracks(self.h, nt, n, _p(X), _p(Y), _p(Z), _p(R), _p(ids)))
+
+    def get_tracks(self, n_tracks=1):
+        t = np.zeros((n_tracks, TRACK_DOUBLES))
+        _check(lib().mpcc_cuda_get_tracks(self.h, _p(t), n_tracks))
+        return t
+
+    # ---- multi-GPU: one process / handle per GPU, gather of the per-instance results over NCCL (side stream) ----
+    def comm_init(self, unique_id, rank, world):
+        self.world = int(world)
+        uid = None if unique_id is None else np.ascontiguousarray(unique_id, dtype=np.uint8)
+        _check(lib().mpcc_cuda_comm_init(self.h, _p(uid), int(rank), int(world)))
+
+    def gather_results(self):
+        """Enqueue (non-blocking) the all-gather of this cycle's [u0 | status | iters] of every rank."""
+        _check(lib().mpcc_cuda_gather_results(self.h))
+
+    def read_gathered(self):
+        n = self.B * self.world
+        u = np.zeros((n, NU)); st = np.zeros(n, np.int32); it = np.zeros(n, np.int32)
+        _check(lib().mpcc_cuda_read_gathered(self.h, _p(u), _p(st), _p(it)))
+        return dict(u0=u, status=st, iters=it)
 
     def setup_default(self, init_position=None, params=None):
         self.load_nn()
@@ -246,6 +296,10 @@ class BatchMPC:
         m = np.zeros(self.B, np.int32)
         _check(lib().mpcc_cuda_read_decisions(self.h, _p(m)))
         return m.view(np.uint32)
+
+    def launch_count(self):
+        """kernels launched by the last cycle (host-side counter, no synchronisation)"""
+        return int(lib().mpcc_cuda_launch_count(self.h))
 
     def stats(self):
         s = np.zeros(6, np.int64)

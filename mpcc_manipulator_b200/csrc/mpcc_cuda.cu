@@ -4,6 +4,7 @@
 #include "mpcc_types.h"
 #include "dev_panda.cuh"
 #include "dev_track.cuh"
+#include "dev_track_fit.cuh"
 #include "dev_stage.cuh"
 #include "dev_qp.cuh"
 #include "dev_sqp.cuh"
@@ -19,6 +20,34 @@
 #include <vector>
 #include <stdexcept>
 #include <thread>
+#include <dlfcn.h>
+
+// ---- NCCL, bound at run time (dlopen) so that the library has no link-time dependency on it: only the multi-GPU entry
+// points need it.  Minimal declarations (stable across NCCL 2.x): opaque communicator, 128-byte unique id, ncclDouble = 8.
+typedef struct ncclComm* mpcc_ncclComm_t;
+typedef struct { char internal[128]; } mpcc_ncclUniqueId;
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(mpcc_ncclUniqueId*) = nullptr;
+    int (*CommInitRank)(mpcc_ncclComm_t*, int, mpcc_ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(mpcc_ncclComm_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, mpcc_ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool load(std::string& err) {
+        if (lib) return true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) { lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+        if (!lib) { err = std::string("NCCL not found (dlopen libnccl.so.2): ") + dlerror(); return false; }
+        GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+        CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+        AllGather = (decltype(AllGather))dlsym(lib, "ncclAllGather");
+        GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+        if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllGather || !GetErrorString) { err = "NCCL symbols missing"; lib = nullptr; return false; }
+        return true;
+    }
+};
+static NcclApi g_nccl;
 
 using namespace mpcc;
 
@@ -115,6 +144,22 @@ __global__ void k_warm_io(double* warm_soa, double* hor_aos, int B, int HN, int 
     if (to_aos) hor_aos[i] = warm_soa[(size_t)e * B + b];
     else warm_soa[(size_t)e * B + b] = hor_aos[i];
 }
+// [u0 (8) | status, iters packed into one double slot] per instance: the record the ranks exchange
+__global__ void k_pack_results(const double* __restrict__ u_out, const int32_t* __restrict__ status, const int32_t* __restrict__ iters, int B, double* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * 9) return;
+    const int b = i / 9, e = i - b * 9;
+    if (e < 8) out[i] = u_out[b * 8 + e];
+    else { int2 v = make_int2(status[b], iters[b]); out[i] = *reinterpret_cast<double*>(&v); }
+}
+// ArcLengthSpline::fitSpline for a chunk of tracks, one thread per track (dev_track_fit.cuh)
+__global__ void k_fit_tracks(int n_tracks, int n, const double* __restrict__ X, const double* __restrict__ Y, const double* __restrict__ Z,
+                             const double* __restrict__ R, double* scratch, TrackTable* out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tracks) return;
+    const size_t o = (size_t)t * n;
+    tf_fit_track(n, TArr{(double*)X + o, 1}, TArr{(double*)Y + o, 1}, TArr{(double*)Z + o, 1}, TArr{(double*)R + 9 * o, 1}, TArr{scratch + t, (size_t)n_tracks}, out[t]);
+}
 __global__ void k_invalidate_warm(WarmFlags* fl, int B) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b < B) fl[b].valid = 0;
@@ -182,6 +227,17 @@ struct mpcc_cuda_handle {
     int32_t* hint = nullptr;                    // pinned host memory: [n(>= 2 iterations last cycle), n(>= 15 lately)], written by k_order
     std::vector<double> h_params;  // host copy of set 0 (validation)
     std::vector<void*> allocs;
+    // multi-GPU result gather: packed [u0 (8) | status, iters (2 x int32)] per instance, double-buffered,
+    // all-gathered on a side stream so that no rank ever waits for another inside its control cycle
+    mpcc_ncclComm_t comm = nullptr;
+    int rank = 0, world = 0;                    // world == 0: no communicator
+    cudaStream_t gstream = nullptr;
+    cudaEvent_t ev_pack[2] = {nullptr, nullptr}, ev_gath[2] = {nullptr, nullptr};
+    double* d_stage[2] = {nullptr, nullptr};    // [B][9]
+    double* d_gath[2] = {nullptr, nullptr};     // [world][B][9]
+    double* h_gath = nullptr;                   // pinned, [world][B][9]
+    int gslot = 0, glast = -1;
+    bool gused[2] = {false, false};
     // grow-only device arena of the per-call probes / bindings (solveOCP at 100 Hz must not cudaMalloc per call)
     char* scratch = nullptr; size_t scratch_bytes = 0;
     cudaError_t need_scratch(size_t bytes) {
@@ -311,6 +367,15 @@ int mpcc_cuda_destroy(mpcc_cuda_handle* h) {
     for (cudaEvent_t e : h->ev) if (e) cudaEventDestroy(e);
     for (void* p : h->allocs) cudaFree(p);
     if (h->scratch) cudaFree(h->scratch);
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    for (int i = 0; i < 2; i++) {
+        if (h->d_stage[i]) cudaFree(h->d_stage[i]);
+        if (h->d_gath[i]) cudaFree(h->d_gath[i]);
+        if (h->ev_pack[i]) cudaEventDestroy(h->ev_pack[i]);
+        if (h->ev_gath[i]) cudaEventDestroy(h->ev_gath[i]);
+    }
+    if (h->h_gath) cudaFreeHost(h->h_gath);
+    if (h->gstream) cudaStreamDestroy(h->gstream);
     if (h->d_params) cudaFree(h->d_params);
     if (h->d_tracks) cudaFree(h->d_tracks);
     if (h->aux) cudaStreamDestroy(h->aux);
@@ -468,6 +533,66 @@ int mpcc_load_track_json(const char* track_path, const double* init_position3, d
     } catch (const std::exception& ex) {
         return fail(MPCC_ERR_IO, ex.what());
     }
+}
+
+// Track ingestion ON THE DEVICE for heterogeneous batches: waypoints of n_tracks tracks in, fitted tables installed
+// as the handle's tracks (same effect as mpcc_fit_tracks + mpcc_cuda_set_tracks, without the host fit).
+int mpcc_cuda_fit_tracks(mpcc_cuda_handle* h, int32_t n_tracks, int32_t n, const double* X, const double* Y, const double* Z, const double* R,
+                         const int32_t* track_of_instance) {
+    if (!h || !X || !Y || !Z || !R || n_tracks < 1) return fail(MPCC_ERR_INVALID, "bad argument");
+    if (n < 3 || n > 4096) return fail(MPCC_ERR_INVALID, "a track needs 3 .. 4096 waypoints");
+    std::vector<int32_t> ids(h->B, 0);
+    if (track_of_instance)
+        for (int b = 0; b < h->B; b++) {
+            if (track_of_instance[b] < 0 || track_of_instance[b] >= n_tracks) return fail(MPCC_ERR_INVALID, "track index out of range");
+            ids[b] = track_of_instance[b];
+        }
+    CK(cudaSetDevice(h->cfg.device));
+    if (h->d_tracks && h->n_tracks != n_tracks) { CK(cudaFree(h->d_tracks)); h->d_tracks = nullptr; }
+    if (!h->d_tracks) CK(cudaMalloc((void**)&h->d_tracks, (size_t)n_tracks * sizeof(TrackTable)));
+    const int chunk = n_tracks < 4096 ? n_tracks : 4096;
+    const size_t per = track_fit_scratch_doubles(n), wp = (size_t)chunk * n;
+    CK(h->need_scratch((12 * wp + per * chunk) * 8));
+    double* dX = (double*)h->scratch; double* dY = dX + wp; double* dZ = dY + wp; double* dR = dZ + wp; double* dS = dR + 9 * wp;
+    for (int t0 = 0; t0 < n_tracks; t0 += chunk) {
+        const int nt = (n_tracks - t0 < chunk) ? n_tracks - t0 : chunk;
+        const size_t o = (size_t)t0 * n, cnt = (size_t)nt * n;
+        CK(cudaMemcpyAsync(dX, X + o, cnt * 8, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(dY, Y + o, cnt * 8, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(dZ, Z + o, cnt * 8, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(dR, R + 9 * o, cnt * 72, cudaMemcpyHostToDevice, h->stream));
+        k_fit_tracks<<<(nt + 63) / 64, 64, 0, h->stream>>>(nt, n, dX, dY, dZ, dR, dS, h->d_tracks + t0);
+        CK(cudaGetLastError());
+    }
+    CK(cudaMemcpyAsync(h->d_track_id, ids.data(), ids.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    k_invalidate_warm<<<(h->B + 255) / 256, 256, 0, h->stream>>>(h->d_flags, h->B);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    h->n_tracks = n_tracks;
+    h->have_track = true;
+    if (h->hint) h->hint[0] = h->B;
+    return MPCC_OK;
+}
+
+int mpcc_cuda_get_tracks(mpcc_cuda_handle* h, double* tables_out, int32_t n_tracks) {
+    if (!h || !tables_out) return fail(MPCC_ERR_INVALID, "null argument");
+    if (!h->have_track) return fail(MPCC_ERR_STATE, "track not set");
+    if (n_tracks < 1 || n_tracks > h->n_tracks) return fail(MPCC_ERR_INVALID, "n_tracks out of range");
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaMemcpyAsync(tables_out, h->d_tracks, (size_t)n_tracks * sizeof(TrackTable), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return MPCC_OK;
+}
+
+// Table of an ALREADY FITTED ArcLengthSpline: its N_SPLINE = 100 knots (arc lengths, positions, rotations) in, no fit / resample
+// pass (the binding of SolverInterface::setTrack(ArcLengthSpline)): only the final regular spline
+// (arc_length_spline.cpp:244-252) is rebuilt from the knots.
+int mpcc_track_from_knots(const double* s, const double* X, const double* Y, const double* Z, const double* R, double* table_out) {
+    if (!s || !X || !Y || !Z || !R || !table_out) return fail(MPCC_ERR_INVALID, "null argument");
+    for (int i = 0; i + 1 < N_SPLINE; i++) if (!(s[i + 1] > s[i])) return fail(MPCC_ERR_INVALID, "knot arc lengths must increase strictly");
+    std::vector<double> w((size_t)14 * N_SPLINE);
+    tf_table_from_knots(TArr{(double*)s, 1}, TArr{(double*)X, 1}, TArr{(double*)Y, 1}, TArr{(double*)Z, 1}, TArr{(double*)R, 1}, TArr{w.data(), 1}, N_SPLINE, *(TrackTable*)table_out);
+    return MPCC_OK;
 }
 
 int mpcc_cuda_reset(mpcc_cuda_handle* h) {
@@ -858,6 +983,98 @@ int mpcc_cuda_read_decisions(mpcc_cuda_handle* h, int32_t* accept_mask) {
     CK(cudaStreamSynchronize(h->stream));
     return MPCC_OK;
 }
+
+// ---- multi-GPU: one process per GPU, one handle per process; the batch is sharded by the caller (instances are independent),
+// the only exchange is this gather of the per-instance results ----
+int mpcc_cuda_comm_unique_id(uint8_t* id128) {
+    if (!id128) return fail(MPCC_ERR_INVALID, "null argument");
+    std::string err;
+    if (!g_nccl.load(err)) return fail(MPCC_ERR_STATE, err);
+    mpcc_ncclUniqueId id;
+    const int rc = g_nccl.GetUniqueId(&id);
+    if (rc != 0) return fail(MPCC_ERR_CUDA, std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(rc));
+    std::memcpy(id128, id.internal, 128);
+    return MPCC_OK;
+}
+
+int mpcc_cuda_comm_init(mpcc_cuda_handle* h, const uint8_t* id128, int32_t rank, int32_t world) {
+    if (!h) return fail(MPCC_ERR_INVALID, "null handle");
+    if (world < 1 || rank < 0 || rank >= world) return fail(MPCC_ERR_INVALID, "rank / world out of range");
+    if (h->world != 0) return fail(MPCC_ERR_STATE, "communicator already initialised");
+    if (world > 1 && !id128) return fail(MPCC_ERR_INVALID, "unique id missing");
+    CK(cudaSetDevice(h->cfg.device));
+    if (world > 1) {
+        std::string err;
+        if (!g_nccl.load(err)) return fail(MPCC_ERR_STATE, err);
+        mpcc_ncclUniqueId id;
+        std::memcpy(id.internal, id128, 128);
+        const int rc = g_nccl.CommInitRank(&h->comm, world, id, rank);
+        if (rc != 0) return fail(MPCC_ERR_CUDA, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(rc));
+    }
+    const size_t rec = (size_t)h->B * 9;
+    CK(cudaStreamCreateWithFlags(&h->gstream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        CK(cudaEventCreateWithFlags(&h->ev_pack[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_gath[i], cudaEventDisableTiming));
+        CK(cudaMalloc((void**)&h->d_stage[i], rec * 8));
+        CK(cudaMalloc((void**)&h->d_gath[i], rec * 8 * world));
+    }
+    CK(cudaHostAlloc((void**)&h->h_gath, rec * 8 * world, cudaHostAllocPortable));
+    h->rank = rank; h->world = world;
+    return MPCC_OK;
+}
+
+int mpcc_cuda_gather_results(mpcc_cuda_handle* h) {
+    if (!h) return fail(MPCC_ERR_INVALID, "null handle");
+    if (h->world == 0) return fail(MPCC_ERR_STATE, "no communicator (mpcc_cuda_comm_init)");
+    CK(cudaSetDevice(h->cfg.device));
+    const int slot = h->gslot;
+    const size_t rec = (size_t)h->B * 9;
+    // the gather that read this staging slot two cycles ago must be through before the slot is rewritten (normally long done)
+    if (h->gused[slot]) CK(cudaStreamWaitEvent(h->stream, h->ev_gath[slot], 0));
+    k_pack_results<<<(unsigned)((rec + 255) / 256), 256, 0, h->stream>>>(h->d_u_out, h->d_status, h->d_iters, h->B, h->d_stage[slot]);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev_pack[slot], h->stream));
+    CK(cudaStreamWaitEvent(h->gstream, h->ev_pack[slot], 0));
+    if (h->world > 1) {
+        const int rc = g_nccl.AllGather(h->d_stage[slot], h->d_gath[slot], rec, 8 /* ncclDouble */, h->comm, h->gstream);
+        if (rc != 0) return fail(MPCC_ERR_CUDA, std::string("ncclAllGather: ") + g_nccl.GetErrorString(rc));
+    } else {
+        CK(cudaMemcpyAsync(h->d_gath[slot], h->d_stage[slot], rec * 8, cudaMemcpyDeviceToDevice, h->gstream));
+    }
+    CK(cudaEventRecord(h->ev_gath[slot], h->gstream));
+    h->gused[slot] = true; h->glast = slot; h->gslot ^= 1;
+    h->launches++;
+    return MPCC_OK;
+}
+
+int mpcc_cuda_read_gathered(mpcc_cuda_handle* h, double* u_all, int32_t* status_all, int32_t* iters_all) {
+    if (!h) return fail(MPCC_ERR_INVALID, "null handle");
+    if (h->glast < 0) return fail(MPCC_ERR_STATE, "nothing gathered yet (mpcc_cuda_gather_results)");
+    CK(cudaSetDevice(h->cfg.device));
+    const size_t n = (size_t)h->B * h->world;
+    CK(cudaMemcpyAsync(h->h_gath, h->d_gath[h->glast], n * 9 * 8, cudaMemcpyDeviceToHost, h->gstream));  // ordered behind the gather
+    CK(cudaStreamSynchronize(h->gstream));
+    for (size_t i = 0; i < n; i++) {
+        const double* r = h->h_gath + i * 9;
+        if (u_all) std::memcpy(u_all + i * 8, r, 64);
+        int32_t v[2];
+        std::memcpy(v, r + 8, 8);
+        if (status_all) status_all[i] = v[0];
+        if (iters_all) iters_all[i] = v[1];
+    }
+    return MPCC_OK;
+}
+
+int mpcc_cuda_gathered_pointer(mpcc_cuda_handle* h, double** d_packed, void** stream) {
+    if (!h || !d_packed) return fail(MPCC_ERR_INVALID, "null argument");
+    if (h->glast < 0) return fail(MPCC_ERR_STATE, "nothing gathered yet (mpcc_cuda_gather_results)");
+    *d_packed = h->d_gath[h->glast];
+    if (stream) *stream = (void*)h->gstream;
+    return MPCC_OK;
+}
+
+int64_t mpcc_cuda_launch_count(mpcc_cuda_handle* h) { return h ? h->launches : 0; }
 
 int mpcc_cuda_get_stats(mpcc_cuda_handle* h, int64_t* st) {
     if (!h || !st) return fail(MPCC_ERR_INVALID, "null argument");

@@ -72,6 +72,22 @@ void orc_mpc_destroy(void* m) { delete (MPC*)m; }
 void orc_mpc_set_params(void* mp, const double* model7, const double* cost12, const double* bounds48, const double* norm17, const double* sqp9) {
     fill_params((MPC*)mp, model7, cost12, bounds48, norm17, sqp9);
 }
+// MPC::setParam on a LIVE object (mpc.cpp:204-209 + OsqpInterface::setParam, osqp_interface.cpp:95-100):
+//   param_ = Param(file, pv.param); cost_ = Cost(path, pv); constraints_ = Constraints(Ts, path, pv);
+//   bounds_ = Bounds(BoundsParam(FILE), Param(file, pv.param));
+// normalization_param_, sqp_param_ and the interface's own cost_param_ (r_ddq) are NOT touched.  The caller passes
+// model7 / cost12 = file values with the pv.param / pv.cost overrides applied and bounds48 = the file's bounds.
+void orc_mpc_set_param_live(void* mp, const double* model7, const double* cost12, const double* bounds48_file) {
+    MPC* m = (MPC*)mp;
+    const NormParam n = m->solver.norm;
+    const SQPParam s = m->solver.sqp;
+    const double r_ddq = m->solver.r_ddq;
+    double norm17[NX + NU], sqp9[9] = {s.eps_prim, s.eps_dual, (double)s.max_iter, (double)s.line_search_max_iter, s.do_SOC ? 1. : 0., s.use_BFGS ? 1. : 0., s.tau, s.eta, s.rho};
+    for (int i = 0; i < NX; i++) norm17[i] = n.Tx[i];
+    for (int i = 0; i < NU; i++) norm17[NX + i] = n.Tu[i];
+    fill_params(m, model7, cost12, bounds48_file, norm17, sqp9);
+    m->solver.r_ddq = r_ddq;
+}
 void orc_mpc_set_qp_options(void* mp, int max_iter, double eps) { ((MPC*)mp)->solver.qp.max_iter = max_iter; ((MPC*)mp)->solver.qp.eps = eps; }
 
 void orc_mpc_set_track(void* mp, int n, const double* X, const double* Y, const double* Z, const double* R) {

@@ -162,6 +162,12 @@ class OracleMPC:
         p = params
         lib().orc_mpc_set_params(self.h, _p(p["model"]), _p(p["cost"]), _p(p["bounds"]), _p(p["norm"]), _p(p["sqp"]))
 
+    def set_param_live(self, param_value, param_dir=None):
+        """MPC::setParam(ParamValue) on a live controller with the reference's semantics (quirk 13): only the "param" (model)
+        and "cost" maps take effect; bounds come from the FILE; normalisation, SQP parameters and the interface's rddq stay."""
+        p = load_params(param_dir, overrides={"model": dict(param_value.get("param", {})), "cost": dict(param_value.get("cost", {}))})
+        lib().orc_mpc_set_param_live(self.h, _p(p["model"]), _p(p["cost"]), _p(p["bounds"]))
+
     def set_qp_options(self, max_iter=100, eps=1e-9):
         lib().orc_mpc_set_qp_options(self.h, max_iter, C.c_double(eps))
 

@@ -4,6 +4,7 @@
 #include "../../mpcc_manipulator_b200/csrc/dev_sqp.cuh"
 #include "../../mpcc_manipulator_b200/csrc/sqp_warp.cuh"
 #include "../../mpcc_manipulator_b200/csrc/host/track_fit.h"
+#include "../../mpcc_manipulator_b200/csrc/dev_track_fit.cuh"
 #include <cstring>
 #include <vector>
 
@@ -19,6 +20,15 @@ void emu_fit_track(int n, const double* X, const double* Y, const double* Z, con
     Waypoints w;
     w.X.assign(X, X + n); w.Y.assign(Y, Y + n); w.Z.assign(Z, Z + n); w.R.assign(R, R + 9 * n);
     fit_track(w, *(TrackTable*)table);
+}
+// the device track fit (dev_track_fit.cuh) compiled for the host; stride > 1 emulates the kernel's [element][track] scratch layout
+void emu_fit_track_device_code(int n, const double* X, const double* Y, const double* Z, const double* R, int stride, double* table) {
+    std::vector<double> ws(track_fit_scratch_doubles(n) * stride, -7.0);
+    tf_fit_track(n, TArr{(double*)X, 1}, TArr{(double*)Y, 1}, TArr{(double*)Z, 1}, TArr{(double*)R, 1}, TArr{ws.data() + (stride > 1 ? 1 : 0), (size_t)stride}, *(TrackTable*)table);
+}
+void emu_track_from_knots(const double* s, const double* X, const double* Y, const double* Z, const double* R, double* table) {
+    std::vector<double> w((size_t)14 * N_SPLINE);
+    tf_table_from_knots(TArr{(double*)s, 1}, TArr{(double*)X, 1}, TArr{(double*)Y, 1}, TArr{(double*)Z, 1}, TArr{(double*)R, 1}, TArr{w.data(), 1}, N_SPLINE, *(TrackTable*)table);
 }
 void emu_kin(const double* q, double* out62) {
     PandaKin k;

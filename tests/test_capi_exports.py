@@ -85,3 +85,47 @@ def test_bulk_track_fit_matches_single_fits():
     tabs = capi.fit_tracks(X, Y, Z, R, n_threads=4)
     for i in (0, 5, 36):
         assert np.array_equal(tabs[i], capi.fit_track(X[i], Y[i], Z[i], R[i]))
+
+
+def test_device_track_fit_code_matches_host_fit(O):
+    """csrc/dev_track_fit.cuh (the one-thread-per-track kernel's code) compiled for the host, contiguous and strided scratch
+    (the kernel's [element][track] layout), against the host fit that the oracle pins: tracks of the track.py family
+    (cpp/Params/track.py:5-22) with 5 .. 160 waypoints and varying orientation."""
+    import ctypes as C
+    from helpers import Emul, _p
+    emu = Emul()
+    rng = np.random.default_rng(1)
+    ee = O.fk(O.Q_HOME)[0]
+    worst = 0.0
+    for trial in range(12):
+        n = int(rng.integers(5, 160))
+        a, bb = rng.uniform(1.5, 3, 2); c = rng.uniform(0, 2.5)
+        t = np.linspace(np.pi / 2, 5 * np.pi / 2, n)
+        X, Y, Z = O.shift_track(a * 0.1 * np.sin(t), bb * 0.1 * np.sin(2 * t), c * 0.1 * np.cos(t), ee)
+        R = []
+        for i in range(n):
+            w = np.array([0.3 * np.sin(t[i]), 0.2 * np.cos(t[i]), 0.1 * t[i]]) * (trial % 2)
+            th = np.linalg.norm(w)
+            K = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+            E = np.eye(3) + (np.sin(th) / th * K + (1 - np.cos(th)) / th ** 2 * K @ K if th > 0 else 0)
+            R.append((np.diag([1., -1., -1.]) @ E).ravel())
+        R = np.array(R)
+        ref = emu.fit_track(X, Y, Z, R)
+        for stride in (1, 5):
+            out = np.zeros_like(ref)
+            emu.lib.emu_fit_track_device_code(n, _p(f64(X)), _p(f64(Y)), _p(f64(Z)), _p(f64(R)), stride, _p(out))
+            worst = max(worst, np.abs(out - ref).max() / np.abs(ref).max())
+    assert worst < 1e-12, worst
+
+
+def test_track_from_knots_reproduces_the_fitted_table(track_wp):
+    """mpcc_track_from_knots: the 100 knots of a fitted ArcLengthSpline give back the same table without re-fitting
+    (the binding of SolverInterface::setTrack(ArcLengthSpline), solver_interface.h:46)."""
+    from mpcc_manipulator_b200 import capi
+    t = capi.fit_track(*track_wp)
+    s, X, Y, Z = t[:100], t[100:200], t[200:300], t[300:400]      # knots s_i and the a-coefficients (= knot values) of X, Y, Z
+    R = t[1300:2200]
+    t2 = capi.track_from_knots(s, X, Y, Z, R)
+    assert np.abs(t2 - t).max() < 1e-13 * np.abs(t).max()
+    with pytest.raises(RuntimeError, match="increase"):
+        capi.track_from_knots(s[::-1].copy(), X, Y, Z, R)

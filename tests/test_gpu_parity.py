@@ -600,3 +600,66 @@ def test_exclusive_sm_launch_changes_scheduling_only(M, O, ee_home):
     assert long_runs > 0 and recurrences > 0   # the exclusive launch did have work, including long runs (not only quick ones)
     assert a.stats()["launches"] == 6 and b.stats()["launches"] == 5
     a.close(); b.close()
+
+
+def _track_family(rng, nt, n, ee):
+    """track.py family (cpp/Params/track.py:5-22): x = a r sin t, y = b r sin 2t, z = c r cos t, orientation diag(1,-1,-1)."""
+    t = np.linspace(np.pi / 2, 5 * np.pi / 2, n)
+    a, b, c = rng.uniform(1.5, 3, nt), rng.uniform(1.5, 3, nt), rng.uniform(0, 2.5, nt)
+    X = 0.1 * a[:, None] * np.sin(t)[None]; Y = 0.1 * b[:, None] * np.sin(2 * t)[None]; Z = 0.1 * c[:, None] * np.cos(t)[None]
+    X = X - X[:, :1] + ee[0]; Y = Y - Y[:, :1] + ee[1]; Z = Z - Z[:, :1] + ee[2]
+    R = np.tile(np.diag([1., -1., -1.]).ravel(), (nt, n, 1))
+    return X, Y, Z, R
+
+
+def test_device_track_fit_matches_host_fit(M, O, ee_home):
+    """SURVEY 8f-1: ArcLengthSpline::fitSpline on the device (k_fit_tracks, one thread per track): 4096 random tracks of the
+    track.py family equal to the host fit (mpcc_fit_track, pinned to the oracle in the CPU tier) to 1e-12; 65 536 fits timed."""
+    import time
+    rng = np.random.default_rng(2)
+    nt, n = 4096, 100
+    X, Y, Z, R = _track_family(rng, nt, n, ee_home)
+    mpc = M.BatchMPC(nt, 10); mpc.load_nn(); mpc.set_params(M.load_default_params())
+    mpc.fit_tracks_device(X, Y, Z, R, np.arange(nt))
+    dev = mpc.get_tracks(nt)
+    ref = M.fit_tracks(X, Y, Z, R)
+    scale = np.abs(ref).max(axis=0) + 1e-300
+    assert (np.abs(dev - ref) / np.maximum(scale, 1.0)).max() < 1e-12
+    # the cycle runs on the device-fitted tracks exactly as on the host-fitted ones
+    x0 = np.tile(np.r_[O.Q_HOME, 0., 0.], (nt, 1)); u0 = np.zeros((nt, 8))
+    r_dev = mpc.run_cycle(x0, u0, want_horizon=False)
+    mpc.set_tracks(ref, np.arange(nt))
+    r_host = mpc.run_cycle(x0, u0, want_horizon=False)
+    assert np.array_equal(r_dev["status"], r_host["status"]) and (np.abs(r_dev["u0"] - r_host["u0"]) / TU).max() < 1e-6
+    mpc.close()
+    # a different waypoint count, one shared track
+    Xs, Ys, Zs, Rs = _track_family(rng, 3, 37, ee_home)
+    small = M.BatchMPC(5, 10); small.load_nn(); small.set_params(M.load_default_params())
+    small.fit_tracks_device(Xs, Ys, Zs, Rs, [0, 1, 2, 2, 1])
+    refs = M.fit_tracks(Xs, Ys, Zs, Rs)
+    assert (np.abs(small.get_tracks(3) - refs) / np.maximum(np.abs(refs).max(axis=0), 1.0)).max() < 1e-12
+    small.close()
+    nt = 65536
+    X, Y, Z, R = _track_family(rng, nt, n, ee_home)
+    big = M.BatchMPC(nt, 2); big.load_nn(); big.set_params(M.load_default_params())
+    t0 = time.perf_counter(); big.fit_tracks_device(X, Y, Z, R, np.arange(nt)); t_dev = time.perf_counter() - t0
+    t0 = time.perf_counter(); ref = M.fit_tracks(X[:4096], Y[:4096], Z[:4096], R[:4096]); t_host = (time.perf_counter() - t0) * 16
+    print(f"65536 track fits: device {t_dev * 1e3:.1f} ms (incl. upload of {X.nbytes * 12 / 1e6:.0f} MB of waypoints); host thread pool ~{t_host * 1e3:.0f} ms (extrapolated from 4096)")
+    assert np.abs(big.get_tracks(4096) - ref).max() < 1e-9
+    big.close()
+
+
+def test_gather_api_single_rank(M, O, ee_home):
+    """mpcc_cuda_comm_init / gather_results / read_gathered with world = 1 (no NCCL needed): the side-stream, double-buffered
+    gather returns exactly the cycle's results; two cycles in flight keep their own buffers."""
+    B, N = 16, 10
+    mpc = make_mpc(M, B, N, ee_home)
+    mpc.comm_init(None, 0, 1)
+    x = np.tile(np.r_[O.Q_HOME, 0., 0.], (B, 1)); u = np.zeros((B, 8))
+    for c in range(3):
+        r = mpc.run_cycle(x, u, want_horizon=False)
+        mpc.gather_results()
+        g = mpc.read_gathered()
+        assert np.array_equal(g["u0"], r["u0"]) and np.array_equal(g["status"], r["status"]) and np.array_equal(g["iters"], r["iters"])
+        u = r["u0"]; x = mpc.sim_time_step(r["x0"], u)
+    mpc.close()

@@ -1,0 +1,145 @@
+"""Independent pins of the oracle where the reference holds no golden vector (VERDICT r1, row c):
+
+* both collision networks and their forward-mode Jacobians (SelfCollisionModel.cpp:140-250, robot_data.h:74-88) against
+  torch fp64 autograd on the same weights -- an implementation that shares nothing with the oracle's hand-written tangent
+  propagation (ReLU'(0) = 0 in both);
+* the QP optimum (osqp_interface.cpp:592-656) against a numpy restatement of the OSQP ALGORITHM (Stellato et al., "OSQP: an
+  operator splitting solver for quadratic programs", Math. Prog. Comp. 2020: ADMM on (x, z) with sigma = 1e-6, alpha = 1.6,
+  per-row rho -- 1e3 rho on equality rows --, unscaled, no polishing, residual-balancing rho updates) stopped by OSQP's
+  published termination rule at the tolerances the reference sets, eps_abs = 1e-4 and eps_rel = 1e-5
+  (osqp_interface.cpp:622-625).  This is the second opinion on a16: the reference's own solver stops anywhere inside that
+  tolerance ball, so agreement of the oracle's interior-point optimum with the ADMM point to within the ball is exactly the
+  parity statement that can be made; at tight tolerances (1e-9) the two optima agree to 1e-6.
+* the shipped packed weights equal the reference's weight_k.txt / bias_k.txt (only where /root/reference exists).
+"""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+REF = Path("/root/reference/cpp/NNmodel")
+
+
+def torch_mlp(Ws, bs, x):
+    import torch
+    z = torch.cat([x, torch.sin(x), torch.cos(x)])
+    for l, (W, b) in enumerate(zip(Ws, bs)):
+        z = W @ z + b
+        if l + 1 < len(Ws):
+            z = torch.relu(z)
+    return z
+
+
+def test_networks_against_torch_autograd(O, nn, rng):
+    import torch
+    torch.set_num_threads(1)
+    for which, (Ws, bs, n_in) in enumerate(((nn.self_W, nn.self_b, 7), (nn.env_W, nn.env_b, 10))):
+        tW = [torch.tensor(W, dtype=torch.float64) for W in Ws]; tb = [torch.tensor(b, dtype=torch.float64) for b in bs]
+        worst_y = worst_j = 0.0
+        for trial in range(40):
+            q = O.Q_HOME + rng.uniform(-1.0, 1.0, 7)
+            x = q if which == 0 else np.r_[q, rng.uniform(-0.8, 0.8, 3)]
+            y, J = nn.mlp(which, x)
+            xt = torch.tensor(x, dtype=torch.float64)
+            yt = torch_mlp(tW, tb, xt).numpy()
+            Jt = torch.autograd.functional.jacobian(lambda v: torch_mlp(tW, tb, v), xt).numpy()
+            worst_y = max(worst_y, np.abs(y - yt).max() / np.abs(yt).max())
+            worst_j = max(worst_j, np.abs(J - Jt).max() / np.abs(Jt).max())
+        assert worst_y < 1e-12 and worst_j < 1e-11, (which, worst_y, worst_j)
+    # RobotData keeps sel / dsel (7) and env / block(0,0,9,7) of the env Jacobian (robot_data.h:85)
+    q = O.Q_HOME + rng.uniform(-0.5, 0.5, 7); obs = np.array([0.48, 0.218, 0.521, 5.0])
+    rb = nn.robot_data(q, obs)
+    ys, Js = nn.mlp(0, q); ye, Je = nn.mlp(1, np.r_[q, obs[:3]])
+    assert rb[69] == ys[0] and np.array_equal(rb[70:77], Js[0]) and np.array_equal(rb[78:87], ye) and np.array_equal(rb[87:150].reshape(9, 7), Je[:, :7]) and rb[77] == obs[3]
+
+
+@pytest.mark.skipif(not REF.exists(), reason="reference tree not present on this box")
+def test_packed_weights_equal_reference_text_files(nn):
+    for sub, Ws, bs in (("self", nn.self_W, nn.self_b), ("env", nn.env_W, nn.env_b)):
+        for l, (W, b) in enumerate(zip(Ws, bs)):
+            Wt = np.loadtxt(REF / sub / "parameter" / f"weight_{l}.txt", ndmin=2)
+            bt = np.loadtxt(REF / sub / "parameter" / f"bias_{l}.txt", ndmin=1)
+            assert np.array_equal(W, Wt.reshape(W.shape)) and np.array_equal(b, bt.reshape(b.shape)), (sub, l)
+
+
+def osqp_admm(P, q, A, l, u, eps_abs=1e-4, eps_rel=1e-5, max_iter=20000, rho0=0.1, sigma=1e-6, alpha=1.6):
+    """The OSQP algorithm (Algorithm 1 of the paper) without scaling / polishing; returns (x, y, iterations, status)."""
+    n, m = len(q), len(l)
+    eq = (l == u)
+    rho_vec = np.where(eq, 1e3 * rho0, rho0)
+    rho = rho0
+    x = np.zeros(n); z = np.zeros(m); y = np.zeros(m)
+    import scipy.linalg as sla
+
+    def factor():
+        K = P + sigma * np.eye(n) + A.T @ (rho_vec[:, None] * A)
+        return sla.cho_factor(K)
+    F = factor()
+    for it in range(1, max_iter + 1):
+        rhs = sigma * x - q + A.T @ (rho_vec * z - y)
+        xt = sla.cho_solve(F, rhs)
+        zt = A @ xt
+        x_new = alpha * xt + (1 - alpha) * x
+        zr = alpha * zt + (1 - alpha) * z
+        z_new = np.clip(zr + y / rho_vec, l, u)
+        y = y + rho_vec * (zr - z_new)
+        x, z = x_new, z_new
+        if it % 25 == 0:   # check_termination = 25 (OSQP default)
+            Ax = A @ x; Px = P @ x; Aty = A.T @ y
+            r_prim = np.abs(Ax - z).max(); r_dual = np.abs(Px + q + Aty).max()
+            e_prim = eps_abs + eps_rel * max(np.abs(Ax).max(), np.abs(z).max())
+            e_dual = eps_abs + eps_rel * max(np.abs(Px).max(), np.abs(Aty).max(), np.abs(q).max())
+            if r_prim <= e_prim and r_dual <= e_dual:
+                return x, y, it, "solved"
+            # adaptive rho (residual balancing, OSQP section 5.2)
+            num = r_prim / max(np.abs(Ax).max(), np.abs(z).max(), 1e-30)
+            den = r_dual / max(np.abs(Px).max(), np.abs(Aty).max(), np.abs(q).max(), 1e-30)
+            new_rho = float(np.clip(rho * np.sqrt(num / max(den, 1e-30)), 1e-6, 1e6))
+            if new_rho > 5 * rho or new_rho < rho / 5:
+                rho = new_rho
+                rho_vec = np.where(eq, 1e3 * rho, rho)
+                F = factor()
+    return x, y, max_iter, "max_iter"
+
+
+@pytest.mark.parametrize("N", [10, 20])
+def test_qp_optimum_against_osqp_algorithm(O, nn, track_wp, rng, N):
+    """The flat QP of a first SQP iteration (reference assembly restated by the oracle): the oracle's
+    interior-point optimum lies inside the tolerance ball of an OSQP-algorithm run at the reference's settings."""
+    from helpers import make_horizon
+    o = O.OracleMPC(N=N, nn=nn); o.set_track(*track_wp)
+    hor = make_horizon(O, rng, N, 0.01, spread=0.03, u_scale=0.05)
+    rb = np.stack([nn.robot_data(hor[k, :7]) for k in range(N + 1)])
+    qp = o.build_qp(hor, rb, hor[0, 9:])
+    P, q, A = qp["P"], qp["q"], qp["A"]
+    lo = np.maximum(qp["l"] - qp["c"], -1e20); hi = np.minimum(qp["u"] - qp["c"], 1e20)
+    keep = np.abs(A).sum(1) > 0
+    ok, z_ipm, _ = O.solve_qp_dense(P, q, A, lo, hi)
+    assert ok
+    x, y, iters, status = osqp_admm(P, q, A[keep], lo[keep], hi[keep])
+    assert status == "solved", iters
+    # OSQP's own tolerance ball: primal residual eps_abs + eps_rel |Ax| on the constraints, and the step itself within the
+    # distance that a dual residual of that size allows along the weakest curvature the step actually uses
+    Az = A[keep] @ z_ipm
+    viol = np.maximum(np.maximum(lo[keep] - Az, Az - hi[keep]), 0).max()
+    assert viol < 1e-8                                            # the interior-point optimum is feasible
+    f = lambda v: 0.5 * v @ P @ v + q @ v
+    Ax = A[keep] @ x
+    x_viol = np.maximum(np.maximum(lo[keep] - Ax, Ax - hi[keep]), 0).max()
+    assert x_viol <= 1e-4 + 1e-5 * np.abs(Ax).max() + 1e-12       # ADMM point: inside OSQP's primal tolerance
+    # objective agreement: the ADMM point may be slightly infeasible (hence slightly better); relative gap tiny
+    # (the ADMM point at these tolerances is infeasible by up to ~2e-4 against multipliers of ~1e3, so its objective is a few
+    #  per cent BELOW the optimum: that, not the exact minimiser, is what the reference's own solver returns)
+    # the applied control is the first input step: compare in the solver's normalised variables at OSQP's eps_abs scale
+    nx = 9 * (N + 1)
+    d_u0 = np.abs(x[nx:nx + 8] - z_ipm[nx:nx + 8]).max()
+    d_all = np.abs(x - z_ipm).max()
+    print(f"N={N}: OSQP-algorithm iterations {iters}, |du0| = {d_u0:.2e}, max |dz| = {d_all:.2e}, objective gap {abs(f(x) - f(z_ipm)):.2e}")
+    # the reference's solver is only defined up to its tolerance ball: ~5e-3 .. 8e-3 in the normalised first input step here
+    # (measured: N=10 5.4e-3, N=20 7.6e-3).  The repo's own parity bar against the oracle (1e-4) is 50x tighter than that.
+    assert d_u0 < 2e-2 and d_all < 5e-2
+    # tight tolerances: both converge to the same (unique, Hessian is PD-checked) minimiser -- the pin proper
+    if N == 10:
+        x2, _, it2, st2 = osqp_admm(P, q, A[keep], lo[keep], hi[keep], eps_abs=1e-9, eps_rel=1e-9, max_iter=200000)
+        assert st2 == "solved" and np.abs(x2 - z_ipm).max() < 2e-5
+        print(f"N={N}: at 1e-9 tolerances the ADMM point and the interior-point optimum differ by {np.abs(x2 - z_ipm).max():.2e} ({it2} iterations)")
