@@ -39,3 +39,17 @@ def test_cpp_closed_loop_matches_golden():
         # state after the plant step of cycle c == golden input of cycle c + 1 (same closed loop, oracle side); filter ties
         # make later cycles branch-dependent, so only the progress along the path is compared loosely there
         assert abs(float(s) - g["x_in"][c + 1][7]) < (1e-4 if c == 0 else 5e-3), (c, s)
+
+
+def test_solver_interface_binding_compiles(tmp_path):
+    """The file a reference maintainer adds (examples/cuda_sqp_interface.h: a SolverInterface subclass over the C ABI,
+    INTEGRATION.md 1) compiles against a stand-in for the reference-side declarations (tests/stubs; Eigen is not in this image)
+    and links against libmpcc_b200.so: every entry point it binds exists with the signature it uses."""
+    src = tmp_path / "chk.cpp"
+    src.write_text('#include "cuda_sqp_interface.h"\n'
+                   'int main() { mpcc::PathToJson p; mpcc::SolverInterface* s = nullptr; if (false) { s = new mpcc::CudaSqpInterface(0.01, p); '
+                   'std::vector<mpcc::OptVariables> o; mpcc::Status st; mpcc::ComputeTime t; s->solveOCP(o, &st, &t); delete s; } return 0; }\n')
+    exe = tmp_path / "chk"
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Werror", "-I", str(ROOT / "tests" / "stubs"), "-I", str(ROOT / "include"), "-I", str(ROOT / "examples"),
+                           str(src), "-L", str(ROOT / "mpcc_manipulator_b200"), "-lmpcc_b200", f"-Wl,-rpath,{ROOT / 'mpcc_manipulator_b200'}", "-o", str(exe)])
+    assert subprocess.run([str(exe)]).returncode == 0
