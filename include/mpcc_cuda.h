@@ -63,7 +63,9 @@ typedef struct {
     int32_t qp_max_iter;  /* interior-point iteration cap of the structured QP solver (0 -> 60) */
     double qp_eps;        /* its residual tolerance (0 -> 1e-9) */
     int32_t sqp_kernel;   /* must be 0 (one SQP kernel ships: a warp per instance) */
-    int32_t reserved;     /* bit 0 (diagnostic): 1 = no exclusive-SM launch for recent long runners (scheduling only, same results) */
+    int32_t reserved;     /* diagnostics: bit 0 = no exclusive-SM launch for recent long runners (scheduling only, same results);
+                           * bit 1 = always the warp-per-instance SQP kernel, bit 2 = always the CTA-per-instance one
+                           * (default: CTA per instance when batch <= 2 x SMs -- the latency path --, else warp per instance) */
 } mpcc_cuda_config;
 
 typedef struct mpcc_cuda_handle mpcc_cuda_handle;

@@ -44,4 +44,13 @@ void launch_sqp_warp(const CycleArgs& a, double* wws, cudaStream_t s, cudaStream
 void launch_solve_ocp_warp(const CycleArgs& a, double* wws, double* guess, const double* rb, const double* cur_u, int n, double* steps, double* alphas,
                            int32_t* qp_ok, int max_log, int32_t* n_logged, cudaStream_t s);
 
+// track ingestion on the device, one thread per track (k_track_fit.cu); scratch: track_fit_scratch_doubles(n) * n_tracks doubles
+void launch_fit_tracks(int n_tracks, int n, const double* X, const double* Y, const double* Z, const double* R, double* scratch, TrackTable* out, cudaStream_t s);
+// one CTA (128 lanes) per instance: the latency path (k_sqp_cta.cu)
+size_t sqp_cta_smem_bytes(int N);
+cudaError_t configure_sqp_cta();
+void launch_sqp_cta(const CycleArgs& a, double* wws, cudaStream_t s);
+void launch_solve_ocp_cta(const CycleArgs& a, double* wws, double* guess, const double* rb, const double* cur_u, int n, double* steps, double* alphas,
+                          int32_t* qp_ok, int max_log, int32_t* n_logged, cudaStream_t s);
+
 }  // namespace mpcc

@@ -1,6 +1,6 @@
 // Warp-per-instance SQP kernels (default): see sqp_warp.cuh.
 #include "cycle_args.h"
-#include "sqp_warp.cuh"
+#include "sqp_cycle.cuh"
 #include <cstdlib>
 
 namespace mpcc {
@@ -55,43 +55,7 @@ __device__ __forceinline__ void sqp_warp_cycle(const CycleArgs& a, double* wws, 
         const int n_excl = min(a.order[a.B], SQPW_EXCL_CTAS * SQPW_WARPS);
         if ((excl == 1) != (slot < n_excl)) return;
     }
-    const int b = a.order[slot];
-    const Params& P = a.params[a.params_per_instance ? b : 0];
-    const TrackTable& T = a.tracks[a.track_id[b]];
-    const size_t B = (size_t)a.B, NS = B * a.S;
-    const int HN = a.S * HZ;
-    WarpSqp w{P, T, make_dyn(P, a.Ts), a.Ts, a.N, a.S, a.qp, Warp{lane}};
-    w.carve(wws + (size_t)b * ws_per, sqpw_smem + (size_t)wid * sm_per);
-    for (int e = lane; e < HN; e += 32) w.GUESS[e] = a.warm[(size_t)e * B + b];
-    __syncwarp();
-    double cur_u[NU], x0[NX];
-    for (int i = 0; i < NU; i++) cur_u[i] = a.u0[b * NU + i];
-    for (int i = 0; i < NX; i++) x0[i] = a.x0[b * NX + i];
-    long long t0, t1;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    SqpResult r = w.run(cur_u, a.rb + (size_t)b * a.S, NS, 1, nullptr);
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-    // epilogue of runMPC_ (mpc.cpp:140-188)
-    WarmFlags fl = a.flags[b];
-    if (r.status == SOLVED) { fl.valid = 1; fl.failed = 0; }
-    else {
-        for (int e = lane; e < HN; e += 32) { const int rr = e % HZ; w.GUESS[e] = (rr < NX) ? x0[0] : 0.0; }
-        __syncwarp();
-        for (int k = lane; k < a.S; k += 32) for (int m = 0; m < NX; m++) w.GUESS[k * HZ + m] = x0[m];
-        fl.valid = 0; fl.failed++;
-    }
-    __syncwarp();
-    const bool ok = r.status == SOLVED || (r.status == MAX_ITER_EXCEEDED && fl.failed < 5);
-    double* h = a.horizon + (size_t)b * HN;
-    for (int e = lane; e < HN; e += 32) { const double v = w.GUESS[e]; a.warm[(size_t)e * B + b] = v; h[e] = v; }
-    if (lane < NU) a.u_out[b * NU + lane] = w.GUESS[NX + lane];
-    if (lane == 0) {
-        a.flags[b] = fl;
-        a.status[b] = r.status; a.iters[b] = r.iters; a.ok[b] = ok ? 1 : 0; a.qp_iters[b] = r.qp_iters; a.qp_fail[b] = r.qp_fail;
-        a.accept_mask[b] = (int32_t)r.accept_mask;
-        a.hist[b] = (int32_t)(((unsigned)a.hist[b] << 8) | (unsigned)min(r.iters, 255));
-        a.sqp_ns[4 * b] = t1 - t0; a.sqp_ns[4 * b + 1] = (long long)w.tm_set_qp; a.sqp_ns[4 * b + 2] = (long long)w.tm_solve_qp; a.sqp_ns[4 * b + 3] = (long long)w.tm_get_alpha;
-    }
+    sqp_group_cycle<32>(a, wws, ws_per, sqpw_smem + (size_t)wid * sm_per, a.order[slot], lane);
 }
 // Two builds of the same code.  k_sqp_warp: 5 CTAs per SM (168 registers, 2.8 KB of spills) -- a steady-state batch (every
 // instance one QP) wants resident warps: 5.0 ms against 5.45.  k_sqp_warp_r255: the full register file (255 registers, 0.8 KB
@@ -106,19 +70,7 @@ __global__ void SQPW_BOUNDS k_solve_ocp_warp(CycleArgs a, double* wws, size_t ws
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * SQPW_WARPS + wid;
     if (b >= n) return;
-    const Params& P = a.params[a.params_per_instance ? b : 0];
-    const TrackTable& T = a.tracks[a.track_id[b]];
-    const int HN = a.S * HZ;
-    WarpSqp w{P, T, make_dyn(P, a.Ts), a.Ts, a.N, a.S, a.qp, Warp{lane}};
-    w.carve(wws + (size_t)b * ws_per, sqpw_smem + (size_t)wid * sm_per);
-    for (int e = lane; e < HN; e += 32) w.GUESS[e] = guess[(size_t)b * HN + e];
-    __syncwarp();
-    double cur_u[NU];
-    for (int i = 0; i < NU; i++) cur_u[i] = cur_u_all[b * NU + i];
-    SqpLogRef lg{steps ? steps + (size_t)b * max_log * HN : nullptr, alphas + (size_t)b * max_log, qp_ok + (size_t)b * max_log, max_log, 0};
-    SqpResult r = w.run(cur_u, rb + (size_t)b * a.S * RB_DOUBLES, 1, RB_DOUBLES, max_log > 0 ? &lg : nullptr);
-    for (int e = lane; e < HN; e += 32) guess[(size_t)b * HN + e] = w.GUESS[e];
-    if (lane == 0) { a.status[b] = r.status; a.iters[b] = r.iters; n_logged[b] = lg.n; }
+    solve_ocp_group<32>(a, wws, ws_per, sqpw_smem + (size_t)wid * sm_per, b, lane, guess, rb, cur_u_all, steps, alphas, qp_ok, max_log, n_logged);
 }
 
 

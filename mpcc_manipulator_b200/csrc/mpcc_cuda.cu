@@ -152,14 +152,6 @@ __global__ void k_pack_results(const double* __restrict__ u_out, const int32_t* 
     if (e < 8) out[i] = u_out[b * 8 + e];
     else { int2 v = make_int2(status[b], iters[b]); out[i] = *reinterpret_cast<double*>(&v); }
 }
-// ArcLengthSpline::fitSpline for a chunk of tracks, one thread per track (dev_track_fit.cuh)
-__global__ void k_fit_tracks(int n_tracks, int n, const double* __restrict__ X, const double* __restrict__ Y, const double* __restrict__ Z,
-                             const double* __restrict__ R, double* scratch, TrackTable* out) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_tracks) return;
-    const size_t o = (size_t)t * n;
-    tf_fit_track(n, TArr{(double*)X + o, 1}, TArr{(double*)Y + o, 1}, TArr{(double*)Z + o, 1}, TArr{(double*)R + 9 * o, 1}, TArr{scratch + t, (size_t)n_tracks}, out[t]);
-}
 __global__ void k_invalidate_warm(WarmFlags* fl, int B) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b < B) fl[b].valid = 0;
@@ -221,6 +213,7 @@ struct mpcc_cuda_handle {
     double *d_wpack = nullptr, *d_bias = nullptr, *d_w_out_env = nullptr, *d_w_out_self = nullptr;
     int64_t launches = 0;
     bool profiling = false;
+    bool use_cta = false;   // SQP kernel family of this handle: k_sqp_cta (one CTA per instance) or k_sqp_warp
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // prologue | kin | mlp | sqp boundaries
     cudaStream_t aux = nullptr;                 // high-priority stream of the exclusive-SM straggler launch
     cudaEvent_t ev_pre = nullptr, ev_order = nullptr, ev_aux = nullptr;
@@ -356,6 +349,9 @@ static int create_impl(mpcc_cuda_handle* h, const mpcc_cuda_config* cfg) {
     CK(cudaMemcpyAsync(h->d_obs_dummy, dummy.data(), dummy.size() * 8, cudaMemcpyHostToDevice, h->stream));
     CK(cudaFuncSetAttribute(k_mlp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_SMEM_BYTES));
     CK(configure_sqp_warp(h->N));
+    CK(configure_sqp_cta());
+    // kernel family: one CTA per instance (latency path) when the batch cannot fill the machine with warps anyway
+    h->use_cta = (h->cfg.reserved & 4) ? true : (h->cfg.reserved & 2) ? false : (h->B <= 2 * h->num_sms);
     CK(cudaStreamSynchronize(h->stream));
     return MPCC_OK;
 }
@@ -561,7 +557,7 @@ int mpcc_cuda_fit_tracks(mpcc_cuda_handle* h, int32_t n_tracks, int32_t n, const
         CK(cudaMemcpyAsync(dY, Y + o, cnt * 8, cudaMemcpyHostToDevice, h->stream));
         CK(cudaMemcpyAsync(dZ, Z + o, cnt * 8, cudaMemcpyHostToDevice, h->stream));
         CK(cudaMemcpyAsync(dR, R + 9 * o, cnt * 72, cudaMemcpyHostToDevice, h->stream));
-        k_fit_tracks<<<(nt + 63) / 64, 64, 0, h->stream>>>(nt, n, dX, dY, dZ, dR, dS, h->d_tracks + t0);
+        launch_fit_tracks(nt, n, dX, dY, dZ, dR, dS, h->d_tracks + t0, h->stream);
         CK(cudaGetLastError());
     }
     CK(cudaMemcpyAsync(h->d_track_id, ids.data(), ids.size() * 4, cudaMemcpyHostToDevice, h->stream));
@@ -644,8 +640,11 @@ int mpcc_cuda_run_cycle_device(mpcc_cuda_handle* h, double* d_x0, const double* 
     rc = launch_robot_data(h, obs, h->S, prof);
     if (rc) return rc;
     if (prof) cudaEventRecord(h->ev[3], h->stream);
-    launch_sqp_warp(a, h->d_wws, h->stream, (h->cfg.reserved & 1) ? nullptr : h->aux, h->ev_pre, h->ev_order, h->ev_aux, h->hint);
-    h->launches += (h->cfg.reserved & 1) ? 1 : 2;  // + the launch-order kernel (+ the exclusive launch)
+    if (h->use_cta) launch_sqp_cta(a, h->d_wws, h->stream);
+    else {
+        launch_sqp_warp(a, h->d_wws, h->stream, (h->cfg.reserved & 1) ? nullptr : h->aux, h->ev_pre, h->ev_order, h->ev_aux, h->hint);
+        h->launches += (h->cfg.reserved & 1) ? 1 : 2;  // + the launch-order kernel (+ the exclusive launch)
+    }
     h->launches++;
     if (prof) cudaEventRecord(h->ev[4], h->stream);
     CK(cudaGetLastError());
@@ -849,7 +848,8 @@ int mpcc_cuda_solve_ocp(mpcc_cuda_handle* h, double* guess, const double* rb, co
     CK(cudaMemcpyAsync(d_cu, cur_u, (size_t)n * NU * 8, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemsetAsync(d_nl, 0, (size_t)n * 4, h->stream));
     CycleArgs a = make_args(h, h->d_x0, h->d_u0, h->d_obs_dummy);
-    launch_solve_ocp_warp(a, h->d_wws, d_g, d_rb, d_cu, n, d_steps, d_alphas, d_qpok, max_log, d_nl, h->stream);
+    if (h->use_cta) launch_solve_ocp_cta(a, h->d_wws, d_g, d_rb, d_cu, n, d_steps, d_alphas, d_qpok, max_log, d_nl, h->stream);
+    else launch_solve_ocp_warp(a, h->d_wws, d_g, d_rb, d_cu, n, d_steps, d_alphas, d_qpok, max_log, d_nl, h->stream);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(guess, d_g, n * HN * 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(status, h->d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));

@@ -55,23 +55,39 @@ static __device__ __noinline__ double warp_all_sum(double v) {
     return v;
 }
 #endif
-struct Warp {
+// NL lanes working in lock step on one instance: a warp (NL = 32, the throughput kernel: one warp per instance, many
+// instances per SM) or a whole CTA (NL = 128, the latency kernel: one CTA per instance, for batches that do not fill the
+// machine).  Phases end with the group's barrier (__syncwarp / __syncthreads).
+template <int NL>
+struct Lanes {
+    static_assert(NL % 32 == 0 && NL >= 32, "whole warps");
 #if defined(__CUDA_ARCH__)
     int lane;
-    template <class F> __device__ __forceinline__ void each(F f) const { f(lane); __syncwarp(); }
-    template <class F> __device__ __forceinline__ double rmax(F f) const { const double v = warp_all_max(f(lane)); __syncwarp(); return v; }
-    template <class F> __device__ __forceinline__ double rmin(F f) const { const double v = warp_all_min(f(lane)); __syncwarp(); return v; }
-    template <class F> __device__ __forceinline__ double rsum(F f) const { const double v = warp_all_sum(f(lane)); __syncwarp(); return v; }
-    template <class F> __device__ __forceinline__ bool any(F f) const {
-        bool r = __any_sync(0xffffffffu, f(lane));
-        __syncwarp();
+    double* red;  // NL > 32: 2 * (NL / 32) doubles of shared memory for the cross-warp step of the reductions
+    __device__ __forceinline__ void sync() const { if (NL == 32) __syncwarp(); else __syncthreads(); }
+    template <class Op> __device__ __forceinline__ double across(double v, Op op) const {
+        if (NL == 32) { __syncwarp(); return v; }
+        if ((lane & 31) == 0) red[lane >> 5] = v;
+        __syncthreads();
+        double r = red[0];
+#pragma unroll
+        for (int w = 1; w < NL / 32; w++) r = op(r, red[w]);
+        __syncthreads();
         return r;
+    }
+    template <class F> __device__ __forceinline__ void each(F f) const { f(lane); sync(); }
+    template <class F> __device__ __forceinline__ double rmax(F f) const { return across(warp_all_max(f(lane)), [](double a, double b) { return fmax(a, b); }); }
+    template <class F> __device__ __forceinline__ double rmin(F f) const { return across(warp_all_min(f(lane)), [](double a, double b) { return fmin(a, b); }); }
+    template <class F> __device__ __forceinline__ double rsum(F f) const { return across(warp_all_sum(f(lane)), [](double a, double b) { return a + b; }); }
+    template <class F> __device__ __forceinline__ bool any(F f) const {
+        if (NL == 32) { const bool r = __any_sync(0xffffffffu, f(lane)); __syncwarp(); return r; }
+        return __syncthreads_or(f(lane) ? 1 : 0) != 0;
     }
 #else
     bool reverse = false;
     template <class F> void each(F f) const {
-        if (!reverse) for (int l = 0; l < 32; l++) f(l);
-        else for (int l = 31; l >= 0; l--) f(l);
+        if (!reverse) for (int l = 0; l < NL; l++) f(l);
+        else for (int l = NL - 1; l >= 0; l--) f(l);
     }
     template <class F> double rmax(F f) const { double v = -INFINITY; each([&](int l) { v = fmax(v, f(l)); }); return v; }
     template <class F> double rmin(F f) const { double v = INFINITY; each([&](int l) { v = fmin(v, f(l)); }); return v; }
@@ -79,6 +95,7 @@ struct Warp {
     template <class F> bool any(F f) const { bool v = false; each([&](int l) { v = f(l) || v; }); return v; }
 #endif
 };
+using Warp = Lanes<32>;
 
 // The interior-point iteration is bound by instruction fetch, not issue (ncu: stall_no_instruction dominates with ten
 // warps per SM in different phases of ~100 KB of code): lane-strided loops of the QP path stay rolled.
@@ -162,6 +179,10 @@ MPCC_HD size_t warp_smem_extra(int N) {
     return ((25 * (N + 1) <= SC_VEC - SW_GK) ? 0 : (size_t)25 * (N + 1)) + ((HZ * (N + 1) <= XG_ROOM) ? 0 : (size_t)HZ * (N + 1));
 }
 MPCC_HD size_t warp_smem_doubles(int N) { return ((size_t)2 * (N + 1) * HZ + SC_SIZE + warp_smem_extra(N) + 1) & ~(size_t)1; }
+// a group of NL > 32 lanes has its own tile ring (three slots of 19 NL doubles: five vectors of NL polytopic rows and their
+// 14 NL coefficients), 5 NL per-lane accumulators and the cross-warp reduction cells behind the warp layout
+template <int NL>
+MPCC_HD size_t group_smem_doubles(int N) { return warp_smem_doubles(N) + (NL > 32 ? (size_t)(3 * 19 * NL + 5 * NL + 2 * (NL / 32) + 2) : (size_t)0); }
 
 // isPosdef / isNan of one packed-lower 9 x 9 Hessian block, fully unrolled (static indices: registers).
 // pd is cleared at the first non-positive pivot unless that pivot is NaN (NaN is reported through `nan`).
@@ -188,18 +209,20 @@ MPCC_HD void block9_pd_nan(const double* Qp, bool& pd, bool& nan) {
     }
 }
 
-struct WarpSqp {
+template <int NL>
+struct GroupSqp {
+    static constexpr int TS1 = 3 * NL, TS2 = NL;   // tile sizes of the streamed per-constraint passes (box + rate rows | polytopic rows)
     const Params& P;
     const TrackTable& T;
     DynConst dyn;
     double Ts;
     int N, S;
     QpOptions opt;
-    Warp W;
+    Lanes<NL> W;
     // per-instance global workspace
     double *LIN, *CST, *IT, *ILAM, *IRP, *IW, *IV, *IDT, *IDLAM, *IH, *G, *KAP, *FACT, *SSTEP, *GUESS, *RBFV, *FILT;
-    // per-warp shared memory
-    double *VAR, *STEP, *SC;
+    // per-instance shared memory
+    double *VAR, *STEP, *SC, *RING, *RED_;
     // working copies between QP solves: the iterate (in the scratch) and the persistent step (in STEP); their homes
     // GUESS / SSTEP in the global workspace are written before and re-read after every executed QP solve
     double *XG, *XS;
@@ -226,6 +249,11 @@ struct WarpSqp {
         // FACT and G on even offsets (16-byte copies)
         FACT = gws; gws += S_ * WF_SIZE; G = gws; gws += S_ * HZ; KAP = gws; gws += S_ * 8; SSTEP = gws; gws += S_ * HZ; GUESS = gws; gws += S_ * HZ; RBFV = gws; gws += S_ * 2 * NPOLY; FILT = gws;
         VAR = sm; STEP = sm + S_ * HZ; SC = sm + 2 * S_ * HZ;
+        if (NL == 32) { RING = SC; RED_ = SC + SC_RED; }   // the tile ring shares the (idle) factorisation scratch
+        else { RING = sm + warp_smem_doubles(N); RED_ = RING + 3 * 19 * NL; }
+#if defined(__CUDA_ARCH__)
+        W.red = RED_ + 5 * NL;
+#endif
         OR_ = 18 * S; OP_ = 32 * S;
         XG = (HZ * S <= XG_ROOM) ? SC : SC + SC_SIZE;
         XS = STEP;
@@ -270,11 +298,11 @@ struct WarpSqp {
     // f(i, gz, h) for every PRESENT constraint (i = index into the per-constraint vectors), on vector Z
     template <class F>
     MPCC_HD void for_present(int lane, const double* Z, bool need_h, F f) const {
-        for (int i = 18 + lane; i < 18 * S; i += 32) { const int k = i / 18, c = i - k * 18; f(i, gz_box(Z, k, c), need_h ? h_box(k, c) : 0.0); }
+        for (int i = 18 + lane; i < 18 * S; i += NL) { const int k = i / 18, c = i - k * 18; f(i, gz_box(Z, k, c), need_h ? h_box(k, c) : 0.0); }
         MPCC_ROLLED
-        for (int i = lane; i < 14 * N; i += 32) { const int k = i / 14, c = i - k * 14; f(OR_ + i, gz_rate(Z, k, c), need_h ? h_rate(k, c) : 0.0); }
+        for (int i = lane; i < 14 * N; i += NL) { const int k = i / 14, c = i - k * 14; f(OR_ + i, gz_rate(Z, k, c), need_h ? h_rate(k, c) : 0.0); }
         MPCC_ROLLED
-        for (int i = lane; i < NPOLY * N; i += 32) { const int k = i / NPOLY, j = i - k * NPOLY; f(OP_ + i, gz_poly(Z, k, j), need_h ? h_poly(k, j) : 0.0); }
+        for (int i = lane; i < NPOLY * N; i += NL) { const int k = i / NPOLY, j = i - k * NPOLY; f(OP_ + i, gz_poly(Z, k, j), need_h ? h_poly(k, j) : 0.0); }
     }
 
     // Same traversal, four rounds at a time: f4(idx[4], gz[4], h[4]) gets four items of one lane (idx < 0: none) so that it
@@ -282,30 +310,30 @@ struct WarpSqp {
     template <class F4>
     MPCC_HD void for_present4(int lane, const double* Z, bool need_h, F4 f4) const {
         int idx[4]; double g[4], h[4];
-        for (int base = 18 + lane; base < 18 * S; base += 128) {
+        for (int base = 18 + lane; base < 18 * S; base += 4 * NL) {
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                const int i = base + 32 * u;
+                const int i = base + NL * u;
                 idx[u] = (i < 18 * S) ? i : -1; g[u] = 0; h[u] = 0;
                 if (i < 18 * S) { const int k = i / 18, c = i - k * 18; g[u] = gz_box(Z, k, c); if (need_h) h[u] = h_box(k, c); }
             }
             f4(idx, g, h);
         }
         MPCC_ROLLED
-        for (int base = lane; base < 14 * N; base += 128) {
+        for (int base = lane; base < 14 * N; base += 4 * NL) {
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                const int i = base + 32 * u;
+                const int i = base + NL * u;
                 idx[u] = (i < 14 * N) ? OR_ + i : -1; g[u] = 0; h[u] = 0;
                 if (i < 14 * N) { const int k = i / 14, c = i - k * 14; g[u] = gz_rate(Z, k, c); if (need_h) h[u] = h_rate(k, c); }
             }
             f4(idx, g, h);
         }
         MPCC_ROLLED
-        for (int base = lane; base < NPOLY * N; base += 128) {
+        for (int base = lane; base < NPOLY * N; base += 4 * NL) {
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                const int i = base + 32 * u;
+                const int i = base + NL * u;
                 idx[u] = (i < NPOLY * N) ? OP_ + i : -1; g[u] = 0; h[u] = 0;
                 if (i < NPOLY * N) { const int k = i / NPOLY, j = i - k * NPOLY; g[u] = gz_poly(Z, k, j); if (need_h) h[u] = h_poly(k, j); }
             }
@@ -329,8 +357,8 @@ struct WarpSqp {
     struct TileGeom { int base, cnt, ts, rows; };
     MPCC_HD TileGeom tile_geom(int t, int nt1) const {
         TileGeom g;
-        if (t < nt1) { g.base = 18 + 96 * t; g.ts = 96; g.rows = 0; const int end = OR_ + 14 * N; g.cnt = (end - g.base < 96) ? end - g.base : 96; }
-        else { g.base = OP_ + 32 * (t - nt1); g.ts = 32; g.rows = 1; const int end = OP_ + NPOLY * N; g.cnt = (end - g.base < 32) ? end - g.base : 32; }
+        if (t < nt1) { g.base = 18 + TS1 * t; g.ts = TS1; g.rows = 0; const int end = OR_ + 14 * N; g.cnt = (end - g.base < TS1) ? end - g.base : TS1; }
+        else { g.base = OP_ + TS2 * (t - nt1); g.ts = TS2; g.rows = 1; const int end = OP_ + NPOLY * N; g.cnt = (end - g.base < TS2) ? end - g.base : TS2; }
         return g;
     }
     static MPCC_HDNI void issue_tile(int lane, const double* vec0, size_t vec_stride, const double* cst, int op, double* dst, unsigned ids, int na,
@@ -339,27 +367,27 @@ struct WarpSqp {
         // constraints = 48 pairs per vector (two predicated copies per lane, no loop: ~6 instructions per copy instead of
         // ~18 per loop round) and 32 x 14 coefficient doubles = 224 pairs (seven)
         const int half = (cnt + 1) >> 1;
-        const bool c0 = lane < half, c1 = lane + 32 < half;
+        const bool c0 = lane < half, c1 = lane + NL < half;
         MPCC_ROLLED
         for (int a = 0; a < na; a++) {
             const double* src = vec0 + (size_t)((ids >> (3 * a)) & 7u) * vec_stride + base + 2 * lane;
             double* d = dst + a * ts + 2 * lane;
             if (c0) async_copy16(d, src);
-            if (c1) async_copy16(d + 64, src + 64);
+            if (c1) async_copy16(d + 2 * NL, src + 2 * NL);
         }
         if (rows) {
             const double* src = cst + (size_t)(base - op) * 14 + 2 * lane;
             double* d = dst + na * ts + 2 * lane;
             const int n2 = cnt * 7 - lane;
 #pragma unroll
-            for (int r = 0; r < 7; r++) if (32 * r < n2) async_copy16(d + 64 * r, src + 64 * r);
+            for (int r = 0; r < 7; r++) if (NL * r < n2) async_copy16(d + 2 * NL * r, src + 2 * NL * r);
         }
     }
     template <class F>
     MPCC_HD void stream_constraints(unsigned ids, int na, F body) const {
-        const int nt1 = (OR_ + 14 * N - 18 + 95) / 96, nt = nt1 + (NPOLY * N + 31) / 32;
-        const int s1 = na * 96, s2 = na * 32 + 32 * 14, slot = (s1 > s2) ? s1 : s2;  // <= 608 for na <= 5: three slots stay below SC_TXU
-        double* ring = SC;
+        const int nt1 = (OR_ + 14 * N - 18 + TS1 - 1) / TS1, nt = nt1 + (NPOLY * N + TS2 - 1) / TS2;
+        const int s1 = na * TS1, s2 = na * TS2 + TS2 * 14, slot = (s1 > s2) ? s1 : s2;  // NL = 32: <= 608 for na <= 5, three slots stay below SC_TXU
+        double* ring = RING;
         const size_t vstride = cvec_stride(N);
         auto issue = [&](int lane, int t) {
             if (t < nt) {
@@ -375,7 +403,7 @@ struct WarpSqp {
                 const double* v = ring + (t % 3) * slot;
                 const TileGeom g = tile_geom(t, nt1);
                 MPCC_ROLLED
-                for (int j = lane; j < g.cnt; j += 32) {
+                for (int j = lane; j < g.cnt; j += NL) {
                     const int i = g.base + j;
                     int kind, k, c;
                     if (g.rows) { kind = 2; k = (i - OP_) / NPOLY; c = (i - OP_) - k * NPOLY; }
@@ -404,7 +432,7 @@ struct WarpSqp {
     MPCC_HD void gradient(double* dst0, bool cost = true) const {
         W.each([&](int lane) {
             MPCC_ROLLED
-            for (int o = lane; o < NX * S; o += 32) {
+            for (int o = lane; o < NX * S; o += NL) {
                 const int k = o / NX, r = o - k * NX;
                 const double* L = LIN + (size_t)k * WL_SIZE;
                 const double* z = VAR + k * HZ;
@@ -429,7 +457,7 @@ struct WarpSqp {
                 if (dst0) dst0[k * HZ + r] = base + sl;
             }
             MPCC_ROLLED
-            for (int o = lane; o < NU * N; o += 32) {
+            for (int o = lane; o < NU * N; o += NL) {
                 const int k = o / NU, j = o - k * NU;
                 const double* L = LIN + (size_t)k * WL_SIZE;
                 const double* z = VAR + k * HZ + NX;
@@ -471,7 +499,7 @@ struct WarpSqp {
         return W.rmax([&](int lane) {
             double nr = 0;
             MPCC_ROLLED
-            for (int o = lane; o < NU * N; o += 32) {
+            for (int o = lane; o < NU * N; o += NL) {
                 const int k = o / NU, j = o - k * NU;
                 const double* pn = STEP + (k + 1) * HZ;
                 const double btp = (j < 7) ? d_bq(j) * pn[j] : d_bs() * pn[7] + d_bv() * pn[8];
@@ -488,23 +516,23 @@ struct WarpSqp {
     // The diverging multipliers of an interior-point run on an infeasible QP converge to such a ray.  Tested only on
     // iterations that follow a short step (the hot path never gets here); tolerance eps_inf relative to |lam|_inf.
     MPCC_HDNI bool primal_infeasible(double eps_inf) const {
-        double* RED = SC + SC_RED;
-        W.each([&](int lane) { RED[lane] = 0.0; RED[32 + lane] = 0.0; });
+        double* RED = RED_;
+        W.each([&](int lane) { RED[lane] = 0.0; RED[NL + lane] = 0.0; });
         stream_constraints(vec_ids(CV_LAM, CV_H), 2, [&](int lane, int, int kind, int, int, const double* v, int j, const double*) {
-            const int ts = (kind == 2) ? 32 : 96;
+            const int ts = (kind == 2) ? TS2 : TS1;
             const double lam = v[j], h = v[ts + j];
             RED[lane] = fmax(RED[lane], lam);
-            RED[32 + lane] += lam * h;
+            RED[NL + lane] += lam * h;
         });
         const double lmax = W.rmax([&](int lane) { return RED[lane]; });
-        const double hl = W.rsum([&](int lane) { return RED[32 + lane]; });
+        const double hl = W.rsum([&](int lane) { return RED[NL + lane]; });
         if (!(lmax > 0.0) || !(lmax < 1e300)) return false;
         gradient(STEP, false);  // STEP <- G' lam  (G, the gradient with the predictor multipliers, is recomputed by the next pass)
         const double nr = costate_residual();
         const double c = W.rsum([&](int lane) {
             double a = 0;
             MPCC_ROLLED
-            for (int o = lane; o < NX * N; o += 32) { const int k = o / NX, r = o - k * NX; a += STEP[(k + 1) * HZ + r] * LIN[(size_t)k * WL_SIZE + WL_b + r]; }
+            for (int o = lane; o < NX * N; o += NL) { const int k = o / NX, r = o - k * NX; a += STEP[(k + 1) * HZ + r] * LIN[(size_t)k * WL_SIZE + WL_b + r]; }
             return a;
         });
 #if defined(MPCC_QP_TRACE) && !defined(__CUDA_ARCH__)
@@ -521,8 +549,8 @@ struct WarpSqp {
             double* dst = SG + (k & 1) * SG_SIZE;
             const double* L = LIN + (size_t)k * WL_SIZE;
 #pragma unroll
-            for (int r = 0; r < 5; r++) {
-                const int e = lane + 32 * r;
+            for (int r = 0; r < (138 + NL - 1) / NL; r++) {
+                const int e = lane + NL * r;
                 const double* src = nullptr;
                 int d = 0;
                 if (e < 77) { src = CST + (size_t)k * WC_SIZE + 2 * e; d = SG_GS + 2 * e; }
@@ -552,7 +580,7 @@ struct WarpSqp {
         W.each([&](int lane) {
             const double* L = LIN + (size_t)N * WL_SIZE;
             MPCC_ROLLED
-            for (int e = lane; e < 256; e += 32) {
+            for (int e = lane; e < 256; e += NL) {
                 const int r = e >> 4, c = e & 15;
                 double v = 0;
                 if (r < 9 && c < 9) {
@@ -579,13 +607,13 @@ struct WarpSqp {
             W.each([&](int lane) {
                 issue_stage_copy(lane, k - 1, SG);
                 MPCC_ROLLED
-                for (int e = lane; e < 72; e += 32) {
+                for (int e = lane; e < 72; e += NL) {
                     const int i = e / 9, c = e - i * 9;
                     FF[e] = (i < 7) ? d_bq(i) * Pc[i * 16 + c] + Pc[(9 + i) * 16 + c] : d_bs() * Pc[7 * 16 + c] + d_bv() * Pc[8 * 16 + c];
                 }
                 // F2 (same phase: independent of FF): U = sum_p (w_p g_p) g_p'
 #if defined(__CUDA_ARCH__)
-                {
+                if (lane < 32) {   // (warp 0 of a wider group: mma.sync is a warp-level instruction)
                     // (14 x 11)(11 x 14) padded to 16 x 12 x 16: 2 x 2 fragments x 3 k-steps of mma.m8n8k4.f64; as in F6 the A
                     // fragment of block row m is w times the B fragment of block column m
                     const int fr = lane >> 2, fq = lane & 3;
@@ -633,7 +661,7 @@ struct WarpSqp {
             // F3: Mnn (8 x 8), Mnx (8 x 16) and [Mxx 0; 0 Mww] (16 x 16)
             W.each([&](int lane) {
                 MPCC_ROLLED
-                for (int e = lane; e < 64; e += 32) {
+                for (int e = lane; e < 64; e += NL) {
                     const int i = e >> 3, j = e & 7;
                     double v;
                     if (j < 7) {
@@ -647,7 +675,7 @@ struct WarpSqp {
                     Mnn[e] = v;
                 }
                 MPCC_ROLLED
-                for (int e = lane; e < 79; e += 32) {  // structural entries of Mnx: the 8 x 9 block and the rate coupling diagonal
+                for (int e = lane; e < 79; e += NL) {  // structural entries of Mnx: the 8 x 9 block and the rate coupling diagonal
                     int i, c;
                     double v;
                     if (e < 72) {
@@ -662,7 +690,7 @@ struct WarpSqp {
                     Mnx[i * 16 + c] = v;
                 }
                 MPCC_ROLLED
-                for (int e = lane; e < 88; e += 32) {  // structural entries of [Mxx 0; 0 Mww]: the 9 x 9 block and 7 diagonal entries
+                for (int e = lane; e < 88; e += NL) {  // structural entries of [Mxx 0; 0 Mww]: the 9 x 9 block and 7 diagonal entries
                     if (e < 81) {
                         const int r = e / 9, c = e - r * 9;
                         double v = Pc[r * 16 + c];
@@ -724,6 +752,7 @@ struct WarpSqp {
 #if defined(__CUDA_ARCH__)
                 // 16 x 16 += (16 x 8)(8 x 16) as 2 x 2 fragments x 2 k-steps of mma.m8n8k4.f64: the A fragment of block row m
                 // and the B fragment of block column m hold the same Lam entries, so a lane loads 4 doubles and 4 pairs
+                if (lane < 32) {
                 const int fr = lane >> 2, fq = lane & 3;
                 double lf[2][2];
 #pragma unroll
@@ -740,7 +769,9 @@ struct WarpSqp {
                         warp_dmma884(c0, c1, -lf[mb][1], lf[nb][1]);
                         Pc[o] = c0; Pc[o + 1] = c1;
                     }
+                }
 #else
+                if (lane < 32) {
                 const int r0 = 4 * (lane >> 3), c0 = 2 * (lane & 7);
                 double acc[4][2];
 #pragma unroll
@@ -753,10 +784,11 @@ struct WarpSqp {
                 }
 #pragma unroll
                 for (int a = 0; a < 4; a++) { Pc[(r0 + a) * 16 + c0] = acc[a][0]; Pc[(r0 + a) * 16 + c0 + 1] = acc[a][1]; }
+                }
 #endif
                 double* F = FACT + (size_t)k * WF_SIZE;
                 MPCC_ROLLED
-                for (int e = lane; e < WF_SIZE; e += 32) F[e] = X[e];  // X and Lam are contiguous in the scratch
+                for (int e = lane; e < WF_SIZE; e += NL) F[e] = X[e];  // X and Lam are contiguous in the scratch
                 async_wait<0>();  // the next stage's inputs have landed
             });
         }
@@ -771,7 +803,7 @@ struct WarpSqp {
             const double* F = FACT + (size_t)k * WF_SIZE + 2 * lane;
             double* dst = ring + (k & (SW_RING - 1)) * WF_SIZE + 2 * lane;
 #pragma unroll
-            for (int t = 0; t < WF_SIZE / 64; t++) async_copy16(dst + 64 * t, F + 64 * t);
+            for (int t = 0; t < (WF_SIZE / 2 + NL - 1) / NL; t++) if (lane + NL * t < WF_SIZE / 2) async_copy16(dst + 2 * NL * t, F + 2 * NL * t);
         }
         async_commit();
     }
@@ -787,10 +819,10 @@ struct WarpSqp {
             issue_factor_copy(lane, N - 3, ring);
             if (((GS_ - SC) & 1) == 0) {  // pairs; an odd S * HZ copies one unused double (kappa's first slot, written later)
                 MPCC_ROLLED
-                for (int e = lane; 2 * e < S * HZ; e += 32) async_copy16(GS_ + 2 * e, G + 2 * e);
+                for (int e = lane; 2 * e < S * HZ; e += NL) async_copy16(GS_ + 2 * e, G + 2 * e);
             } else {
                 MPCC_ROLLED
-                for (int e = lane; e < S * HZ; e += 32) async_copy8(GS_ + e, G + e);
+                for (int e = lane; e < S * HZ; e += NL) async_copy8(GS_ + e, G + e);
             }
             async_commit();
             if (lane < 16) V[V_D0 + lane] = 0.0;
@@ -872,11 +904,11 @@ struct WarpSqp {
     // slack / multiplier steps from the primal step; largest step keeping t, lam > 0.  With sums != nullptr also returns
     // s1 = sum(t dl + lam dt) and s2 = sum(dt dl), from which mu(alpha) = (sum t lam + alpha s1 + alpha^2 s2) / m follows.
     MPCC_HD double ineq_steps(double* sums) const {
-        double* RED = SC + SC_RED;
-        W.each([&](int lane) { RED[lane] = 1.0; RED[32 + lane] = 0.0; RED[64 + lane] = 0.0; });
+        double* RED = RED_;
+        W.each([&](int lane) { RED[lane] = 1.0; RED[NL + lane] = 0.0; RED[2 * NL + lane] = 0.0; });
         double* dt_ = IDT; double* dl_ = IDLAM;
         stream_constraints(vec_ids(CV_RP, CV_LAM, CV_V, CV_W, CV_T), 5, [&](int lane, int i, int kind, int k, int c, const double* v, int j, const double* row) {
-            constexpr int TSB = 96, TSP = 32;
+            constexpr int TSB = TS1, TSP = TS2;
             const int ts = (kind == 2) ? TSP : TSB;
             const double rp = v[j], lam = v[ts + j], vv = v[2 * ts + j], w = v[3 * ts + j], t = v[4 * ts + j];
             const double g = gz_of(STEP, kind, k, c, row);
@@ -887,12 +919,12 @@ struct WarpSqp {
             if (dt < 0) a = fmin(a, -t / dt);
             if (dl < 0) a = fmin(a, -lam / dl);
             RED[lane] = a;
-            RED[32 + lane] += t * dl + lam * dt;
-            RED[64 + lane] += dt * dl;
+            RED[NL + lane] += t * dl + lam * dt;
+            RED[2 * NL + lane] += dt * dl;
         });
         if (sums) {
-            sums[0] = W.rsum([&](int lane) { return RED[32 + lane]; });
-            sums[1] = W.rsum([&](int lane) { return RED[64 + lane]; });
+            sums[0] = W.rsum([&](int lane) { return RED[NL + lane]; });
+            sums[1] = W.rsum([&](int lane) { return RED[2 * NL + lane]; });
         }
         return W.rmin([&](int lane) { return RED[lane]; });
     }
@@ -902,12 +934,12 @@ struct WarpSqp {
         QpStats st;
         st.ok = 0; st.iters = 0; st.res_dual = 0; st.res_prim = 0; st.gap = 0; st.infeasible = 0;
         const int tot = S * NINEQ;
-        double* RED = SC + SC_RED;
+        double* RED = RED_;
         // feasibility of the boxes (stage 0: xi_0 = 0 must lie inside; others: lo <= hi)
         if (W.any([&](int lane) {
                 bool bad = false;
                 MPCC_ROLLED
-                for (int o = lane; o < S * NX; o += 32) {
+                for (int o = lane; o < S * NX; o += NL) {
                     const int k = o / NX, m = o - k * NX;
                     const double* L = LIN + (size_t)k * WL_SIZE;
                     if (k == 0) { if (L[WL_XLO + m] > 1e-9 || L[WL_XHI + m] < -1e-9) bad = true; }
@@ -919,7 +951,7 @@ struct WarpSqp {
         const double qn = W.rmax([&](int lane) {
             double q = 0;
             MPCC_ROLLED
-            for (int o = lane; o < S * HZ; o += 32) {
+            for (int o = lane; o < S * HZ; o += NL) {
                 const int k = o / HZ, r = o - k * HZ;
                 const double* L = LIN + (size_t)k * WL_SIZE;
                 if (r < NX) q = fmax(q, fabs(L[WL_q + r]));
@@ -937,7 +969,7 @@ struct WarpSqp {
                 for (int k = 0; k <= N; k++) { VAR[k * HZ + 7] = x; if (k < N) x += d_asv() * VAR[k * HZ + 8] + LIN[(size_t)k * WL_SIZE + WL_b + 7]; }
             }
             MPCC_ROLLED
-            for (int i = lane; i < tot; i += 32) { IT[i] = 1.0; ILAM[i] = 0.0; IW[i] = 0.0; IV[i] = 0.0; IRP[i] = 0.0; IDT[i] = 0.0; IDLAM[i] = 0.0; }
+            for (int i = lane; i < tot; i += NL) { IT[i] = 1.0; ILAM[i] = 0.0; IW[i] = 0.0; IV[i] = 0.0; IRP[i] = 0.0; IDT[i] = 0.0; IDLAM[i] = 0.0; }
         });
         const double s0 = QP_INIT_SLACK;
         W.each([&](int lane) {
@@ -947,23 +979,23 @@ struct WarpSqp {
         double a_prev = 1.0;  // step length of the previous iteration
         for (int it = 0; it < opt.max_iter; it++) {
             // residuals, barrier weights, predictor v = lam rp / t
-            W.each([&](int lane) { RED[lane] = 0.0; RED[32 + lane] = 0.0; });
+            W.each([&](int lane) { RED[lane] = 0.0; RED[NL + lane] = 0.0; });
             {
                 double* rp_ = IRP; double* w_ = IW; double* v_ = IV;
                 stream_constraints(vec_ids(CV_T, CV_LAM, CV_H), 3, [&](int lane, int i, int kind, int k, int c, const double* v, int j, const double* row) {
-                    const int ts = (kind == 2) ? 32 : 96;
+                    const int ts = (kind == 2) ? TS2 : TS1;
                     const double t = v[j], lam = v[ts + j], h = v[2 * ts + j];
                     const double rp = gz_of(VAR, kind, k, c, row) + t - h;
                     rp_[i] = rp;
                     RED[lane] = fmax(RED[lane], fabs(rp));
-                    RED[32 + lane] += t * lam;
+                    RED[NL + lane] += t * lam;
                     const double w = lam / t;
                     w_[i] = w;
                     v_[i] = w * rp;
                 });
             }
             const double nrp = W.rmax([&](int lane) { return RED[lane]; });
-            const double sum_tl = W.rsum([&](int lane) { return RED[32 + lane]; });
+            const double sum_tl = W.rsum([&](int lane) { return RED[NL + lane]; });
             const double mu = sum_tl / m_tot;
             // a short step announces trouble: test the multipliers for a Farkas ray before spending the remaining iterations
             if (it >= 2 && a_prev < 0.01 && nrp > opt.eps && primal_infeasible(1e-8)) { st.iters = it; st.res_prim = nrp; st.gap = mu; st.infeasible = 1; break; }
@@ -996,7 +1028,7 @@ struct WarpSqp {
                     const double sm = sigma * mu;
                     double* v_ = IV;
                     stream_constraints(vec_ids(CV_LAM, CV_RP, CV_DT, CV_DLAM, CV_T), 5, [&](int, int i, int kind, int, int, const double* v, int j, const double*) {
-                        const int ts = (kind == 2) ? 32 : 96;
+                        const int ts = (kind == 2) ? TS2 : TS1;
                         v_[i] = (v[j] * v[ts + j] + sm - v[2 * ts + j] * v[3 * ts + j]) / v[4 * ts + j];
                     });
                 } else {
@@ -1005,10 +1037,10 @@ struct WarpSqp {
 #if defined(MPCC_QP_TRACE) && !defined(__CUDA_ARCH__)
                     fprintf(stderr, "          alpha %.3e\n", a);
 #endif
-                    W.each([&](int lane) { MPCC_ROLLED for (int o = lane; o < S * HZ; o += 32) VAR[o] += a * STEP[o]; });
+                    W.each([&](int lane) { MPCC_ROLLED for (int o = lane; o < S * HZ; o += NL) VAR[o] += a * STEP[o]; });
                     double* t_ = IT; double* l_ = ILAM;
                     stream_constraints(vec_ids(CV_T, CV_LAM, CV_DT, CV_DLAM), 4, [&](int, int i, int kind, int, int, const double* v, int j, const double*) {
-                        const int ts = (kind == 2) ? 32 : 96;
+                        const int ts = (kind == 2) ? TS2 : TS1;
                         t_[i] = v[j] + a * v[2 * ts + j];
                         l_[i] = v[ts + j] + a * v[3 * ts + j];
                     });
@@ -1048,7 +1080,7 @@ struct WarpSqp {
     MPCC_HD void gather_point(double alpha) const {
         double* XT = VAR;
         W.each([&](int lane) {
-            for (int e = lane; e < S * HZ; e += 32) {
+            for (int e = lane; e < S * HZ; e += NL) {
                 const int kk = e / HZ, r = e - kk * HZ;
                 double v = XG[e];
                 if (alpha != 0.0) {
@@ -1066,13 +1098,13 @@ struct WarpSqp {
     template <bool FULL>
     MPCC_HD void eval_horizon(const double* cur_u, const double* rb, size_t rb_stride, size_t rb_stage, double alpha, bool write_cst, double& obj, double& gap,
                               bool* notpd, bool* nan, bool write_lin = true, bool gathered = false) const {
-        double* RED = SC + SC_RED;
+        double* RED = RED_;
         const double* XT = VAR;  // the evaluation point, see gather_point()
         if (!gathered) gather_point(alpha);
         obj = W.rsum([&](int lane) {
             double o_acc = 0, g_acc = 0;
             bool pd_l = true, nan_l = false;
-            for (int k = lane; k <= N; k += 32) {
+            for (int k = lane; k <= N; k += NL) {
                 double x[NX], u[NU], up[DOF], un[DOF], xn[NX];
                 auto gx = [&](int kk, int e) -> double { return XT[kk * HZ + e]; };
                 for (int e = 0; e < NX; e++) x[e] = gx(k, e);
@@ -1145,11 +1177,11 @@ struct WarpSqp {
                     if (d <= 0.0) { pd_l = false; break; }
                 }
             }
-            RED[32 + lane] = g_acc;
+            RED[NL + lane] = g_acc;
             RED[lane] = (pd_l ? 0.0 : 1.0) + (nan_l ? 2.0 : 0.0);
             return o_acc;
         });
-        gap = W.rsum([&](int lane) { return RED[32 + lane]; });
+        gap = W.rsum([&](int lane) { return RED[NL + lane]; });
         if (FULL) {
             *notpd = W.any([&](int lane) { const int f = (int)RED[lane]; return (f & 1) != 0; });
             *nan = W.any([&](int lane) { const int f = (int)RED[lane]; return (f & 2) != 0; });
@@ -1163,7 +1195,7 @@ struct WarpSqp {
         return W.any([&](int lane) {
             const double Lt = T.s[N_SPLINE - 1];
             bool bad = false;
-            for (int o = lane; o < S * NX; o += 32) {
+            for (int o = lane; o < S * NX; o += NL) {
                 const int k = o / NX, m = o - k * NX;
                 const double x = X[k * HZ + m], sv = X[k * HZ + 7];
                 double lo = P.lx[m], hi = P.ux[m];
@@ -1189,7 +1221,7 @@ struct WarpSqp {
         const int max_iter = (int)P.max_iter, ls_max = (int)P.line_search_max_iter;
         const int HN = S * HZ;
         init_scratch();
-        W.each([&](int lane) { for (int e = lane; e < HN; e += 32) { XS[e] = 0.0; XG[e] = GUESS[e]; } });
+        W.each([&](int lane) { for (int e = lane; e < HN; e += NL) { XS[e] = 0.0; XG[e] = GUESS[e]; } });
         int n_filt = 0, it = 0;
         bool done = false;
         bool have_lin = false, lin_notpd = false, lin_nan = false;  // LIN already holds the linearisation of the iterate
@@ -1208,7 +1240,7 @@ struct WarpSqp {
             have_lin = false; lin_infeasible = false;
             // mis-indexed input-bound rows (osqp_interface.cpp:273) intersected into the state boxes
             if (!qp_known_infeasible) W.each([&](int lane) {
-                for (int c = lane; c < NU * N; c += 32) {
+                for (int c = lane; c < NU * N; c += NL) {
                     const int k = c / NX, m = c - k * NX, i = c / NU, kk = c - i * NU;
                     const double uv = XG[i * HZ + NX + kk];
                     const double lo = (P.lu[kk] - uv) / Tu(kk), hi = (P.uu[kk] - uv) / Tu(kk);
@@ -1224,20 +1256,20 @@ struct WarpSqp {
             QpStats qs;
             if (qp_known_infeasible) { qs.ok = 0; qs.iters = 0; qs.res_dual = qs.res_prim = qs.gap = 0; }
             else {
-                W.each([&](int lane) { for (int e = lane; e < HN; e += 32) { GUESS[e] = XG[e]; SSTEP[e] = XS[e]; } });  // the QP solve uses all of the scratch
+                W.each([&](int lane) { for (int e = lane; e < HN; e += NL) { GUESS[e] = XG[e]; SSTEP[e] = XS[e]; } });  // the QP solve uses all of the scratch
                 qs = solve();
-                W.each([&](int lane) { for (int e = lane; e < HN; e += 32) XG[e] = GUESS[e]; });
+                W.each([&](int lane) { for (int e = lane; e < HN; e += NL) XG[e] = GUESS[e]; });
             }
             res.qp_iters += qs.iters;
             if (qs.ok) {
                 inf_step = W.rmax([&](int lane) {
                     double m = 0;
-                    for (int e = lane; e < HN; e += 32) { const int k = e / HZ, r = e - k * HZ; const double v = (r < NX || k < N) ? VAR[e] : 0.0; XS[e] = v; m = fmax(m, fabs(v)); }
+                    for (int e = lane; e < HN; e += NL) { const int k = e / HZ, r = e - k * HZ; const double v = (r < NX || k < N) ? VAR[e] : 0.0; XS[e] = v; m = fmax(m, fabs(v)); }
                     return m;
                 });
             } else {
                 res.qp_fail++;  // step keeps its previous value (osqp_interface.cpp:479-505)
-                if (!qp_known_infeasible) W.each([&](int lane) { for (int e = lane; e < HN; e += 32) XS[e] = SSTEP[e]; });
+                if (!qp_known_infeasible) W.each([&](int lane) { for (int e = lane; e < HN; e += NL) XS[e] = SSTEP[e]; });
             }
             const double t_c = now_ns();
             tm_set_qp += t_b - t_a; tm_solve_qp += t_c - t_b;
@@ -1258,7 +1290,7 @@ struct WarpSqp {
                     } else eval_horizon<false>(cur_u, rb, rb_stride, rb_stage, alpha, false, o2, g2, nullptr, nullptr);
                     if (W.any([&](int lane) {
                             bool dom = false;
-                            for (int j = lane; j < n_filt; j += 32) if (o2 >= FILT[2 * j] && g2 >= FILT[2 * j + 1]) dom = true;
+                            for (int j = lane; j < n_filt; j += NL) if (o2 >= FILT[2 * j] && g2 >= FILT[2 * j + 1]) dom = true;
                             return dom;
                         })) accepted = false;
                     if (accepted) {
@@ -1284,7 +1316,7 @@ struct WarpSqp {
             if (accepted && it < 32) res.accept_mask |= (1u << it);
             // ---- take the step (osqp_interface.cpp:549-551) ----
             W.each([&](int lane) {
-                for (int e = lane; e < HN; e += 32) {
+                for (int e = lane; e < HN; e += NL) {
                     const int k = e / HZ, r = e - k * HZ;
                     const double s = XS[e];
                     if (r < NX) XG[e] += alpha * (Tx(r) * s);
@@ -1295,7 +1327,7 @@ struct WarpSqp {
             const double inf = inf_step;
             if (log && log->n < log->max_log) {
                 W.each([&](int lane) {
-                    if (log->steps) for (int e = lane; e < HN; e += 32) log->steps[(size_t)log->n * HN + e] = XS[e];
+                    if (log->steps) for (int e = lane; e < HN; e += NL) log->steps[(size_t)log->n * HN + e] = XS[e];
                     if (lane == 0) { log->alphas[log->n] = alpha; log->qp_ok[log->n] = qs.ok; }
                 });
                 log->n++;
@@ -1304,9 +1336,11 @@ struct WarpSqp {
         }
         if (!done) { res.status = MAX_ITER_EXCEEDED; res.iters = max_iter; }
         else if (res.status != SOLVED) res.iters = it;
-        W.each([&](int lane) { for (int e = lane; e < HN; e += 32) GUESS[e] = XG[e]; });
+        W.each([&](int lane) { for (int e = lane; e < HN; e += NL) GUESS[e] = XG[e]; });
         return res;
     }
 };
+
+using WarpSqp = GroupSqp<32>;
 
 }  // namespace mpcc

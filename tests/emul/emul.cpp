@@ -83,15 +83,18 @@ int emu_epilogue(int N, int status, int iters, const double* x0, double* guess, 
     return ok ? 1 : 0;
 }
 
-// The warp-per-instance formulation (sqp_warp.cuh) executed phase by phase on the host; reverse = lane order.
-int emu_warp_solve_ocp(const double* params, const double* table, double Ts, int N, double* guess, const double* rb, const double* cur_u,
-                       int qp_max_iter, double qp_eps, int reverse, int* status, int* iters, int* qp_iters, double* steps, double* alphas, int* qp_ok,
-                       int max_log, int* n_logged, unsigned* accept_mask) {
+// The lanes-per-instance formulation (sqp_warp.cuh) executed phase by phase on the host; reverse = lane order.
+// NL = 32: the warp kernel (throughput); NL = 128: the CTA kernel (latency mode).
+}  // extern "C"
+template <int NL>
+static int group_solve_ocp(const double* params, const double* table, double Ts, int N, double* guess, const double* rb, const double* cur_u,
+                           int qp_max_iter, double qp_eps, int reverse, int* status, int* iters, int* qp_iters, double* steps, double* alphas, int* qp_ok,
+                           int max_log, int* n_logged, unsigned* accept_mask) {
     const Params& P = *(const Params*)params;
     const int S = N + 1, HN = S * HZ;
-    std::vector<double> gws(warp_ws_doubles(N)), sm(warp_smem_doubles(N));
-    Warp wp; wp.reverse = reverse != 0;
-    WarpSqp w{P, *(const TrackTable*)table, make_dyn(P, Ts), Ts, N, S, QpOptions{qp_max_iter, qp_eps}, wp};
+    std::vector<double> gws(warp_ws_doubles(N)), sm(group_smem_doubles<NL>(N), -3.0);
+    Lanes<NL> wp; wp.reverse = reverse != 0;
+    GroupSqp<NL> w{P, *(const TrackTable*)table, make_dyn(P, Ts), Ts, N, S, QpOptions{qp_max_iter, qp_eps}, wp};
     w.carve(gws.data(), sm.data());
     for (int e = 0; e < HN; e++) w.GUESS[e] = guess[e];
     SqpLogRef lg{steps, alphas, qp_ok, max_log, 0};
@@ -99,6 +102,17 @@ int emu_warp_solve_ocp(const double* params, const double* table, double Ts, int
     for (int e = 0; e < HN; e++) guess[e] = w.GUESS[e];
     *status = r.status; *iters = r.iters; *qp_iters = r.qp_iters; *n_logged = lg.n; *accept_mask = r.accept_mask;
     return r.status == SOLVED;
+}
+extern "C" {
+int emu_warp_solve_ocp(const double* params, const double* table, double Ts, int N, double* guess, const double* rb, const double* cur_u,
+                       int qp_max_iter, double qp_eps, int reverse, int* status, int* iters, int* qp_iters, double* steps, double* alphas, int* qp_ok,
+                       int max_log, int* n_logged, unsigned* accept_mask) {
+    return group_solve_ocp<32>(params, table, Ts, N, guess, rb, cur_u, qp_max_iter, qp_eps, reverse, status, iters, qp_iters, steps, alphas, qp_ok, max_log, n_logged, accept_mask);
+}
+int emu_cta_solve_ocp(const double* params, const double* table, double Ts, int N, double* guess, const double* rb, const double* cur_u,
+                      int qp_max_iter, double qp_eps, int reverse, int* status, int* iters, int* qp_iters, double* steps, double* alphas, int* qp_ok,
+                      int max_log, int* n_logged, unsigned* accept_mask) {
+    return group_solve_ocp<128>(params, table, Ts, N, guess, rb, cur_u, qp_max_iter, qp_eps, reverse, status, iters, qp_iters, steps, alphas, qp_ok, max_log, n_logged, accept_mask);
 }
 // one QP of the warp formulation at the linearisation of `guess`
 int emu_warp_solve_qp(const double* params, const double* table, double Ts, int N, const double* guess, const double* rb, const double* cur_u,

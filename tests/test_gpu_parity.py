@@ -436,7 +436,7 @@ def test_warm_start_state_roundtrip_and_failure_policy(M, O, ee_home):
     # the jumped instance regenerated its guess (num_valid_guess_failed_++ in the prologue, mpc.cpp:117-121), solved, and the
     # epilogue then set valid = true / failed = 0 (mpc.cpp:140-144); projection pulled s back near the path point
     assert np.all(v3 == 1) and np.all(f3 == 0)
-    assert abs(r1["x0"][0, 7] - x1[0, 7]) > 0.4 and np.abs(r1["x0"][1:, 7] - x1[1:, 7]).max() < 1e-3
+    assert abs(r1["x0"][0, 7] - x1[0, 7]) > 0.03 and np.abs(r1["x0"][1:, 7] - x1[1:, 7]).max() < 1e-3   # moved by more than max_dist_proj
     assert r1["iters"][0] >= r1["iters"][1:].max()      # a regenerated (cold) guess needs at least as many SQP iterations
     assert np.abs(r1["horizon"][0, 0, :9] - r1["x0"][0]).max() == 0.0
     mpc.close()
@@ -574,10 +574,36 @@ def test_instrumentation_and_counters(M, O, ee_home):
     qi, qf = mpc.qp_counters()
     st = mpc.stats()
     assert st["qp_iters"] == int(qi.sum()) and st["qp_fail"] == int(qf.sum()) and st["sqp_iters"] == int(r["iters"].sum())
-    assert st["launches"] == 6 and st["solved"] == B  # prologue, kin, mlp, order, sqp (exclusive + main launch)
+    assert st["launches"] == 4 and st["solved"] == B  # prologue, kin, mlp, sqp (B <= 2 x SMs: one CTA per instance)
     masks = mpc.decisions()
     assert np.all((masks & 1) == 1)  # the first trial of the first iteration meets an empty filter: always accepted
     mpc.close()
+
+
+def test_cta_kernel_agrees_with_warp_kernel(M, O, ee_home, rng):
+    """The two SQP kernel families are one code (sqp_warp.cuh, template on the lane count): k_sqp_warp (a warp per instance,
+    throughput) and k_sqp_cta (a 128-thread CTA per instance, latency mode; default for batch <= 2 x SMs).  Forced either way
+    (mpcc_cuda_config.reserved bits 1 / 2) they must take the same branch and agree to rounding; where a noise-level filter tie
+    splits them, the split is bounded."""
+    for N, over in ((10, None), (40, {"sqp.eps_prim": 0.01})):
+        B = 48
+        a = M.BatchMPC(B, N, flags=2); b = M.BatchMPC(B, N, flags=4)
+        for m in (a, b):
+            m.load_nn(); m.set_params(M.load_default_params(overrides=over)); m.set_tracks(M.load_track_json(None, ee_home))
+        x = np.tile(np.r_[O.Q_HOME, 0., 0.], (B, 1)); x[:, :7] += rng.uniform(-0.05, 0.05, (B, 7)); u = np.zeros((B, 8))
+        n_same = n_tot = 0
+        for c in range(3):
+            wa = a.get_warm_state(); b.set_warm_state(*wa)      # identical inputs every cycle
+            ra, rb_ = a.run_cycle(x, u), b.run_cycle(x, u)
+            assert np.array_equal(ra["status"], rb_["status"]) and np.abs(ra["x0"] - rb_["x0"]).max() == 0.0
+            same = (ra["iters"] == rb_["iters"]) & (a.decisions() == b.decisions())
+            err = (np.abs(ra["u0"] - rb_["u0"]) / TU).max(axis=1)
+            assert err[same].max() < 1e-7, err[same].max()     # same branch: same arithmetic up to reduction order
+            n_same += int(same.sum()); n_tot += B
+            u = ra["u0"]; x = a.sim_time_step(ra["x0"], u, 0.01)
+        assert n_same >= 0.85 * n_tot, (n_same, n_tot)
+        assert a.stats()["launches"] == 6 and b.stats()["launches"] == 4
+        a.close(); b.close()
 
 
 def test_exclusive_sm_launch_changes_scheduling_only(M, O, ee_home):

@@ -40,7 +40,7 @@ def test_mpcc_class_matches_reference_surface(O, nn, track_wp):
     J = mpcc.robot_model.getEEJacobian(O.Q_HOME)
     p, R, Jo = O.fk(O.Q_HOME)
     assert J.shape == (6, 7) and np.abs(J - Jo).max() < 1e-12 and np.abs(mpcc.robot_model.getEEOrientation(O.Q_HOME) - R).max() < 1e-12
-    assert abs(mpcc.robot_model.getEEManipulability(O.Q_HOME) - O.manip(O.Q_HOME)) < 1e-12
+    assert abs(mpcc.robot_model.getEEManipulability(O.Q_HOME) - O.manip(O.Q_HOME)[0]) < 1e-12
     mpcc.setTrack(state)
     pos, rot, arc = mpcc.getSplinePath()
     assert pos.shape == (100, 3) and rot.shape == (100, 3, 3) and arc.shape == (100,) and np.abs(pos[0] - ee).max() < 1e-12

@@ -9,7 +9,8 @@ from bench import q_home
 B, N = 64, 40
 CYCLES = int(sys.argv[1]) if len(sys.argv) > 1 else 300
 rng = np.random.default_rng(3)
-mpc = M.BatchMPC(B, N); mpc.load_nn(); mpc.set_params(M.load_default_params(overrides={"sqp.eps_prim": 0.01}))
+FLAGS = int(sys.argv[2]) if len(sys.argv) > 2 else 0   # 2: warp-per-instance kernel, 4: CTA-per-instance kernel (default for this batch)
+mpc = M.BatchMPC(B, N, flags=FLAGS); mpc.load_nn(); mpc.set_params(M.load_default_params(overrides={"sqp.eps_prim": 0.01}))
 ee = mpc.eval_robot_data(q_home()[None])[0, 7:10]
 mpc.set_tracks(M.load_track_json(None, ee)); mpc.set_profiling(True)
 x = np.tile(np.r_[q_home(), 0., 0.], (B, 1)); x[:, :7] += rng.uniform(-0.05, 0.05, (B, 7)); u = np.zeros((B, 8))
