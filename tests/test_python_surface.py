@@ -51,12 +51,15 @@ def test_mpcc_class_matches_reference_surface(O, nn, track_wp):
     assert abs(mpcc.getContourError(0.0, ee)) < 1e-12
     x, u = state.copy(), np.zeros(8)
     for c in range(3):
+        w_hor, w_valid, w_failed = mpcc.mpc.get_warm_state()
         ok, x_upd, u_new, hor, ct = mpcc.runMPC(x, u)
+        r = mpcc.mpc.read_results()
+        dec = [(int(mpcc.mpc.decisions()[0]) >> i) & 1 for i in range(min(int(r["iters"][0]), 32))]
+        o.set_warm_state(w_hor[0], w_valid[0], w_failed[0]); o.set_forced_decisions(dec)      # along the device's line-search branch (filter ties)
         ro = o.run(x, u)
         assert ok is True and ro["ok"] and len(hor) == 11 and set(hor[0]) == {"state", "input"} and set(ct) == {"total", "set_qp", "solve_qp", "get_alpha", "set_env"}
         assert np.abs(x_upd - ro["x0"]).max() < 1e-9 and ct["total"] > 0
-        if c == 0:
-            assert (np.abs(u_new - ro["u0"]) / TU).max() < 5e-4          # free-running: a filter tie may split later cycles
+        assert r["iters"][0] == ro["iters"] and (np.abs(u_new - ro["u0"]) / TU).max() < 1e-4
         assert np.array_equal(hor[0]["input"], u_new)
         u = u_new; x = O.sim_time_step(x_upd, u_new, 0.01)
     mpcc.close()

@@ -21,6 +21,8 @@ for c in range(CYCLES):
     w = int(np.argmax(ct[:, 0]))
     rows.append((dt, kt[2], kt[3], it.max(), it.mean(), ct[w, 0], it[w], qi[w], qf[w], np.median(ct[:, 0]), qi.max(), (r["status"] != 0).sum()))
     u = r["u0"]; x = mpc.sim_time_step(r["x0"], u)
+    if len(sys.argv) > 3:
+        print("cycle", c, "max iters", it.max(), "qp_iters max", qi.max(), "fails", qf.sum(), "non-solved", (r["status"] != 0).sum(), flush=True)
 a = np.array(rows[20:], dtype=float)
 print("cycles", len(a))
 print("e2e ms  p50 %.2f p90 %.2f p99 %.2f max %.2f" % tuple(np.percentile(a[:, 0], [50, 90, 99, 100])))
