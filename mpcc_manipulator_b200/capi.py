@@ -5,7 +5,8 @@ from pathlib import Path
 import numpy as np
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libmpcc_b200.so"
+import os as _os
+LIB_PATH = Path(_os.environ.get("MPCC_B200_LIB", PKG / "libmpcc_b200.so"))   # the override serves kernel-variant experiments (tools/)
 ASSETS = PKG / "assets"
 
 NX, NU, HZ, RB, LIN = 9, 8, 17, 150, 212
@@ -40,8 +41,9 @@ def lib():
         _lib = C.CDLL(str(LIB_PATH))
         _lib.mpcc_cuda_last_error.restype = C.c_char_p
         _lib.mpcc_cuda_stream.restype = C.c_void_p
-        _lib.mpcc_cuda_launch_count.restype = C.c_int64
-        _lib.mpcc_cuda_launch_count.argtypes = [C.c_void_p]
+        if hasattr(_lib, "mpcc_cuda_launch_count"):   # (absent only in older builds loaded through MPCC_B200_LIB for comparisons)
+            _lib.mpcc_cuda_launch_count.restype = C.c_int64
+            _lib.mpcc_cuda_launch_count.argtypes = [C.c_void_p]
     return _lib
 
 

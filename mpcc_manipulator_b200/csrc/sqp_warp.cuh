@@ -99,7 +99,7 @@ using Warp = Lanes<32>;
 
 // The interior-point iteration is bound by instruction fetch, not issue (ncu: stall_no_instruction dominates with ten
 // warps per SM in different phases of ~100 KB of code): lane-strided loops of the QP path stay rolled.
-#if defined(__CUDACC__)
+#if defined(__CUDACC__) && !defined(MPCC_NO_ROLL)
 #define MPCC_ROLLED _Pragma("unroll 1")
 #else
 #define MPCC_ROLLED
@@ -222,7 +222,11 @@ struct GroupSqp {
     // per-instance global workspace
     double *LIN, *CST, *IT, *ILAM, *IRP, *IW, *IV, *IDT, *IDLAM, *IH, *G, *KAP, *FACT, *SSTEP, *GUESS, *RBFV, *FILT;
     // per-instance shared memory
-    double *VAR, *STEP, *SC, *RING, *RED_;
+    double *VAR, *STEP, *SC;
+    double* GRP;   // NL > 32 only: the group's own tile ring | per-lane accumulators | reduction cells (behind the warp layout)
+    // the warp instantiation keeps both in the (idle) factorisation scratch: no extra pointers live in registers
+    MPCC_HD double* ring_base() const { return NL == 32 ? SC : GRP; }
+    MPCC_HD double* red_base() const { return NL == 32 ? SC + SC_RED : GRP + 3 * 19 * NL; }
     // working copies between QP solves: the iterate (in the scratch) and the persistent step (in STEP); their homes
     // GUESS / SSTEP in the global workspace are written before and re-read after every executed QP solve
     double *XG, *XS;
@@ -249,10 +253,9 @@ struct GroupSqp {
         // FACT and G on even offsets (16-byte copies)
         FACT = gws; gws += S_ * WF_SIZE; G = gws; gws += S_ * HZ; KAP = gws; gws += S_ * 8; SSTEP = gws; gws += S_ * HZ; GUESS = gws; gws += S_ * HZ; RBFV = gws; gws += S_ * 2 * NPOLY; FILT = gws;
         VAR = sm; STEP = sm + S_ * HZ; SC = sm + 2 * S_ * HZ;
-        if (NL == 32) { RING = SC; RED_ = SC + SC_RED; }   // the tile ring shares the (idle) factorisation scratch
-        else { RING = sm + warp_smem_doubles(N); RED_ = RING + 3 * 19 * NL; }
+        GRP = sm + warp_smem_doubles(N);
 #if defined(__CUDA_ARCH__)
-        W.red = RED_ + 5 * NL;
+        W.red = (NL == 32) ? nullptr : red_base() + 5 * NL;
 #endif
         OR_ = 18 * S; OP_ = 32 * S;
         XG = (HZ * S <= XG_ROOM) ? SC : SC + SC_SIZE;
@@ -387,7 +390,7 @@ struct GroupSqp {
     MPCC_HD void stream_constraints(unsigned ids, int na, F body) const {
         const int nt1 = (OR_ + 14 * N - 18 + TS1 - 1) / TS1, nt = nt1 + (NPOLY * N + TS2 - 1) / TS2;
         const int s1 = na * TS1, s2 = na * TS2 + TS2 * 14, slot = (s1 > s2) ? s1 : s2;  // NL = 32: <= 608 for na <= 5, three slots stay below SC_TXU
-        double* ring = RING;
+        double* ring = ring_base();
         const size_t vstride = cvec_stride(N);
         auto issue = [&](int lane, int t) {
             if (t < nt) {
@@ -489,7 +492,7 @@ struct GroupSqp {
 
     // costates of the xi-stationarity recursion p_N = g_N, p_k = g_k + A' p_{k+1}, in place on the xi part of STEP (which holds g);
     // returns the inf-norm of the nu-stationarity residual g_nu,k + B' p_{k+1}
-    MPCC_HDNI double costate_residual() const {
+    MPCC_HD double costate_residual() const {
         W.each([&](int lane) {
             if (lane < 8) for (int k = N - 1; k >= 1; k--) STEP[k * HZ + lane] += STEP[(k + 1) * HZ + lane];
         });
@@ -515,8 +518,12 @@ struct GroupSqp {
     // nu-stationarity residual.  If r vanishes (relative to |lam|) and sum_k p_{k+1}' b_k - h' lam > 0, no such z has G z <= h.
     // The diverging multipliers of an interior-point run on an infeasible QP converge to such a ray.  Tested only on
     // iterations that follow a short step (the hot path never gets here); tolerance eps_inf relative to |lam|_inf.
-    MPCC_HDNI bool primal_infeasible(double eps_inf) const {
-        double* RED = RED_;
+    // Out of line and called on a COPY of this object: a noinline member call would make `this` escape, and the compiler then
+    // keeps the object in local memory for the whole kernel (+500 local loads in the hot loops, steady-state kernel 7.2 instead
+    // of 5.1 ms, although the call never executes in a healthy batch).
+    static MPCC_HDNI bool primal_infeasible(GroupSqp g, double eps_inf) { return g.primal_infeasible_impl(eps_inf); }
+    MPCC_HD bool primal_infeasible_impl(double eps_inf) const {
+        double* RED = red_base();
         W.each([&](int lane) { RED[lane] = 0.0; RED[NL + lane] = 0.0; });
         stream_constraints(vec_ids(CV_LAM, CV_H), 2, [&](int lane, int, int kind, int, int, const double* v, int j, const double*) {
             const int ts = (kind == 2) ? TS2 : TS1;
@@ -904,7 +911,7 @@ struct GroupSqp {
     // slack / multiplier steps from the primal step; largest step keeping t, lam > 0.  With sums != nullptr also returns
     // s1 = sum(t dl + lam dt) and s2 = sum(dt dl), from which mu(alpha) = (sum t lam + alpha s1 + alpha^2 s2) / m follows.
     MPCC_HD double ineq_steps(double* sums) const {
-        double* RED = RED_;
+        double* RED = red_base();
         W.each([&](int lane) { RED[lane] = 1.0; RED[NL + lane] = 0.0; RED[2 * NL + lane] = 0.0; });
         double* dt_ = IDT; double* dl_ = IDLAM;
         stream_constraints(vec_ids(CV_RP, CV_LAM, CV_V, CV_W, CV_T), 5, [&](int lane, int i, int kind, int k, int c, const double* v, int j, const double* row) {
@@ -934,7 +941,7 @@ struct GroupSqp {
         QpStats st;
         st.ok = 0; st.iters = 0; st.res_dual = 0; st.res_prim = 0; st.gap = 0; st.infeasible = 0;
         const int tot = S * NINEQ;
-        double* RED = RED_;
+        double* RED = red_base();
         // feasibility of the boxes (stage 0: xi_0 = 0 must lie inside; others: lo <= hi)
         if (W.any([&](int lane) {
                 bool bad = false;
@@ -976,8 +983,12 @@ struct GroupSqp {
             for_present(lane, VAR, true, [&](int i, double g, double h) { const double t0 = fmax(h - g, s0); IT[i] = t0; ILAM[i] = s0 / t0; IH[i] = h; });
         });
         const double m_tot = 43.0 * N;
-        double a_prev = 1.0;  // step length of the previous iteration
-        for (int it = 0; it < opt.max_iter; it++) {
+        // The certificate test sits OUTSIDE the iteration loop (the loop leaves for it and is re-entered): with a call inside the
+        // loop body the steady-state kernel was 40 % slower although the call never executed (measured: 7.19 vs 5.09 ms).
+        int it = 0;
+        bool suspicious = false;   // the last step was short: test for an infeasibility certificate before going on
+        for (;;) {
+        for (; it < opt.max_iter; it++) {
             // residuals, barrier weights, predictor v = lam rp / t
             W.each([&](int lane) { RED[lane] = 0.0; RED[NL + lane] = 0.0; });
             {
@@ -997,8 +1008,6 @@ struct GroupSqp {
             const double nrp = W.rmax([&](int lane) { return RED[lane]; });
             const double sum_tl = W.rsum([&](int lane) { return RED[NL + lane]; });
             const double mu = sum_tl / m_tot;
-            // a short step announces trouble: test the multipliers for a Farkas ray before spending the remaining iterations
-            if (it >= 2 && a_prev < 0.01 && nrp > opt.eps && primal_infeasible(1e-8)) { st.iters = it; st.res_prim = nrp; st.gap = mu; st.infeasible = 1; break; }
             // Two passes over ONE copy of gradient / sweeps / step lengths (the loop is kept rolled on purpose: code footprint).
             //   pass 0: Lagrangian gradient and residual test, factorisation, affine (predictor) step, centring parameter
             //   pass 1: corrector right-hand side, combined step, update
@@ -1033,7 +1042,7 @@ struct GroupSqp {
                     });
                 } else {
                     const double a = fmin(1.0, 0.995 * a_max);
-                    a_prev = a;
+                    if (a < 0.01 && it >= 1 && nrp > opt.eps) suspicious = true;   // a short step announces trouble
 #if defined(MPCC_QP_TRACE) && !defined(__CUDA_ARCH__)
                     fprintf(stderr, "          alpha %.3e\n", a);
 #endif
@@ -1048,6 +1057,16 @@ struct GroupSqp {
             }
             if (stop) break;
             st.iters = it + 1;
+            if (suspicious) { it++; break; }
+        }
+#if !defined(MPCC_NO_CERT)
+        if (!suspicious) break;
+        suspicious = false;
+        // test the multipliers for a Farkas ray before spending the remaining iterations
+        if (primal_infeasible(*this, 1e-8)) { st.infeasible = 1; break; }
+#else
+        break;
+#endif
         }
         if (st.ok) {
             // make the equalities exact: xi = rollout(nu)
@@ -1098,7 +1117,7 @@ struct GroupSqp {
     template <bool FULL>
     MPCC_HD void eval_horizon(const double* cur_u, const double* rb, size_t rb_stride, size_t rb_stage, double alpha, bool write_cst, double& obj, double& gap,
                               bool* notpd, bool* nan, bool write_lin = true, bool gathered = false) const {
-        double* RED = RED_;
+        double* RED = red_base();
         const double* XT = VAR;  // the evaluation point, see gather_point()
         if (!gathered) gather_point(alpha);
         obj = W.rsum([&](int lane) {

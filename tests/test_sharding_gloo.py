@@ -90,3 +90,17 @@ def test_result_gatherer_gloo():
     idx = np.arange(world * b)
     assert np.array_equal(gu, idx[:, None] * 10.0 + np.arange(8)[None] + 1)
     assert np.array_equal(gs, idx % 3) and np.array_equal(gi, idx % 5 + 1)
+
+
+@pytest.mark.gpu
+def test_abi_gather_over_nccl_on_two_gpus():
+    """The product ABI's own gather (mpcc_cuda_gather_results, NCCL on a side stream) on two GPUs of one box; skipped on a
+    single-GPU box (the CPU tier covers the sharding logic with gloo above)."""
+    import subprocess, sys, torch
+    from pathlib import Path
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = Path(__file__).resolve().parent.parent
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29731",
+                        str(root / "tools" / "multi_gpu_check.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "multi-GPU gather ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
