@@ -320,6 +320,26 @@ def measure(M, name, args, steps, warmup, world, rank, local, dist, full):
         launches["n"] += 1
         x, xn = xn, x
 
+    # ---- settle: the closed loop is run from its cold start until every instance tracks with one SQP iteration per cycle
+    #      ("report steady-state cycles/s x B; also a cold first cycle").  The start-up transient is timed on the
+    #      way and reported separately (`cold_start`), including round 1's window (cycles 5..24 after the cold start). ----
+    settle = args.settle if name != "c5" else 0
+    cold = None
+    if settle > 0:
+        sev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(settle)]
+        for i in range(settle):
+            with torch.cuda.stream(stream):
+                sev[i][0].record(stream)
+            step()
+            with torch.cuda.stream(stream):
+                sev[i][1].record(stream)
+        mpc.synchronize()
+        sms = np.array([a.elapsed_time(b) for a, b in sev])
+        cold = {"first_cycle_ms": float(sms[0]), "settle_cycles": settle}
+        if settle >= 25:
+            cold["cycles_5_24_mean_ms"] = float(sms[5:25].mean())
+            cold["value_cycles_5_24"] = world * B / (float(sms[5:25].mean()) * 1e-3)
+            cold["note"] = "per-rank device time; cycles_5_24 is the window round 1's bench line was measured on"
     for _ in range(warmup):
         step()
     mpc.synchronize()
@@ -373,8 +393,10 @@ def measure(M, name, args, steps, warmup, world, rank, local, dist, full):
     huo = torch.empty((B, 8), dtype=torch.float64).pin_memory(); hhor = torch.empty((B, S, 17), dtype=torch.float64).pin_memory()
     hobs = torch.from_numpy(obs_host.copy()).pin_memory() if obs_host is not None else None
     hst = torch.empty(B, dtype=torch.int32).pin_memory(); hit = torch.empty(B, dtype=torch.int32).pin_memory(); hok = torch.empty(B, dtype=torch.int32).pin_memory()
-    mpc.reset()   # same closed loop from the same start as the device-resident measurement
-    hx.copy_(torch.from_numpy(x_host)); hu.copy_(torch.from_numpy(u_host))
+    # the same closed loop goes on from where the device-resident measurement left it (warm starts stay on the device)
+    hx.copy_(x.cpu()); hu.copy_(u.cpu())
+    if hobs is not None:
+        hobs.copy_(obs.cpu())
     gu = np.zeros((world * B, 8)); gs = np.zeros(world * B, np.int32); gi = np.zeros(world * B, np.int32)
 
     def e2e_step():
@@ -422,7 +444,7 @@ def measure(M, name, args, steps, warmup, world, rank, local, dist, full):
                           + ("; + mpcc_cuda_gather_results / read_gathered over NCCL" if world > 1 else "") + ")",
                    "latency_ms": {"p50": float(np.percentile(lat, 50)), "p90": float(np.percentile(lat, 90)), "p99": float(np.percentile(lat, 99)), "max": float(lat.max())},
                    "max_sqp_iters_per_cycle": {"p50": int(np.percentile(iters_max, 50)), "p99": int(np.percentile(iters_max, 99)), "max": int(iters_max.max())}},
-           "info": info}
+           "info": info, "cold_start": cold}
     mpc.close()
     return res
 
@@ -433,7 +455,7 @@ def summary_of(r):
     return {"workload": r["workload"], "batch_per_gpu": r["B"], "horizon": r["N"], "value": r["value"], "unit": UNIT, "ms_per_step": r["ms_per_step"],
             "device_step_ms": {"p50": float(np.percentile(sm, 50)), "p99": float(np.percentile(sm, 99)), "max": float(sm.max())},
             "e2e": r["e2e"], "kernels_ms": {n: round(float(t), 4) for n, t in zip(KERNEL_NAMES, r["ktimes"].mean(axis=0))},
-            "last_step_stats": r["stats"], **r["info"]}
+            "last_step_stats": r["stats"], "cold_start": r["cold_start"], **r["info"]}
 
 
 KERNEL_NAMES = ["k_prologue", "k_kin", "k_mlp", "k_sqp_warp"]
@@ -509,12 +531,13 @@ def run_ours(args):
                "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                "config": {"workload": r["workload"], "name": args.config,
                           "batch_per_gpu": B, "horizon": N, "l2": "flushed (256 MiB memset) between timed steps",
+                          "regime": f"steady-state closed-loop tracking: {args.settle} settle cycles from the cold start before the warm-up steps (SURVEY 8d C2); the start-up transient is in `cold_start`",
                           "parallelism": f"dp{world} (instances sharded; all-gather of u0/status/iters only, NCCL on a side stream through mpcc_cuda_gather_results)"},
                "latency_ms": {"p50": float(np.percentile(step_ms, 50)), "p99": float(np.percentile(step_ms, 99)), "max": float(step_ms.max()),
                               "what": "device time of one closed-loop step of the whole batch (CUDA events)"},
                "clocks": r["clocks"], "e2e": r["e2e"],
                "gpu_launches": r["launches"], "kernels_ms": kernels, "roofline": roof, "roofline_mlp": roof_mlp, "roofline_sqp": roof_sqp,
-               "last_step_stats": stats_acc, "wall_s_timed_region": r["t_wall"]}
+               "last_step_stats": stats_acc, "wall_s_timed_region": r["t_wall"], "cold_start": r["cold_start"]}
         if secondary:
             out["secondary_configs"] = secondary
     if world > 1:
@@ -535,6 +558,7 @@ def main():
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS), help="BASELINE configuration (SURVEY 8d); c2 is the metric's")
     ap.add_argument("--batch", type=int, default=0, help="instances per GPU (0: the configuration's own)")
     ap.add_argument("--horizon", type=int, default=0, help="N (0: the configuration's own)")
+    ap.add_argument("--settle", type=int, default=40, help="closed-loop cycles run from the cold start before warm-up (0: time the start-up transient itself)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the short C3 / C4 / C5 runs that the default (c2) line carries")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-worker", action="store_true")
