@@ -476,13 +476,19 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     r = measure(M, args.config, args, args.steps, args.warmup, world, rank, local, dist, full=True)
     B, N, S = r["B"], r["N"], r["N"] + 1
+    peak = M.fp64_peak(local) if rank == 0 else None   # before the secondary runs: nothing the metric's line needs depends on them
     # secondary BASELINE configurations, short runs, reported inside the same JSON line (the driver only runs the default command)
     secondary = {}
     if args.config == "c2" and not args.no_secondary:
         names = ["c3", "c4", "c5"] if world == 1 else ["c4"]
         for nm in names:
             st, wu = (300, 20) if nm == "c5" else (10, 3)
-            secondary[nm] = summary_of(measure(M, nm, args, st, wu, world, rank, local, dist, full=False))
+            try:   # a failure in a short secondary run must not take the metric's line with it (single GPU only: ranks stay in step)
+                secondary[nm] = summary_of(measure(M, nm, args, st, wu, world, rank, local, dist, full=False))
+            except Exception as ex:
+                if world > 1:
+                    raise
+                secondary[nm] = {"error": repr(ex)[:300]}
 
     out = None
     if rank == 0:
@@ -490,7 +496,6 @@ def run_ours(args):
         km = ktimes.mean(axis=0)
         names = KERNEL_NAMES
         dom = int(np.argmax(km))
-        peak = M.fp64_peak(local)
         peak_src = ("FP64 microbenchmark measured in this run (mpcc_cuda_fp64_peak: larger of the DFMA and the mma.m8n8k4.f64 figure, one shared pipe); MEASURED_PEAKS.json holds no FP64 figure; "
                     "nominal 148 SM x 64 FMA/clk x 1.965 GHz = %.1f" % NOMINAL_FP64_TFLOPS)
         # DRAM traffic per launch: ncu --set full captures of STEADY-STATE launches, committed with their capture conditions;

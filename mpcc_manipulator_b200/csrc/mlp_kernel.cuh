@@ -98,6 +98,41 @@ __device__ __forceinline__ void mlp_chunk(const double2* __restrict__ Wc, const 
     }
 }
 
+// First layer of a network, one 16-row chunk of its (zero-padded) 32 encoded inputs, WITHOUT the tensor path: the encoded input
+// z = [x, sin x, cos x] has a diagonal Jacobian (input j only moves rows j, NIN + j, 2 NIN + j), so the 7 tangent columns of this
+// layer cost 3 MAC per neuron and joint instead of the 32 a dense 8-column product spends: 51 (env) / 42 (self) DFMA per neuron and
+// sample instead of 256 MAC on DMMA -- 5 x less work on the shared FP64 pipe for 7 % of the kernel's former DMMA count.
+//   Wc: the warp's slice of the chunk as [k 16][row 32] (row = 8 mb + fr: the lane's D-fragment rows)    Zs: [k 32][sample 8]
+// The accumulators have the D-fragment ownership of mlp_chunk (acc[mb][column][e]: row 32 warp + 8 mb + fr, sample 2 fq + e).
+template <int NIN, int CH>
+__device__ __forceinline__ void mlp_layer0_chunk(const double* __restrict__ Wc, const double* __restrict__ Zs, int fr, int fq, double (&acc)[4][8][2]) {
+#pragma unroll
+    for (int kk = 0; kk < MLP_KC; kk++) {
+        constexpr int K0 = CH * MLP_KC;
+        const int k = K0 + kk;
+        if (k < 3 * NIN) {
+            const int kind = k / NIN, src = k - kind * NIN;
+            double w[4];
+#pragma unroll
+            for (int mb = 0; mb < 4; mb++) w[mb] = Wc[kk * 32 + mb * 8 + fr];
+            const double z0 = Zs[k * 8 + 2 * fq], z1 = Zs[k * 8 + 2 * fq + 1];
+#pragma unroll
+            for (int mb = 0; mb < 4; mb++) { acc[mb][0][0] = fma(w[mb], z0, acc[mb][0][0]); acc[mb][0][1] = fma(w[mb], z1, acc[mb][0][1]); }
+            if (src < 7) {
+                // d z_k / d q_src: 1 (x), cos q (sin row), -sin q (cos row)
+                double t0 = 1.0, t1 = 1.0;
+                if (kind == 1) { t0 = Zs[(2 * NIN + src) * 8 + 2 * fq]; t1 = Zs[(2 * NIN + src) * 8 + 2 * fq + 1]; }
+                if (kind == 2) { t0 = -Zs[(NIN + src) * 8 + 2 * fq]; t1 = -Zs[(NIN + src) * 8 + 2 * fq + 1]; }
+#pragma unroll
+                for (int mb = 0; mb < 4; mb++) {
+                    if (kind == 0) { acc[mb][1 + src][0] += w[mb]; acc[mb][1 + src][1] += w[mb]; }
+                    else { acc[mb][1 + src][0] = fma(w[mb], t0, acc[mb][1 + src][0]); acc[mb][1 + src][1] = fma(w[mb], t1, acc[mb][1 + src][1]); }
+                }
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp(MlpArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2* Xs = reinterpret_cast<double2*>(smem_raw);                              // fragment-ordered activation tile
@@ -136,28 +171,22 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp(MlpArgs a) {
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
         const int s0 = tile * MLP_TILE_S;
         for (int net = 0; net < 2; net++) {  // 0: env, 1: self
-            // ---- stage the encoded input X0 (32 rows) : row k = ty of sample tx ----
+            // ---- stage the encoded inputs z = [x, sin x, cos x] of the tile's 8 samples: Zs [k 32][sample 8] (in the idle X tile) ----
             __syncthreads();  // previous users of Xs are done
+            double* Zs = Xd;
             {
                 const int nin = (net == 0) ? 10 : 7;  // raw inputs; encoded rows = 3 * nin
-                const int k = ty, n = s0 + tx;
-                double v[8];
-#pragma unroll
-                for (int c = 0; c < 8; c++) v[c] = 0.0;
-                if (n < a.NS && k < 3 * nin) {
-                    const int src = k % nin, kind = k / nin;  // kind 0: x, 1: sin x, 2: cos x
-                    double xin;
-                    if (src < 7) xin = a.qs[(size_t)src * a.NS + n];
-                    else xin = a.obs[(size_t)(n / a.S) * 4 + (src - 7)];
+                const int src = tid >> 3, sidx = tid & 7, n = s0 + sidx;
+                if (src < nin) {
+                    double xin = 0.0;
+                    if (n < a.NS) xin = (src < 7) ? a.qs[(size_t)src * a.NS + n] : a.obs[(size_t)(n / a.S) * 4 + (src - 7)];
                     double sn, cs;
                     sincos(xin, &sn, &cs);
-                    v[0] = (kind == 0) ? xin : (kind == 1 ? sn : cs);
-                    if (src < 7) v[1 + src] = (kind == 0) ? 1.0 : (kind == 1 ? cs : -sn);
+                    if (n >= a.NS) { xin = 0.0; sn = 0.0; cs = 0.0; }   // samples beyond the batch: zero inputs (results are not stored)
+                    Zs[src * 8 + sidx] = xin; Zs[(nin + src) * 8 + sidx] = sn; Zs[(2 * nin + src) * 8 + sidx] = cs;
                 }
-#pragma unroll
-                for (int j = 0; j < 4; j++) Xs[xl2(k, j, tx)] = make_double2(v[2 * j], v[2 * j + 1]);
             }
-            __syncthreads();  // X0 is in place
+            __syncthreads();  // Z is in place
             const int n_hidden = (net == 0) ? 4 : 1;  // layers producing 256 neurons
             for (int layer = 0; layer < n_hidden; layer++) {
                 double acc[4][8][2];
@@ -165,11 +194,22 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp(MlpArgs a) {
                 for (int mb = 0; mb < 4; mb++)
 #pragma unroll
                     for (int c = 0; c < 8; c++) acc[mb][c][0] = acc[mb][c][1] = 0.0;
-                const int nch = (layer == 0) ? 2 : 16;
-                for (int ch = 0; ch < nch; ch++) {
+                if (layer == 0) {
+                    // encoded input -> 256 neurons on DFMA, exploiting the diagonal encoding Jacobian (mlp_layer0_chunk)
                     next_chunk();
-                    mlp_chunk(Wmine + buf * SLICE2, Xs, ch * (MLP_KC / 4), lane, bslot, acc);
+                    if (net == 0) mlp_layer0_chunk<10, 0>(reinterpret_cast<const double*>(Wmine + buf * SLICE2), Zs, fr, fq, acc);
+                    else mlp_layer0_chunk<7, 0>(reinterpret_cast<const double*>(Wmine + buf * SLICE2), Zs, fr, fq, acc);
                     advance();
+                    next_chunk();
+                    if (net == 0) mlp_layer0_chunk<10, 1>(reinterpret_cast<const double*>(Wmine + buf * SLICE2), Zs, fr, fq, acc);
+                    else mlp_layer0_chunk<7, 1>(reinterpret_cast<const double*>(Wmine + buf * SLICE2), Zs, fr, fq, acc);
+                    advance();
+                } else {
+                    for (int ch = 0; ch < 16; ch++) {
+                        next_chunk();
+                        mlp_chunk(Wmine + buf * SLICE2, Xs, ch * (MLP_KC / 4), lane, bslot, acc);
+                        advance();
+                    }
                 }
                 // bias + ReLU mask, then the tile becomes the next layer's input
                 const double* bias = a.bias + ((net == 0) ? (MLP_BIAS_ENV + layer * 256) : MLP_BIAS_SELF0);
@@ -311,12 +351,22 @@ inline void pack_mlp_weights(const double* const env_W[5], const double* const s
                                 *o++ = (k < in_dim) ? W[(size_t)row * in_dim + k] : 0.0;
                             }
     };
+    // first layers (direct DFMA path, mlp_layer0_chunk): chunk = 16 encoded inputs: [warp 8][k 16][row 32] = W[32 warp + row][k0 + k], zero-padded to 32
+    auto pack_l0 = [&](const double* W, int in_dim, double*& o) {
+        for (int k0 = 0; k0 < 32; k0 += MLP_KC)
+            for (int warp = 0; warp < 8; warp++)
+                for (int kk = 0; kk < MLP_KC; kk++)
+                    for (int row = 0; row < 32; row++) {
+                        const int k = k0 + kk;
+                        *o++ = (k < in_dim) ? W[(size_t)(32 * warp + row) * in_dim + k] : 0.0;
+                    }
+    };
     double* o = out;
-    pack256(env_W[0], 30, 32, o);
+    pack_l0(env_W[0], 30, o);
     pack256(env_W[1], 256, 256, o);
     pack256(env_W[2], 256, 256, o);
     pack256(env_W[3], 256, 256, o);
-    pack256(self_W[0], 21, 32, o);
+    pack_l0(self_W[0], 21, o);
     for (int ch = 0; ch < 4; ch++)
         for (int warp = 0; warp < 8; warp++)
             for (int kp = 0; kp < 8; kp++)
