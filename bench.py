@@ -239,7 +239,7 @@ def setup_config(M, name, B, N, local, rank):
         over = {"model.tol_envcol": 1.0, "model.tol_sing": 0.018, "model.desired_ee_velocity": 0.1}
     if name == "c5":
         over = {"sqp.eps_prim": 0.01}
-    mpc = M.BatchMPC(B, N, device=local, qp_eps=float(os.environ.get("MPCC_BENCH_QP_EPS", "0")))  # 0 = library default; env: diagnostic sweeps only
+    mpc = M.BatchMPC(B, N, device=local, qp_eps=float(os.environ.get("MPCC_BENCH_QP_EPS", "0")), flags=int(os.environ.get("MPCC_BENCH_FLAGS", "0")))  # 0 = library default; env: diagnostic sweeps only
     mpc.load_nn()
     base = M.load_default_params(overrides=over)
     seed = {"c2": 0, "c3": 1, "c4": 2, "c5": 3}[name] + 1000 * rank

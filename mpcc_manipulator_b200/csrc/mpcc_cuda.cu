@@ -10,6 +10,7 @@
 #include "dev_sqp.cuh"
 #include "cycle_args.h"
 #include "mlp_kernel.cuh"
+#include "mlp_oz_kernel.cuh"
 #include "host/params_io.h"
 #include "host/track_fit.h"
 
@@ -211,6 +212,10 @@ struct mpcc_cuda_handle {
     int32_t *d_hist = nullptr, *d_order = nullptr;
     double* d_wws = nullptr; size_t wws_per = 0, wsm_per = 0;  // warp-kernel workspace (doubles per instance / per warp)
     double *d_wpack = nullptr, *d_bias = nullptr, *d_w_out_env = nullptr, *d_w_out_self = nullptr;
+    double *d_oz_dpack = nullptr, *d_oz_rowscale = nullptr;  // int8-split MLP kernel (mlp_oz_kernel.cuh)
+    uint8_t* d_oz_wq = nullptr;
+    long long* d_oz_dbg = nullptr;
+    bool mlp_oz = false;
     int64_t launches = 0;
     bool profiling = false;
     bool use_cta = false;   // SQP kernel family of this handle: k_sqp_cta (one CTA per instance) or k_sqp_warp
@@ -272,7 +277,14 @@ static int launch_robot_data(mpcc_cuda_handle* h, const double* d_obs, int S_for
     m.qs = h->d_qs; m.obs = d_obs; m.rb = h->d_rb; m.NS = NS; m.S = S_for_obs;
     m.n_tiles = (NS + MLP_TILE_S - 1) / MLP_TILE_S;
     int grid = m.n_tiles < h->num_sms ? m.n_tiles : h->num_sms;
-    k_mlp<<<grid, MLP_THREADS, MLP_SMEM_BYTES, h->stream>>>(m);
+    if (h->mlp_oz) {
+        MlpOzArgs oa;
+        oa.m = m; oa.m.wpack = h->d_oz_dpack; oa.wq = h->d_oz_wq; oa.rowscale = h->d_oz_rowscale; oa.dbg = h->d_oz_dbg; oa.dbg_flags = (h->cfg.reserved >> 5) & 3;
+        if (h->cfg.reserved & 128) grid = 16;  // experiment: few CTAs (is the weight stream limited per SM or by the whole chip's L2 traffic?)
+        k_mlp_oz<<<grid, MLP_THREADS, OZ_SMEM_BYTES, h->stream>>>(oa);
+    } else {
+        k_mlp<<<grid, MLP_THREADS, MLP_SMEM_BYTES, h->stream>>>(m);
+    }
     h->launches += 2;
     CK(cudaGetLastError());
     return MPCC_OK;
@@ -343,11 +355,15 @@ static int create_impl(mpcc_cuda_handle* h, const mpcc_cuda_config* cfg) {
     A(h->alloc(&h->d_status, B)); A(h->alloc(&h->d_iters, B)); A(h->alloc(&h->d_ok, B)); A(h->alloc(&h->d_qp_iters, B)); A(h->alloc(&h->d_qp_fail, B)); A(h->alloc(&h->d_accept, B)); A(h->alloc(&h->d_sqp_ns, 4 * B)); A(h->alloc(&h->d_hist, B)); A(h->alloc(&h->d_order, B + 1));
     A(h->alloc(&h->d_wpack, (size_t)MLP_NCHUNK * MLP_CHUNK_D)); A(h->alloc(&h->d_bias, MLP_BIAS_TOTAL));
     A(h->alloc(&h->d_w_out_env, 9 * 256)); A(h->alloc(&h->d_w_out_self, 64));
+    A(h->alloc(&h->d_oz_dpack, (size_t)OZ_NDCHUNK * OZ_DCHUNK_D)); A(h->alloc(&h->d_oz_rowscale, 3 * 256)); A(h->alloc(&h->d_oz_wq, (size_t)OZ_CHUNKS_PER_TILE * OZ_CHUNK));
+    h->mlp_oz = (h->cfg.reserved & 8) != 0;
+    if (h->cfg.reserved & 16) A(h->alloc(&h->d_oz_dbg, 8));
     if (ae != cudaSuccess) return fail(MPCC_ERR_CUDA, std::string("device allocation failed: ") + cudaGetErrorString(ae));
     std::vector<double> dummy(B * 4);
     for (size_t b = 0; b < B; b++) { dummy[4 * b] = 3; dummy[4 * b + 1] = 3; dummy[4 * b + 2] = 3; dummy[4 * b + 3] = 0; }  // mpc.cpp:97-100
     CK(cudaMemcpyAsync(h->d_obs_dummy, dummy.data(), dummy.size() * 8, cudaMemcpyHostToDevice, h->stream));
     CK(cudaFuncSetAttribute(k_mlp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(k_mlp_oz, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM_BYTES));
     CK(configure_sqp_warp(h->N));
     CK(configure_sqp_cta());
     // kernel family: one CTA per instance (latency path) when the batch cannot fill the machine with warps anyway
@@ -404,6 +420,12 @@ int mpcc_cuda_upload_nn(mpcc_cuda_handle* h, const double* self_w, const double*
     CK(cudaMemcpyAsync(h->d_bias, bias.data(), bias.size() * 8, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_w_out_env, eW[4], 9 * 256 * 8, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_w_out_self, sW[2], 64 * 8, cudaMemcpyHostToDevice, h->stream));
+    std::vector<double> oz_d((size_t)OZ_NDCHUNK * OZ_DCHUNK_D), oz_rs(3 * 256);
+    std::vector<uint8_t> oz_q((size_t)OZ_CHUNKS_PER_TILE * OZ_CHUNK);
+    pack_mlp_oz_weights(eW, sW, oz_d.data(), oz_q.data(), oz_rs.data());
+    CK(cudaMemcpyAsync(h->d_oz_dpack, oz_d.data(), oz_d.size() * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_oz_rowscale, oz_rs.data(), oz_rs.size() * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_oz_wq, oz_q.data(), oz_q.size(), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->have_nn = true;
     return MPCC_OK;
@@ -769,6 +791,12 @@ int mpcc_cuda_eval_robot_data(mpcc_cuda_handle* h, const double* q, const double
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(rb_out, d_out, (size_t)n * RB_DOUBLES * 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    if (h->d_oz_dbg) {  // diagnostics (reserved bit 4): cycles of CTA 0 of k_mlp_oz per phase
+        long long t[8];
+        CK(cudaMemcpy(t, h->d_oz_dbg, sizeof(t), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "k_mlp_oz CTA 0, %lld tiles: cycles per tile: first layers %lld | split %lld | MMA passes %lld | epilogues %lld | env output %lld | self net %lld || issuer waiting for weight chunks %lld\n", t[6],
+                t[0] / t[6], t[1] / t[6], t[2] / t[6], t[3] / t[6], t[4] / t[6], t[5] / t[6], t[7] / t[6]);
+    }
     return MPCC_OK;
 }
 

@@ -6,7 +6,8 @@ import numpy as np
 import mpcc_manipulator_b200 as M
 from bench import synthetic_inputs, q_home
 B, N = 4096, 20
-mpc = M.BatchMPC(B, N); mpc.load_nn(); mpc.set_params(M.load_default_params())
+import os
+mpc = M.BatchMPC(B, N, flags=int(os.environ.get('MPCC_BENCH_FLAGS', '0'))); mpc.load_nn(); mpc.set_params(M.load_default_params())
 ee = mpc.eval_robot_data(q_home()[None])[0, 7:10]
 mpc.set_tracks(M.load_track_json(None, ee))
 mpc.set_profiling(True)
