@@ -47,7 +47,7 @@ constexpr int OZ_OFF_MISC = OZ_OFF_RING + OZ_RING_BYTES;
 constexpr int OZ_MISC_COLMAX = 0, OZ_MISC_SC = 256, OZ_MISC_COLSCALE = 768, OZ_MISC_BARS = 1280, OZ_MISC_TMEM = 1280 + 8 * (2 * OZ_NSLOT + 1);
 constexpr size_t OZ_SMEM_BYTES = OZ_OFF_MISC + 1536;
 static_assert(OZ_S >= 4 && OZ_S <= 7, "int64 Horner of the accumulators holds up to 7 digits");
-static_assert(OZ_S * 64 <= 512, "accumulators must fit TMEM");
+static_assert(OZ_S * 64 + 4 * (OZ_CHUNK_BYTES / 512) <= 512, "accumulators and the four A buffers must fit TMEM");
 static_assert(OZ_RING_BYTES >= 32768, "the DMMA layers' per-warp rings live in the ring region");
 static_assert(OZ_SMEM_BYTES <= 232448, "shared memory");
 // DMMA chunk stream of one tile: env L0 (4 chunks of 8 encoded inputs) | self L0 (4) | self L1 (8 chunks of 32 k-steps x 64 neurons); 16 KB each
@@ -79,6 +79,14 @@ __device__ __forceinline__ void oz_mma_i8(uint32_t tmem_d, uint64_t adesc, uint6
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc),
                  "r"(idesc), "r"(acc)
                  : "memory");
+}
+__device__ __forceinline__ void oz_mma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {  // A operand in TMEM
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc),
+                 "r"(idesc), "r"(acc)
+                 : "memory");
+}
+__device__ __forceinline__ void oz_utccp(uint32_t tmem_dst, uint64_t sdesc) {  // 128 rows x 32 bytes, shared memory (canonical K-major core matrices) -> 8 TMEM columns
+    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;\n" ::"r"(tmem_dst), "l"(sdesc) : "memory");
 }
 __device__ __forceinline__ void oz_commit(uint32_t bar) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory"); }
 __device__ __forceinline__ bool oz_elect_one() {
@@ -174,13 +182,19 @@ __device__ __noinline__ long long oz_issue_pass(uint32_t tmem, uint32_t ring_add
         const uint64_t ad = oz_desc(ring_addr + slot * OZ_CHUNK, 2048, 128);
         uint64_t bd = bd0 + (uint64_t)((kc * (OZ_KCH * 16)) >> 4);
         if (oz_elect_mask(self_mask)) {  // re-establishes "one thread" for the compiler after the wait loop (see oz_mbar_wait_asm)
-            for (int g = i; g < OZ_S; g++, bd += (uint64_t)(OZ_PLANE >> 4)) {  // planes j = 0 .. S-1-i, accumulator g = i + j
-                oz_mma_i8(tmem + g * 64, ad, bd, IDESC, (touched >> g) & 1u);
+            // the chunk goes to TMEM once (tcgen05.cp, 8 columns per 32-k step; 4 rotating buffers behind the accumulators) and the MMAs take A from
+            // there: shared memory is read once per chunk instead of once per MMA (4 KB each), and the ring slot is free as soon as the copy is done.
+            // Copies and MMAs execute in issue order, so a buffer is not overwritten before the MMAs issued earlier have read it.
+            const uint32_t ta = tmem + OZ_S * 64 + (n & 3u) * (OZ_KCH / 4);
 #pragma unroll
-                for (int ks = 1; ks < OZ_KCH / 32; ks++) oz_mma_i8(tmem + g * 64, ad + (uint64_t)((ks * 4096) >> 4), bd + (uint64_t)((ks * 512) >> 4), IDESC, 1u);
+            for (int ks = 0; ks < OZ_KCH / 32; ks++) oz_utccp(ta + ks * 8, ad + (uint64_t)((ks * 4096) >> 4));
+            oz_commit(bar_empty + 8 * slot);
+            for (int g = i; g < OZ_S; g++, bd += (uint64_t)(OZ_PLANE >> 4)) {  // planes j = 0 .. S-1-i, accumulator g = i + j
+                oz_mma_i8_ts(tmem + g * 64, ta, bd, IDESC, (touched >> g) & 1u);
+#pragma unroll
+                for (int ks = 1; ks < OZ_KCH / 32; ks++) oz_mma_i8_ts(tmem + g * 64, ta + ks * 8, bd + (uint64_t)((ks * 512) >> 4), IDESC, 1u);
                 touched |= 1u << g;
             }
-            oz_commit(bar_empty + 8 * slot);
             if (pos + 1 == (uint32_t)OZ_CHUNKS_PER_PASS) oz_commit(bar_acc);
         }
     }

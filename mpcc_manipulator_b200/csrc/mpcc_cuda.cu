@@ -356,7 +356,7 @@ static int create_impl(mpcc_cuda_handle* h, const mpcc_cuda_config* cfg) {
     A(h->alloc(&h->d_wpack, (size_t)MLP_NCHUNK * MLP_CHUNK_D)); A(h->alloc(&h->d_bias, MLP_BIAS_TOTAL));
     A(h->alloc(&h->d_w_out_env, 9 * 256)); A(h->alloc(&h->d_w_out_self, 64));
     A(h->alloc(&h->d_oz_dpack, (size_t)OZ_NDCHUNK * OZ_DCHUNK_D)); A(h->alloc(&h->d_oz_rowscale, 3 * 256)); A(h->alloc(&h->d_oz_wq, (size_t)OZ_CHUNKS_PER_TILE * OZ_CHUNK));
-    h->mlp_oz = (h->cfg.reserved & 8) != 0;
+    h->mlp_oz = (h->cfg.reserved & 8) == 0;  // default: the int8-split tcgen05 kernel; bit 3 selects the fp64 DMMA kernel (k_mlp)
     if (h->cfg.reserved & 16) A(h->alloc(&h->d_oz_dbg, 8));
     if (ae != cudaSuccess) return fail(MPCC_ERR_CUDA, std::string("device allocation failed: ") + cudaGetErrorString(ae));
     std::vector<double> dummy(B * 4);

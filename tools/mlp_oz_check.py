@@ -20,7 +20,7 @@ def main():
     obs = np.c_[rng.uniform(-1, 1, (n, 3)), rng.uniform(0.02, 0.3, n)]
     out = {}
     import os
-    for name, flags in (("dmma", 0),) + tuple((f"oz{f}", 24 + f) for f in map(int, os.environ.get("OZ_EXP", "0").split(","))):
+    for name, flags in (("dmma", 8),) + tuple((f"oz{f}", 16 + f) for f in map(int, os.environ.get("OZ_EXP", "0").split(","))):
         mpc = M.BatchMPC(B, N, flags=flags)
         mpc.load_nn()
         out[name] = mpc.eval_robot_data(q, obs)

@@ -217,6 +217,113 @@ static void rate(int planesB) {
     cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dS);
 }
 
+// A from TMEM: tcgen05.cp.128x256b stages one k-step of A (128 rows x 32 bytes, the same canonical K-major core matrices and descriptor as the
+// shared-memory operand) into 8 TMEM columns, and the MMA takes [tmem] as its A operand.  Correctness against the CPU product, then the rate of
+// one pass of an S-slice layer: per 8 KB chunk two copies (16 columns, 4 rotating buffers beside the S x 64 accumulator columns) and 2 (S - i) MMAs.
+__device__ __forceinline__ void mma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc),
+                 "r"(idesc), "r"(acc)
+                 : "memory");
+}
+__device__ __forceinline__ void utccp_128x256b(uint32_t tmem_dst, uint64_t sdesc) {
+    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;\n" ::"r"(tmem_dst), "l"(sdesc) : "memory");
+}
+template <int S>
+__global__ void __launch_bounds__(128, 1) k_ts(const uint8_t* __restrict__ Ag, const uint8_t* __restrict__ Bg, int32_t* __restrict__ Dg, uint32_t* __restrict__ Adump,
+                                               long long* __restrict__ cycles, int a_bytes, int b_bytes, int mode, int reps) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    unsigned char* As = smem;
+    unsigned char* Bs = smem + a_bytes;
+    for (int i = threadIdx.x * 16; i < a_bytes; i += blockDim.x * 16) *reinterpret_cast<uint4*>(As + i) = *reinterpret_cast<const uint4*>(Ag + i);
+    for (int i = threadIdx.x * 16; i < b_bytes; i += blockDim.x * 16) *reinterpret_cast<uint4*>(Bs + i) = *reinterpret_cast<const uint4*>(Bg + i);
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&bar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+    constexpr uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t tmem_a0 = tmem_base + 448;
+    uint32_t parity = 0;
+    if (mode == 0) {  // one product, K = 64: two copies + two MMAs
+        if (warp == 0 && elect_one()) {
+            const uint64_t ad0 = make_desc(smem_u32(As), 2048, 128), bd0 = make_desc(smem_u32(Bs), 128, 8 * 128);
+            for (int ks = 0; ks < 2; ks++) utccp_128x256b(tmem_a0 + ks * 8, ad0 + (uint64_t)((ks * 4096) >> 4));
+            for (int ks = 0; ks < 2; ks++) mma_i8_ts(tmem_base, tmem_a0 + ks * 8, bd0 + (uint64_t)((ks * 512) >> 4), idesc, ks);
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(&bar)) : "memory");
+        }
+        mbar_wait(smem_u32(&bar), parity);
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+            uint32_t v[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + c0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]),
+                  "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+                  "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr)
+                : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+            for (int j = 0; j < 32; j++) Dg[(size_t)(warp * 32 + lane) * 64 + c0 + j] = (int32_t)v[j];
+        }
+        {   // what the copy left in TMEM: 16 columns of A
+            uint32_t v[32];
+            const uint32_t taddr = tmem_a0 + ((uint32_t)(warp * 32) << 16);
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]),
+                  "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+                  "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr)
+                : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+            for (int j = 0; j < 16; j++) Adump[(warp * 32 + lane) * 16 + j] = v[j];
+        }
+    } else {          // rate of a pass
+        long long t_total = 0;
+        for (int rep = 0; rep < reps; rep++) {
+            long long t0 = clock64();
+            if (warp == 0 && elect_one()) {
+                const uint64_t ad0 = make_desc(smem_u32(As), 2048, 128), bd0 = make_desc(smem_u32(Bs), 128, 32 * 128);
+                int chunk = 0;
+                for (int i = 0; i < S; i++)
+                    for (int kc = 0; kc < 4; kc++, chunk++) {
+                        const uint64_t ad = ad0 + (uint64_t)(((chunk % 6) * 8192) >> 4);
+                        const uint32_t ta = tmem_a0 + (chunk & 3) * 16;
+                        utccp_128x256b(ta, ad);
+                        utccp_128x256b(ta + 8, ad + (uint64_t)(4096 >> 4));
+                        for (int j = 0; j + i < S; j++) {
+                            const uint64_t bd = bd0 + (uint64_t)((j * 64 * 256 + kc * 1024) >> 4);
+                            const uint32_t d = tmem_base + (i + j) * 64;
+                            mma_i8_ts(d, ta, bd, idesc, (i > 0 || kc > 0) ? 1u : 0u);
+                            mma_i8_ts(d, ta + 8, bd + (uint64_t)(512 >> 4), idesc, 1u);
+                        }
+                    }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(&bar)) : "memory");
+            }
+            mbar_wait(smem_u32(&bar), parity);
+            parity ^= 1;
+            if (threadIdx.x == 0) t_total += clock64() - t0;
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        }
+        if (threadIdx.x == 0) cycles[0] = t_total;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
 // canonical no-swizzle layouts (bytes), int8
 static int off_kmajor(int mn, int k, int lbo, int sbo) { return (mn % 8) * 16 + (mn / 8) * sbo + (k % 16) + (k / 16) * lbo; }
 static int off_mnmajor(int mn, int k, int lbo, int sbo) { return (mn % 16) + (mn / 16) * sbo + (k % 8) * 16 + (k / 8) * lbo; }
@@ -303,5 +410,50 @@ int main() {
     rate<128, 7>(4);
     rate<256, 7>(2);
     rate<32, 7>(7);
+
+    // ---------------- 3. A operand from TMEM (tcgen05.cp + .ts MMA) ----------------
+    {
+        const int A_LBO2 = 2048, A_SBO2 = 128;
+        std::vector<uint8_t> A((size_t)M * K), B((size_t)N * K);
+        for (int r = 0; r < M; r++)
+            for (int k = 0; k < K; k++) A[off_kmajor(r, k, A_LBO2, A_SBO2)] = (uint8_t)a[r * K + k];
+        for (int n = 0; n < N; n++)
+            for (int k = 0; k < K; k++) B[off_mnmajor(n, k, 128, (K / 8) * 128)] = (uint8_t)b[n * K + k];
+        uint8_t *dA, *dB; int32_t* dD; uint32_t* dAd; long long* dC;
+        CK(cudaMalloc(&dA, A.size())); CK(cudaMalloc(&dB, B.size())); CK(cudaMalloc(&dD, M * N * 4)); CK(cudaMalloc(&dAd, 128 * 16 * 4)); CK(cudaMalloc(&dC, 16));
+        CK(cudaMemcpy(dA, A.data(), A.size(), cudaMemcpyHostToDevice)); CK(cudaMemcpy(dB, B.data(), B.size(), cudaMemcpyHostToDevice));
+        CK(cudaMemset(dD, 0xff, M * N * 4));
+        CK(cudaFuncSetAttribute(k_ts<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        k_ts<7><<<1, 128, A.size() + B.size()>>>(dA, dB, dD, dAd, dC, (int)A.size(), (int)B.size(), 0, 1);
+        CK(cudaDeviceSynchronize());
+        std::vector<int32_t> D(M * N); std::vector<uint32_t> Ad(128 * 16);
+        CK(cudaMemcpy(D.data(), dD, M * N * 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(Ad.data(), dAd, 128 * 16 * 4, cudaMemcpyDeviceToHost));
+        int bad = 0;
+        for (int i = 0; i < M * N; i++) bad += D[i] != ref[i];
+        printf("A from TMEM (tcgen05.cp.128x256b + .ts MMA): %d / %d mismatches (D[0]=%d ref %d)\n", bad, M * N, D[0], ref[0]);
+        // how the copy laid A out: expect lane r, column c = bytes a[r][4c .. 4c+3] (k-step 0: columns 0..7, k-step 1: columns 8..15)
+        int lay_bad = 0;
+        for (int r = 0; r < 128; r++)
+            for (int c = 0; c < 16; c++) {
+                uint32_t w = 0;
+                for (int q = 0; q < 4; q++) w |= (uint32_t)(uint8_t)a[r * K + 4 * c + q] << (8 * q);
+                lay_bad += Ad[r * 16 + c] != w;
+            }
+        printf("TMEM image of A: %d / 2048 words differ from [lane = row][column = k / 4]; lane 0: %08x %08x %08x %08x  expected %02x%02x%02x%02x ...; lane 1: %08x; lane 8: %08x\n", lay_bad, Ad[0], Ad[1],
+               Ad[2], Ad[8], (uint8_t)a[3], (uint8_t)a[2], (uint8_t)a[1], (uint8_t)a[0], Ad[16], Ad[128]);
+        // rate
+        const int a_bytes = 6 * 8192, b_bytes = 7 * 64 * 256;
+        std::vector<uint8_t> A2(a_bytes), B2(b_bytes);
+        for (auto& v : A2) v = (uint8_t)(rand() % 129 - 64);
+        for (auto& v : B2) v = (uint8_t)(rand() % 129 - 64);
+        uint8_t *dA2, *dB2;
+        CK(cudaMalloc(&dA2, a_bytes)); CK(cudaMalloc(&dB2, b_bytes));
+        CK(cudaMemcpy(dA2, A2.data(), a_bytes, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dB2, B2.data(), b_bytes, cudaMemcpyHostToDevice));
+        k_ts<7><<<1, 128, a_bytes + b_bytes>>>(dA2, dB2, dD, dAd, dC, a_bytes, b_bytes, 1, 8);
+        CK(cudaDeviceSynchronize());
+        long long c[2];
+        CK(cudaMemcpy(c, dC, 16, cudaMemcpyDeviceToHost));
+        printf("rate, A from TMEM: one pass (S = 7: 28 chunks = 56 copies + 224 MMAs of 128 x 64 x 32): %.0f cycles per pass, %.1f per MMA\n", (double)c[0] / 8, (double)c[0] / 8 / 224);
+    }
     return 0;
 }
