@@ -25,6 +25,7 @@
 #include "mlp_kernel.cuh"
 #include <cstdint>
 #include <cmath>
+#include <cstring>
 
 namespace mpcc {
 
@@ -44,8 +45,10 @@ constexpr int OZ_OFF_PLANES = 65536;                   // the planes start on th
 constexpr int OZ_OFF_RING = (OZ_OFF_PLANES + OZ_S * OZ_PLANE > 131072) ? OZ_OFF_PLANES + OZ_S * OZ_PLANE : 131072;
 constexpr int OZ_RING_BYTES = OZ_NSLOT * OZ_CHUNK;     // also holds the per-warp rings of the DMMA layers (8 x 2 x 2 KB)
 constexpr int OZ_OFF_MISC = OZ_OFF_RING + OZ_RING_BYTES;
-constexpr int OZ_MISC_COLMAX = 0, OZ_MISC_SC = 256, OZ_MISC_COLSCALE = 768, OZ_MISC_BARS = 1280, OZ_MISC_TMEM = 1280 + 8 * (2 * OZ_NSLOT + 1);
+constexpr int OZ_NBARS = 2 * OZ_NSLOT + OZ_S + 1;     // full[NSLOT] | empty[NSLOT] | accumulator g complete [S] | accumulators read
+constexpr int OZ_MISC_COLMAX = 0, OZ_MISC_SC = 256, OZ_MISC_COLSCALE = 768, OZ_MISC_BARS = 1280, OZ_MISC_TMEM = 1280 + 8 * OZ_NBARS;
 constexpr size_t OZ_SMEM_BYTES = OZ_OFF_MISC + 1536;
+static_assert(OZ_NSLOT == 6 && OZ_CHUNK == 8192, "three producer warps with two ring slots each");
 static_assert(OZ_S >= 4 && OZ_S <= 7, "int64 Horner of the accumulators holds up to 7 digits");
 static_assert(OZ_S * 64 + 4 * (OZ_CHUNK_BYTES / 512) <= 512, "accumulators and the four A buffers must fit TMEM");
 static_assert(OZ_RING_BYTES >= 32768, "the DMMA layers' per-warp rings live in the ring region");
@@ -53,12 +56,65 @@ static_assert(OZ_SMEM_BYTES <= 232448, "shared memory");
 // DMMA chunk stream of one tile: env L0 (4 chunks of 8 encoded inputs) | self L0 (4) | self L1 (8 chunks of 32 k-steps x 64 neurons); 16 KB each
 constexpr int OZ_DCHUNK_D = 2048;
 constexpr int OZ_NDCHUNK = 16;
-// weight plane consumed at position pi of a pass: heavy (low i: S - i products) and light planes alternate, so the stream's demand is even
-constexpr int oz_order(int pi) { return (pi & 1) ? OZ_S - 1 - pi / 2 : pi / 2; }
+constexpr int OZ_WOUT_D = 9 * 256;      // env output layer, appended to the DMMA stream: rows 0..7 in A-fragment order | row 8
+constexpr int OZ_OFF_WOUT = 131072;     // its place in shared memory: above the fp64 tile, in the (by then dead) digit planes
+static_assert(OZ_OFF_WOUT + OZ_WOUT_D * 8 <= OZ_OFF_RING, "output-layer weights must fit between the tile and the ring");
+// weight plane consumed at position pi of a pass: ascending, so that accumulator g (products i + j = g) is complete as soon as plane g is done
+// and the epilogue warps can fold it into their Horner sums while the later planes are still being multiplied
+constexpr int oz_order(int pi) { return pi; }
 constexpr long long oz_bias_const() {  // 64 on each of the lower S - 1 digits: makes them unsigned fields (the top digit stays signed)
     long long c = 0;
     for (int t = 0; t < OZ_S - 1; t++) c += 64LL << (7 * t);
     return c;
+}
+
+
+// ---- scalar arithmetic of the split, shared by the kernel and the host emulation of the CPU test tier (tests/emul) ----
+#if defined(__CUDACC__)
+#define OZ_HD __host__ __device__ __forceinline__
+#else
+#define OZ_HD inline
+#endif
+OZ_HD double oz_bits_to_double(unsigned long long b) {
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)b);
+#else
+    double d; std::memcpy(&d, &b, 8); return d;
+#endif
+}
+OZ_HD long long oz_double_to_bits(double d) {
+#if defined(__CUDA_ARCH__)
+    return __double_as_longlong(d);
+#else
+    long long b; std::memcpy(&b, &d, 8); return b;
+#endif
+}
+// column scales from the high word of the column's largest |entry|: sc = 2^(7 S - e_c), cs = 2^(e_c), e_c = exponent + 2 (so |x| 2^(-e_c) < 1/2);
+// an all-zero (or denormal-range) column gets sc = 0: every digit 0
+OZ_HD void oz_col_scales(uint32_t hi, double& sc, double& cs) {
+    const int be = (int)(hi >> 20);  // biased exponent
+    sc = 0.0; cs = 1.0;
+    if (be >= 7 * OZ_S && be <= 2040) {
+        sc = oz_bits_to_double((unsigned long long)(2044 + 7 * OZ_S - be) << 52);
+        cs = oz_bits_to_double((unsigned long long)(be + 2) << 52);
+    }
+}
+// q' = rint(x sc) + bias constant: rint by the magic-number addition (|x sc| < 2^48), so the lower S - 1 digits are the unsigned 7-bit fields of
+// q' minus 64 and the top digit is its arithmetic shift
+OZ_HD long long oz_quantize(double x, double sc) {
+#if defined(__CUDA_ARCH__)
+    const double t = fma(x, sc, 6755399441055744.0);
+#else
+    const double t = std::fma(x, sc, 6755399441055744.0);
+#endif
+    return oz_double_to_bits(t) - 0x4338000000000000LL + oz_bias_const();
+}
+OZ_HD int oz_digit(long long q, int t) { return (t < OZ_S - 1) ? (int)((q >> (7 * t)) & 127) - 64 : (int)(q >> (7 * (OZ_S - 1))); }  // digit of weight 128^t
+// where digit plane i of W[r][k] sits in the packed stream (byte index)
+inline size_t oz_wq_index(int layer, int r, int k, int i) {
+    const int mb = r / 128, rr = r % 128, kk = k % OZ_KCH;
+    const size_t chunk = (size_t)layer * OZ_CHUNKS_PER_LAYER + (size_t)(mb * OZ_S + i) * OZ_CPP + k / OZ_KCH;
+    return chunk * OZ_CHUNK + (rr % 8) * 16 + (rr / 8) * 128 + (kk % 16) + (kk / 16) * 2048;
 }
 
 struct MlpOzArgs {
@@ -105,6 +161,7 @@ __device__ __forceinline__ void oz_mbar_wait(uint32_t bar, uint32_t parity) {
     while (true) {
         asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
         if (done) break;
+        __nanosleep(64);  // waiting warps must not flood the shared-memory pipe the tensor core reads its operands through
         if (clock64() - t0 > 4000000000LL) __trap();  // two seconds: a protocol error must end the kernel, not hang the GPU
     }
 }
@@ -155,55 +212,178 @@ __device__ __forceinline__ void oz_layer0_chunk(const double* __restrict__ Wc, c
 
 
 // One MMA pass, issued by one thread: the S (S + 1) / 2 digit products of 128 neurons x 64 columns x 256 k, chunk by chunk as the weight digits
-// arrive.  Out of line on purpose: the kernel around it runs at the register limit, and a spill reloaded inside this loop costs more than the
-// 53 cycles an MMA takes.  Returns the cycles spent waiting for chunks.
-__device__ __noinline__ long long oz_issue_pass(uint32_t tmem, uint32_t ring_addr, uint32_t planes_addr, uint32_t bar_full, uint32_t bar_empty, uint32_t bar_acc, uint32_t n,
-                                               uint32_t rot, bool no_stream) {
+// arrive, planes in ascending order; after the last chunk of plane i a commit on `group` barrier i tells the epilogue warps that accumulator i is
+// complete.  Fully unrolled: every descriptor offset, accumulator address and accumulate flag is an immediate (rolled: +20 %).  Called by the whole of warp 0,
+// converged; the elections inside tell the compiler that exactly one thread issues (otherwise it wraps every MMA in an election loop, +40 cycles).
+__device__ __noinline__ long long oz_issue_pass(uint32_t tmem, uint32_t ring_addr, uint32_t planes_addr, uint32_t bar_full, uint32_t bar_empty, uint32_t bar_group, uint32_t bar_tfree,
+                                          uint32_t n, uint32_t tfree_wait, bool no_stream, bool no_fence) {
     constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);  // s32 += s8 (K-major) x s8 (MN-major), M 128, N 64
-    // called by the whole of warp 0, converged: the election inside tells the compiler that exactly one thread issues (no per-MMA election loop)
-    long long waited = 0;
-    // warp-uniform copies of the arguments: tcgen05.mma takes its operands from uniform registers, and values the compiler cannot prove uniform
-    // cost an election loop around every MMA (~40 cycles each)
+    // warp-uniform copies of the arguments (tcgen05 operands live in uniform registers)
     tmem = __shfl_sync(0xffffffffu, tmem, 0); ring_addr = __shfl_sync(0xffffffffu, ring_addr, 0); planes_addr = __shfl_sync(0xffffffffu, planes_addr, 0);
-    bar_full = __shfl_sync(0xffffffffu, bar_full, 0); bar_empty = __shfl_sync(0xffffffffu, bar_empty, 0); bar_acc = __shfl_sync(0xffffffffu, bar_acc, 0);
-    n = __shfl_sync(0xffffffffu, n, 0); rot = __shfl_sync(0xffffffffu, rot, 0);
+    bar_full = __shfl_sync(0xffffffffu, bar_full, 0); bar_empty = __shfl_sync(0xffffffffu, bar_empty, 0); bar_group = __shfl_sync(0xffffffffu, bar_group, 0);
+    bar_tfree = __shfl_sync(0xffffffffu, bar_tfree, 0); n = __shfl_sync(0xffffffffu, n, 0); tfree_wait = __shfl_sync(0xffffffffu, tfree_wait, 0);
+    long long waited = 0;
     if (oz_elect_one()) {
-    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-    const uint32_t self_mask = 1u << (threadIdx.x & 31);
-    uint32_t touched = 0;
-    uint32_t posr = rot;
-    const uint64_t bd0 = oz_desc(planes_addr, 128, 4096);
-    for (uint32_t pos = 0; pos < (uint32_t)OZ_CHUNKS_PER_PASS; pos++, n++) {
-        const int i = oz_order((int)(posr / OZ_CPP)), kc = (int)(posr % OZ_CPP);
-        posr = (posr + 1 == (uint32_t)OZ_CHUNKS_PER_PASS) ? 0u : posr + 1;
-        const uint32_t slot = n % OZ_NSLOT;
-        if (!no_stream) oz_mbar_wait_asm(bar_full + 8 * slot, (n / OZ_NSLOT) & 1);
+        const uint32_t self_mask = 1u << (threadIdx.x & 31);
+        const long long tw0 = clock64();
+        if (tfree_wait) oz_mbar_wait_asm(bar_tfree, tfree_wait - 1);  // the epilogue warps have read the previous pass's accumulators
+        waited = clock64() - tw0;
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        const uint64_t ad = oz_desc(ring_addr + slot * OZ_CHUNK, 2048, 128);
-        uint64_t bd = bd0 + (uint64_t)((kc * (OZ_KCH * 16)) >> 4);
-        if (oz_elect_mask(self_mask)) {  // re-establishes "one thread" for the compiler after the wait loop (see oz_mbar_wait_asm)
-            // the chunk goes to TMEM once (tcgen05.cp, 8 columns per 32-k step; 4 rotating buffers behind the accumulators) and the MMAs take A from
-            // there: shared memory is read once per chunk instead of once per MMA (4 KB each), and the ring slot is free as soon as the copy is done.
-            // Copies and MMAs execute in issue order, so a buffer is not overwritten before the MMAs issued earlier have read it.
-            const uint32_t ta = tmem + OZ_S * 64 + (n & 3u) * (OZ_KCH / 4);
+        uint32_t slot = n % OZ_NSLOT, ph = (n / OZ_NSLOT) & 1;
+        const uint64_t bd0 = oz_desc(planes_addr, 128, 4096);
 #pragma unroll
-            for (int ks = 0; ks < OZ_KCH / 32; ks++) oz_utccp(ta + ks * 8, ad + (uint64_t)((ks * 4096) >> 4));
-            oz_commit(bar_empty + 8 * slot);
-            for (int g = i; g < OZ_S; g++, bd += (uint64_t)(OZ_PLANE >> 4)) {  // planes j = 0 .. S-1-i, accumulator g = i + j
-                oz_mma_i8_ts(tmem + g * 64, ta, bd, IDESC, (touched >> g) & 1u);
+        for (int i = 0; i < OZ_S; i++) {
 #pragma unroll
-                for (int ks = 1; ks < OZ_KCH / 32; ks++) oz_mma_i8_ts(tmem + g * 64, ta + ks * 8, bd + (uint64_t)((ks * 512) >> 4), IDESC, 1u);
-                touched |= 1u << g;
+            for (int kc = 0; kc < OZ_CPP; kc++) {
+                const long long tf0 = clock64();
+                if (!no_stream) oz_mbar_wait_asm(bar_full + 8 * slot, ph);
+                waited += clock64() - tf0;
+                if (!no_fence) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // the chunk was written through the generic proxy (cp.async)
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                const uint64_t ad = oz_desc(ring_addr + slot * OZ_CHUNK, 2048, 128);
+                if (oz_elect_mask(self_mask)) {  // re-establishes "one thread" for the compiler after the wait loop
+                    // the chunk goes to TMEM once (tcgen05.cp, 8 columns per 32-k step; 4 rotating buffers behind the accumulators) and the MMAs take
+                    // A from there: shared memory is read once per chunk instead of once per MMA, and the ring slot is free as soon as the copy is
+                    // done.  Copies and MMAs execute in issue order, so a buffer is not overwritten before the MMAs issued earlier have read it.
+                    const uint32_t ta = tmem + OZ_S * 64 + ((i * OZ_CPP + kc) & 3) * (OZ_KCH / 4);
+#pragma unroll
+                    for (int ks = 0; ks < OZ_KCH / 32; ks++) oz_utccp(ta + ks * 8, ad + (uint64_t)((ks * 4096) >> 4));
+                    oz_commit(bar_empty + 8 * slot);
+#pragma unroll
+                    for (int j = 0; j + i < OZ_S; j++) {  // accumulator g = i + j
+                        const uint64_t bd = bd0 + (uint64_t)((j * OZ_PLANE + kc * (OZ_KCH * 16)) >> 4);
+#pragma unroll
+                        for (int ks = 0; ks < OZ_KCH / 32; ks++)
+                            oz_mma_i8_ts(tmem + (i + j) * 64, ta + ks * 8, bd + (uint64_t)((ks * 512) >> 4), IDESC, (i > 0 || kc > 0 || ks > 0) ? 1u : 0u);
+                    }
+                    if (kc == OZ_CPP - 1) oz_commit(bar_group + 8 * i);
+                }
+                slot = (slot + 1 == (uint32_t)OZ_NSLOT) ? 0u : slot + 1;
+                ph ^= (slot == 0) ? 1u : 0u;
             }
-            if (pos + 1 == (uint32_t)OZ_CHUNKS_PER_PASS) oz_commit(bar_acc);
         }
     }
-    }
     __syncwarp();
-    return waited;
+}
+
+
+// Weight-digit stream of one producer warp (pw = 0..2): its chunks m = pw (mod 3) in [begin, end) of the CTA's stream, global -> ring slot
+// m % NSLOT by 16-byte cp.async (LDGSTS), fully asynchronous: after the copies of a chunk every lane issues cp.async.mbarrier.arrive.noinc on
+// the slot's `full` barrier, which arrives when that lane's copies have landed -- no wait and no registers on the producer side, both of the
+// warp's slots in flight.  (The pattern of CUTLASS' sm100 cp.async + UMMA mainloop; the MMA issuer adds a proxy fence after its wait.)
+// Measured alternatives: cp.async.bulk (one 8 / 16 KB bulk copy per chunk completes every ~1300 / ~1700 cycles however many are outstanding:
+// 6 .. 10 B/cycle, a third of what the MMAs consume); wait_group + fence + arrive by the copying threads (one chunk in flight per warp, six
+// producer warps); copies through registers in an out-of-line function (the ABI leaves it half the register file: the loads were spilled at once).
+__device__ __forceinline__ void oz_produce_range(const uint8_t* __restrict__ wq, unsigned char* ring, uint32_t bar_full, uint32_t bar_empty, uint32_t begin, uint32_t end,
+                                                uint32_t tile_first, uint32_t pw, uint32_t lane) {
+    for (uint32_t m = begin + (pw + 3u - (begin - tile_first) % 3u) % 3u; m < end; m += 3) {
+        const uint32_t slot = m % OZ_NSLOT, use = m / OZ_NSLOT;
+        if (use > 0) oz_mbar_wait(bar_empty + 8 * slot, (use - 1) & 1);  // the slot's previous tenant has been copied to TMEM
+        const unsigned char* src = wq + (size_t)(m % OZ_CHUNKS_PER_TILE) * OZ_CHUNK + lane * 16;
+        unsigned char* dst = ring + slot * OZ_CHUNK + lane * 16;
+#pragma unroll
+        for (int i = 0; i < OZ_CHUNK / 512; i++) cp_async16(dst + i * 512, src + i * 512);
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(bar_full + 8 * slot) : "memory");
+    }
 }
 
 __device__ __forceinline__ uint32_t oz_abs_hi(double v) { return (uint32_t)__double2hiint(v) & 0x7FFFFFFFu; }
+
+// Split of one layer's input: thread = neuron k; its 64 fp64 activations -> S digit planes of the B operand ([n 64][k 256] int8, MN-major core
+// matrices: 16 consecutive columns of a neuron are one 16-byte store).  Column exponents come from the maxima the producing layer left in colmax.
+// All 256 threads call it (it synchronises the CTA).
+__device__ __forceinline__ void oz_split(const double2* Xs, unsigned char* planes, uint32_t* colmax, double* s_sc, double* s_colscale, int tid) {
+    if (tid < 64) {
+        double sc, cs;
+        oz_col_scales(colmax[tid], sc, cs);
+        s_sc[tid] = sc;
+        s_colscale[tid] = cs;
+        colmax[tid] = 0;
+    }
+    __syncthreads();
+    uint32_t w[OZ_S][16];
+#pragma unroll
+    for (int i = 0; i < OZ_S; i++)
+#pragma unroll
+        for (int q = 0; q < 16; q++) w[i][q] = 0;
+    const int k = tid;
+#pragma unroll
+    for (int s = 0; s < 8; s++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const double2 x2 = Xs[xl2(k, j, s)];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int c = 8 * s + 2 * j + h;             // column; 16-column group c >> 4, byte c & 15
+                const int word = (c >> 4) * 4 + ((c & 15) >> 2), sh = 8 * (c & 3);
+                const long long q = oz_quantize(h ? x2.y : x2.x, s_sc[c]);
+#pragma unroll
+                for (int t = 0; t < OZ_S - 1; t++) w[OZ_S - 1 - t][word] |= ((uint32_t)(q >> (7 * t)) & 127u) << sh;
+                w[0][word] |= ((uint32_t)(q >> (7 * (OZ_S - 1))) & 255u) << sh;   // top digit: signed
+            }
+        }
+    __syncthreads();  // every thread holds its row: the planes may overwrite rows 128..255 of the tile
+#pragma unroll
+    for (int i = 0; i < OZ_S; i++)
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            uint4 v = make_uint4(w[i][4 * g], w[i][4 * g + 1], w[i][4 * g + 2], w[i][4 * g + 3]);
+            if (i > 0) {  // unsigned field u -> signed digit u - 64, per byte
+                v.x = ((v.x | 0x80808080u) - 0x40404040u) ^ 0x80808080u; v.y = ((v.y | 0x80808080u) - 0x40404040u) ^ 0x80808080u;
+                v.z = ((v.z | 0x80808080u) - 0x40404040u) ^ 0x80808080u; v.w = ((v.w | 0x80808080u) - 0x40404040u) ^ 0x80808080u;
+            }
+            *reinterpret_cast<uint4*>(planes + i * OZ_PLANE + g * 4096 + (k >> 3) * 128 + (k & 7) * 16) = v;
+        }
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy writes -> tensor-core (async-proxy) reads
+    __syncthreads();
+}
+
+// Epilogue of one pass, all eight warps: warp w reads TMEM lane quadrant w & 3 (neuron = lane) and columns 32 (w >> 2) .. + 31 of the S
+// accumulators, folds them into int64 Horner sums, scales, adds the bias, applies the ReLU mask of the sample's value column to its 8 columns
+// and writes the fp64 tile; the column maxima for the next split are reduced over the warp and kept by the lane that owns the column, one
+// shared-memory atomic per lane at the end.
+__device__ __forceinline__ void oz_epilogue_pass(double2* Xs, uint32_t* colmax, const double* s_colscale, const double* __restrict__ rowscale, const double* __restrict__ bias,
+                                                uint32_t tmem, int mb, int warp, int lane, bool want_colmax) {
+    const int qd = warp & 3, hh = warp >> 2;
+    const int row = mb * 128 + qd * 32 + lane;
+    const double rs = __ldg(rowscale + row), bv = __ldg(bias + row);
+    // Horner with the accumulators taken in pairs: G_g 128 + G_(g+1) still fits int32 (|G_g| <= (g + 1) 2^20), so the 64-bit steps are halved
+    long long acc[32];
+    int pair[32];
+#pragma unroll
+    for (int g = 0; g < OZ_S; g++) {
+        uint32_t v[32];
+        oz_tmem_ld32(tmem + ((uint32_t)(qd * 32) << 16) + g * 64 + hh * 32, v);
+#pragma unroll
+        for (int c = 0; c < 32; c++) {
+            if ((g & 1) == 0 && g + 1 < OZ_S) pair[c] = (int)v[c];
+            else if (g & 1) {
+                pair[c] = pair[c] * 128 + (int)v[c];
+                acc[c] = (g == 1) ? (long long)pair[c] : acc[c] * 16384 + (long long)pair[c];
+            } else acc[c] = (g == 0) ? (long long)(int)v[c] : acc[c] * 128 + (long long)(int)v[c];
+        }
+    }
+    uint32_t mymax = 0;  // lane c: largest |entry| (high word) of column 32 hh + c over this warp's 32 neurons
+#pragma unroll
+    for (int sl = 0; sl < 4; sl++) {
+        const int s = 4 * hh + sl;
+        double y[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) y[c] = (__ll2double_rn(acc[8 * sl + c]) * rs) * s_colscale[8 * s + c];
+        y[0] += bv;
+        const bool on = y[0] > 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) Xs[xl2(row, j, s)] = on ? make_double2(y[2 * j], y[2 * j + 1]) : make_double2(0.0, 0.0);
+        if (want_colmax) {
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                const uint32_t m = __reduce_max_sync(0xffffffffu, on ? oz_abs_hi(y[c]) : 0u);
+                if (lane == 8 * sl + c) mymax = m;
+            }
+        }
+    }
+    if (want_colmax) atomicMax(&colmax[32 * hh + lane], mymax);
+}
 
 __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp_oz(MlpOzArgs oa) {
     const MlpArgs& a = oa.m;
@@ -216,16 +396,18 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp_oz(MlpOzArgs oa) {
     uint32_t* colmax = reinterpret_cast<uint32_t*>(misc + OZ_MISC_COLMAX);   // [64] high word of the largest |entry| of each column of the next split
     double* s_sc = reinterpret_cast<double*>(misc + OZ_MISC_SC);             // [64] 2^(7 S - e_c)
     double* s_colscale = reinterpret_cast<double*>(misc + OZ_MISC_COLSCALE); // [64] 2^(e_c)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(misc + OZ_MISC_BARS);       // full[NSLOT] | empty[NSLOT] | accumulators ready
+    uint64_t* bars = reinterpret_cast<uint64_t*>(misc + OZ_MISC_BARS);       // full[NSLOT] | empty[NSLOT] | accumulator complete [S] | accumulators read
     uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(misc + OZ_MISC_TMEM);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int fr = lane >> 2, fq = lane & 3;
     const int bslot = xslot(fq, fr);
-    const uint32_t bar_full = oz_smem_u32(bars), bar_empty = oz_smem_u32(bars + OZ_NSLOT), bar_acc = oz_smem_u32(bars + 2 * OZ_NSLOT);
+    const uint32_t bar_full = oz_smem_u32(bars), bar_empty = oz_smem_u32(bars + OZ_NSLOT), bar_group = oz_smem_u32(bars + 2 * OZ_NSLOT),
+                   bar_tfree = oz_smem_u32(bars + 2 * OZ_NSLOT + OZ_S);
 
     if (tid == 0) {
-        for (int i = 0; i < 2 * OZ_NSLOT + 1; i++) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar_full + 8 * i), "r"(i < OZ_NSLOT ? 32 : 1) : "memory");
+        for (int i = 0; i < OZ_NBARS; i++)  // arrivals: full = the 32 lanes of the copying warp, empty / group = one tcgen05.commit, read = the 128 epilogue threads
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar_full + 8 * i), "r"(i < OZ_NSLOT ? 32 : (i == OZ_NBARS - 1 ? 128 : 1)) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (tid < 64) colmax[tid] = 0;
@@ -238,66 +420,57 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp_oz(MlpOzArgs oa) {
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const uint32_t tmem = *tmem_ptr_s;
 
-    // ---- per-warp rings of the DMMA layers (k_mlp's scheme, 2 x 2 KB per warp, inside the ring region) ----
-    int p = 0, buf = 0;
+    // ---- per-warp rings of the DMMA / DFMA layers (k_mlp's scheme with three slots of 2 KB per warp, inside the ring region): while chunk p is
+    //      being used, p + 1 and p + 2 are in flight.  The stream pauses after the env net's first layer (chunk 3 of a tile's 16): the ring region
+    //      then belongs to the weight-digit stream until the split layers are done.
     constexpr int SLICE2 = OZ_DCHUNK_D / 2 / 8;  // double2 per warp and chunk
-    double2* Wmine = reinterpret_cast<double2*>(ring) + warp * (2 * SLICE2);
-    auto prefetch = [&](int chunk, int slot) {
-        const double2* src = reinterpret_cast<const double2*>(a.wpack) + ((size_t)chunk * 8 + warp) * SLICE2;
-        double2* dst = Wmine + slot * SLICE2;
+    constexpr uint32_t DSTG = 3;
+    static_assert(8 * DSTG * SLICE2 * 16 <= OZ_RING_BYTES, "per-warp rings must fit the ring region");
+    double2* Wmine = reinterpret_cast<double2*>(ring) + warp * (DSTG * SLICE2);
+    uint32_t p_abs = 0, pi_abs = 0;  // chunks consumed / requested so far (chunk id = counter % OZ_NDCHUNK, slot = counter % DSTG)
+    auto d_topup = [&]() {
+        const uint32_t r = p_abs % OZ_NDCHUNK, base = p_abs - r;
+        const uint32_t lim = (r < 4) ? base + 4 : base + OZ_NDCHUNK + 4;  // never across the pause point
+        while (pi_abs < lim && pi_abs < p_abs + DSTG) {
+            const double2* src = reinterpret_cast<const double2*>(a.wpack) + ((size_t)(pi_abs % OZ_NDCHUNK) * 8 + warp) * SLICE2;
+            double2* dst = Wmine + (pi_abs % DSTG) * SLICE2;
 #pragma unroll
-        for (int i = 0; i < SLICE2 / 32; i++) cp_async16(dst + lane + i * 32, src + lane + i * 32);
-        cp_async_commit();
+            for (int i = 0; i < SLICE2 / 32; i++) cp_async16(dst + lane + i * 32, src + lane + i * 32);
+            cp_async_commit();
+            pi_abs++;
+        }
     };
-    auto next_chunk = [&](bool prefetch_next) {
-        cp_async_wait_all();
+    auto d_wait = [&]() -> const double2* {  // chunk p_abs has landed
+        const uint32_t younger = pi_abs - p_abs - 1;
+        if (younger == 0) asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        else if (younger == 1) asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+        else asm volatile("cp.async.wait_group 2;\n" ::: "memory");
         __syncwarp();
-        if (prefetch_next) prefetch((p + 1) % OZ_NDCHUNK, buf ^ 1);
+        return Wmine + (p_abs % DSTG) * SLICE2;
     };
-    auto advance = [&]() { buf ^= 1; p = (p + 1) % OZ_NDCHUNK; };
-    if ((int)blockIdx.x < a.n_tiles) prefetch(0, 0);
+    auto d_done = [&](bool pause_after) {  // the warp has read chunk p_abs: its slot may be refilled
+        __syncwarp();
+        p_abs++;
+        if (!pause_after) d_topup();
+    };
+    if ((int)blockIdx.x < a.n_tiles) d_topup();
 
     // ---- weight-digit stream (used by the elected lane of warp 0 only) ----
     uint32_t tile_iter = 0;   // tiles this CTA has started: chunk numbers of the stream follow from it (no per-thread state: any lane may be elected)
-    uint32_t n_pass = 0;      // passes waited for so far (parity of the accumulator barrier; every thread counts)
+    uint32_t n_pass = 0;      // passes done so far (parity of the accumulator barriers; every thread counts)
+    uint32_t n_layer = 0;     // split layers done so far (parity of the `accumulators read` barrier)
     const uint32_t ring_addr = oz_smem_u32(ring), planes_addr = oz_smem_u32(planes);
-    // Every CTA walks the chunks of a pass from its own starting point (the integer accumulation is exact in any order), so the CTAs do not
-    // all ask L2 for the same lines at the same moment.
-    const uint32_t rot = (oa.dbg_flags & 2) ? 0u : (blockIdx.x * 11u) % OZ_CHUNKS_PER_PASS;
-    auto src_chunk = [&](uint32_t ml) -> uint32_t { return (ml / OZ_CHUNKS_PER_PASS) * OZ_CHUNKS_PER_PASS + (ml % OZ_CHUNKS_PER_PASS + rot) % OZ_CHUNKS_PER_PASS; };
     const bool no_stream = (oa.dbg_flags & 1) != 0;
-    // Producers: warps 1..NSLOT copy the chunks with 16-byte cp.async (LDGSTS); warp 1 + k owns ring slot k, i.e. the chunks m = k (mod NSLOT) of
-    // the stream, one chunk in flight per warp.  A chunk is handed to the tensor core by its 32 copying lanes: own copies landed (wait_group 0),
-    // proxy fence (generic-proxy writes -> async-proxy reads), arrive on the slot's `full` barrier.  Measured alternatives: cp.async.bulk (one
-    // 8 / 16 KB bulk copy per chunk completes every ~1300 / ~1700 cycles however many are outstanding: 6 .. 10 B/cycle, a third of what the MMAs
-    // consume), and 128 threads sharing every chunk with 5 copy groups in flight per thread (the proxy fence then waits for the younger groups too).
-    uint32_t pm = 0;      // next chunk of the stream this producer warp copies
-    bool pend = false;    // a chunk of this warp is in flight (its slot: (pm - NSLOT) % NSLOT = warp - 1)
-    const bool producer = warp >= 1 && warp <= OZ_NSLOT;
-    auto produce = [&](uint32_t limit, bool final_call) {
-        const uint32_t slot = warp - 1;
-        while (true) {
-            if (pend) {
-                cp_async_wait_all();
-                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar_full + 8 * slot) : "memory");
-                pend = false;
-            }
-            if (pm >= limit) break;
-            const uint32_t use = pm / OZ_NSLOT;
-            if (use > 0) oz_mbar_wait(bar_empty + 8 * slot, (use - 1) & 1);  // the MMAs of the slot's previous tenant are done
-            const unsigned char* src = oa.wq + (size_t)src_chunk(pm % OZ_CHUNKS_PER_TILE) * OZ_CHUNK + lane * 16;
-            unsigned char* dst = ring + slot * OZ_CHUNK + lane * 16;
-#pragma unroll
-            for (int i = 0; i < OZ_CHUNK / 512; i++) cp_async16(dst + i * 512, src + i * 512);
-            cp_async_commit();
-            pend = true;
-            pm += OZ_NSLOT;
-            if (pm >= limit && !final_call) break;  // the last copy stays in flight across the epilogue; the next call completes it first
-        }
-    };
+    // Roles while the split layers run: warp 0 issues the MMAs, warps 1..3 stream the weight digits, warps 4..7 (one TMEM lane quadrant each) are
+    // the epilogue.  Producer warp pw copies the chunks m = pw (mod 3) of the stream -- ring slots pw and pw + 3 -- through registers: 16 x 16
+    // bytes per lane and chunk, two chunks in flight per warp (loads are issued two chunks ahead of their stores).  A chunk is handed to the
+    // tensor core by its 32 lanes: stores done, proxy fence (generic-proxy writes -> async-proxy reads), arrive on the slot's `full` barrier.
+    // Measured alternatives: cp.async.bulk (one 8 / 16 KB bulk copy per chunk completes every ~1300 / ~1700 cycles however many are outstanding:
+    // 6 .. 10 B/cycle, a third of what the MMAs consume); cp.async with several groups in flight per thread (the proxy fence waits for all of them).
+    const bool producer = warp >= 1 && warp <= 3;
     long long dbg_t[7] = {0, 0, 0, 0, 0, 0, 0}, dbg_c = 0, dbg_wait = 0;
     const bool dbg_on = oa.dbg != nullptr && blockIdx.x == 0 && tid == 0;
+#define OZ_MARK(w, e) if (oa.dbg != nullptr && blockIdx.x == 0 && tile_iter == 1 && lane == 0) oa.dbg[8 + (w) * 16 + (e)] = clock64();
 #define OZ_DBG(i) if (dbg_on) { const long long t_ = clock64(); dbg_t[i] += t_ - dbg_c; dbg_c = t_; }
     if (dbg_on) dbg_c = clock64();
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, tile_iter++) {
@@ -329,11 +502,13 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp_oz(MlpOzArgs oa) {
 #pragma unroll
                     for (int c = 0; c < 8; c++) acc[mb][c][0] = acc[mb][c][1] = 0.0;
                 // after the env net's first layer the ring region belongs to the weight-digit stream: no DMMA prefetch across that boundary
-#define OZ_L0_CHUNK(K0, LAST)                                                                                            \
-    next_chunk(!((LAST) && net == 0));                                                                                   \
-    if (net == 0) oz_layer0_chunk<10, K0>(reinterpret_cast<const double*>(Wmine + buf * SLICE2), Zs, fr, fq, acc);         \
-    else oz_layer0_chunk<7, K0>(reinterpret_cast<const double*>(Wmine + buf * SLICE2), Zs, fr, fq, acc);                   \
-    advance();
+#define OZ_L0_CHUNK(K0, LAST)                                                                              \
+    {                                                                                                      \
+        const double* Wc0 = reinterpret_cast<const double*>(d_wait());                                     \
+        if (net == 0) oz_layer0_chunk<10, K0>(Wc0, Zs, fr, fq, acc);                                       \
+        else oz_layer0_chunk<7, K0>(Wc0, Zs, fr, fq, acc);                                                 \
+        d_done((LAST) && net == 0);                                                                        \
+    }
                 OZ_L0_CHUNK(0, false)
                 OZ_L0_CHUNK(8, false)
                 OZ_L0_CHUNK(16, false)
@@ -344,10 +519,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp_oz(MlpOzArgs oa) {
 #pragma unroll
                 for (int mb = 0; mb < 4; mb++) bv[mb] = bias[warp * 32 + mb * 8 + fr];
                 __syncthreads();  // Zs and (env) the DMMA ring slots are free
-                if (net == 0 && producer && !no_stream) {  // the weight-digit stream of this tile starts: one chunk per producer warp
-                    pm = tile_first + (uint32_t)(warp - 1);
-                    produce(tile_first + OZ_NSLOT, false);
-                }
+                if (net == 0 && producer && !no_stream) oz_produce_range(oa.wq, ring, bar_full, bar_empty, tile_first, tile_first + OZ_NSLOT, tile_first, (uint32_t)(warp - 1), (uint32_t)lane);  // the weight-digit stream of this tile starts
                 uint32_t cm[2][8];
 #pragma unroll
                 for (int e = 0; e < 2; e++)
@@ -381,120 +553,50 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp_oz(MlpOzArgs oa) {
             }
             if (net == 0) {
                 // =============== env layers 1..3: int8 split on tcgen05 ===============
+#pragma unroll 1
                 for (int layer = 0; layer < 3; layer++) {
-                    // ---- split: fp64 tile -> S digit planes ----
-                    if (tid < 64) {
-                        const uint32_t hi = colmax[tid];
-                        const int be = (int)(hi >> 20);  // biased exponent of the column's largest entry
-                        double sc = 0.0, cs = 1.0;
-                        if (be >= 7 * OZ_S && be <= 2040) {
-                            sc = __hiloint2double((2044 + 7 * OZ_S - be) << 20, 0);  // 2^(7 S - e_c), e_c = be - 1021
-                            cs = __hiloint2double((be + 2) << 20, 0);                // 2^(e_c)
-                        }
-                        s_sc[tid] = sc;
-                        s_colscale[tid] = cs;
-                        colmax[tid] = 0;
-                    }
-                    __syncthreads();
-                    {
-                        uint32_t w[OZ_S][16];
-#pragma unroll
-                        for (int i = 0; i < OZ_S; i++)
-#pragma unroll
-                            for (int q = 0; q < 16; q++) w[i][q] = 0;
-                        const int k = tid;
-#pragma unroll
-                        for (int s = 0; s < 8; s++)
-#pragma unroll
-                            for (int j = 0; j < 4; j++) {
-                                const double2 x2 = Xs[xl2(k, j, s)];
-#pragma unroll
-                                for (int h = 0; h < 2; h++) {
-                                    const int c = 8 * s + 2 * j + h;             // column; 16-column group c >> 4, byte c & 15
-                                    const int word = (c >> 4) * 4 + ((c & 15) >> 2), sh = 8 * (c & 3);
-                                    const long long q = __double2ll_rn((h ? x2.y : x2.x) * s_sc[c]) + oz_bias_const();
-#pragma unroll
-                                    for (int t = 0; t < OZ_S - 1; t++) w[OZ_S - 1 - t][word] |= ((uint32_t)(q >> (7 * t)) & 127u) << sh;
-                                    w[0][word] |= ((uint32_t)(q >> (7 * (OZ_S - 1))) & 255u) << sh;   // top digit: signed
-                                }
-                            }
-                        __syncthreads();  // every thread holds its row: the planes may overwrite rows 128..255 of the tile
-#pragma unroll
-                        for (int i = 0; i < OZ_S; i++)
-#pragma unroll
-                            for (int g = 0; g < 4; g++) {
-                                uint4 v = make_uint4(w[i][4 * g], w[i][4 * g + 1], w[i][4 * g + 2], w[i][4 * g + 3]);
-                                if (i > 0) {  // unsigned field u -> signed digit u - 64, per byte
-                                    v.x = ((v.x | 0x80808080u) - 0x40404040u) ^ 0x80808080u; v.y = ((v.y | 0x80808080u) - 0x40404040u) ^ 0x80808080u;
-                                    v.z = ((v.z | 0x80808080u) - 0x40404040u) ^ 0x80808080u; v.w = ((v.w | 0x80808080u) - 0x40404040u) ^ 0x80808080u;
-                                }
-                                *reinterpret_cast<uint4*>(planes + i * OZ_PLANE + g * 4096 + (k >> 3) * 128 + (k & 7) * 16) = v;
-                            }
-                        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy writes -> tensor-core (async-proxy) reads
-                        __syncthreads();
-                        OZ_DBG(1)
-                    }
+                    oz_split(Xs, planes, colmax, s_sc, s_colscale, tid);
+                    OZ_DBG(1)
                     for (int mb = 0; mb < 2; mb++) {
-                        // ---- MMA pass: neurons 128 mb .. 128 mb + 127 ----
+                        const uint32_t pass_first = tile_first + (uint32_t)((layer * 2 + mb) * OZ_CHUNKS_PER_PASS);
                         if (warp == 0) {
-                            dbg_wait += oz_issue_pass(tmem, ring_addr, planes_addr, bar_full, bar_empty, bar_acc,
-                                                      tile_first + (uint32_t)((layer * 2 + mb) * OZ_CHUNKS_PER_PASS), rot, no_stream);
+                            // ---- MMA issuer ----
+                            dbg_wait += oz_issue_pass(tmem, ring_addr, planes_addr, bar_full, bar_empty, bar_group, bar_tfree, pass_first, 0u, no_stream, (oa.dbg_flags & 2) != 0);
                         } else if (producer && !no_stream) {
-                            const uint32_t pass_end = tile_first + (uint32_t)((layer * 2 + mb + 1) * OZ_CHUNKS_PER_PASS);
-                            if (pass_end == tile_end) produce(tile_end, true);
-                            else produce(pass_end + OZ_NSLOT, false);  // incl. this warp's first chunk of the next pass
+                            // ---- weight-digit stream: the rest of this pass's chunks and the first NSLOT of the next pass's (they land during the epilogue / split) ----
+                            const uint32_t pb = pass_first + OZ_NSLOT, pe = (pb + OZ_CHUNKS_PER_PASS < tile_end) ? pb + OZ_CHUNKS_PER_PASS : tile_end;
+                            oz_produce_range(oa.wq, ring, bar_full, bar_empty, pb, pe, tile_first, (uint32_t)(warp - 1), (uint32_t)lane);
                         }
-                        // ---- epilogue ----
-                        oz_mbar_wait(bar_acc, n_pass & 1);
+                        if (warp == 0) oz_mbar_wait(bar_group + 8 * (OZ_S - 1), n_pass & 1u);  // the last plane's commit: every MMA of the pass is done
                         n_pass++;
-                        OZ_DBG(2)
-                        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                        if (layer == 2 && mb == 1) prefetch(p, buf);  // all MMAs of the tile are done: the ring region is the DMMA layers' again
-                        {
-                            const int qd = warp & 3, hh = warp >> 2;
-                            const int row = mb * 128 + qd * 32 + lane;
-                            long long acc[32];
-#pragma unroll
-                            for (int g = 0; g < OZ_S; g++) {
-                                uint32_t v[32];
-                                oz_tmem_ld32(tmem + ((uint32_t)(qd * 32) << 16) + g * 64 + hh * 32, v);
-#pragma unroll
-                                for (int c = 0; c < 32; c++) acc[c] = (g == 0) ? (long long)(int)v[c] : acc[c] * 128 + (long long)(int)v[c];
-                            }
-                            const double rs = __ldg(oa.rowscale + layer * 256 + row), bv = __ldg(a.bias + MLP_BIAS_ENV + (layer + 1) * 256 + row);
-#pragma unroll
-                            for (int sl = 0; sl < 4; sl++) {
-                                const int s = 4 * hh + sl;
-                                double y[8];
-#pragma unroll
-                                for (int c = 0; c < 8; c++) y[c] = (__ll2double_rn(acc[8 * sl + c]) * rs) * s_colscale[8 * s + c];
-                                y[0] += bv;
-                                const bool on = y[0] > 0.0;
-#pragma unroll
-                                for (int j = 0; j < 4; j++) Xs[xl2(row, j, s)] = on ? make_double2(y[2 * j], y[2 * j + 1]) : make_double2(0.0, 0.0);
-                                if (layer < 2) {
-#pragma unroll
-                                    for (int c = 0; c < 8; c++) {
-                                        const uint32_t m = __reduce_max_sync(0xffffffffu, on ? oz_abs_hi(y[c]) : 0u);
-                                        if (lane == 0) atomicMax(&colmax[8 * s + c], m);
-                                    }
-                                }
-                            }
+                        __syncthreads();  // the other warps wait in the hardware barrier, not by polling
+                        if (layer == 2 && mb == 1) {  // the digit planes are dead: the output layer's weights (A fragments) land above the tile during the epilogue
+                            const double2* src = reinterpret_cast<const double2*>(a.wpack + (size_t)OZ_NDCHUNK * OZ_DCHUNK_D);
+                            for (int i = tid; i < OZ_WOUT_D / 2; i += MLP_THREADS) cp_async16(reinterpret_cast<double2*>(smem_raw + OZ_OFF_WOUT) + i, src + i);
+                            cp_async_commit();
                         }
+                        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                        OZ_DBG(2)
+                        oz_epilogue_pass(Xs, colmax, s_colscale, oa.rowscale + layer * 256, a.bias + MLP_BIAS_ENV + (layer + 1) * 256, tmem, mb, warp, lane, layer < 2);
                         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
                         __syncthreads();  // accumulators read, tile rows written (the next pass / split / output layer may start)
                         OZ_DBG(3)
                     }
                 }
+                cp_async_wait_all();
+                __syncthreads();  // the output layer's weights are in place
+                d_topup();  // all MMAs of the tile are done: the ring region is the DMMA layers' again
                 // ---- env output layer: 9 x 256 as two m-fragments (rows 0..7, row 8) on DMMA; warp = column kind ----
                 double o[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
                 const double* xb = Xd + ((warp >> 1) * 32 + bslot) * 2 + (warp & 1);
+                const double* Wo0 = reinterpret_cast<const double*>(smem_raw + OZ_OFF_WOUT);  // rows 0..7 as A fragments [kb 64][lane 32]
+                const double* Wo1 = Wo0 + 8 * 256;                                            // row 8 [256]
 #pragma unroll 4
                 for (int kb = 0; kb < 64; kb += 2) {
 #pragma unroll
                     for (int h = 0; h < 2; h++) {
                         const double bx = xb[(kb + h) * 256];
-                        const double a0 = __ldg(a.w_out_env + fr * 256 + (kb + h) * 4 + fq), a1 = (lane < 4) ? __ldg(a.w_out_env + 8 * 256 + (kb + h) * 4 + lane) : 0.0;
+                        const double a0 = Wo0[(kb + h) * 32 + lane], a1 = (lane < 4) ? Wo1[(kb + h) * 4 + lane] : 0.0;
                         dmma884(o[h][0][0], o[h][0][1], a0, bx);
                         dmma884(o[h][1][0], o[h][1][1], a1, bx);
                     }
@@ -521,8 +623,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp_oz(MlpOzArgs oa) {
 #pragma unroll
                 for (int c = 0; c < 8; c++) acc[c][0] = acc[c][1] = 0.0;
                 for (int ch = 0; ch < 8; ch++) {
-                    next_chunk(true);
-                    const double2* Wc = Wmine + buf * SLICE2;  // [kb pair 4][lane 32] -> {kb even, kb odd}
+                    const double2* Wc = d_wait();  // [kb pair 4][lane 32] -> {kb even, kb odd}
 #pragma unroll 2
                     for (int kp = 0; kp < 4; kp++) {
                         const double2 a2 = Wc[kp * 32 + lane];
@@ -540,7 +641,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp_oz(MlpOzArgs oa) {
                             }
                         }
                     }
-                    advance();
+                    d_done(false);
                 }
                 const double bv = a.bias[MLP_BIAS_SELF1 + warp * 8 + fr];
                 __syncthreads();
@@ -593,7 +694,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp_oz(MlpOzArgs oa) {
 #endif  // __CUDACC__
 
 // Host-side packing for k_mlp_oz.
-//   dpack  (OZ_NDCHUNK x OZ_DCHUNK_D doubles): env L0 as 4 chunks [warp 8][k 8][row 32] | self L0 likewise | self L1 as 8 chunks
+//   dpack  (OZ_NDCHUNK x OZ_DCHUNK_D + OZ_WOUT_D doubles): env L0 as 4 chunks [warp 8][k 8][row 32] | self L0 likewise | self L1 as 8 chunks
 //          [warp 8][kb pair 4][lane 32][h 2] = W[8 warp + (l >> 2)][32 ch + 4 (2 kp + h) + (l & 3)]
 //   qpack  (OZ_CHUNKS_PER_TILE x OZ_CHUNK bytes): for env layers 1..3, neuron halves mb, plane positions pi (plane oz_order(pi)), k chunks kc:
 //          128 rows x 64 k of digit plane i as canonical K-major 8 x 16-byte core matrices: byte (r % 8) 16 + (r / 8) 128 + (k % 16) + (k / 16) 2048
@@ -619,8 +720,9 @@ inline void pack_mlp_oz_weights(const double* const env_W[5], const double* cons
                         const int row = 8 * warp + (l >> 2), k = 32 * ch + 4 * (2 * kp + h) + (l & 3);
                         *o++ = self_W[1][(size_t)row * 256 + k];
                     }
-    int pos_of_plane[OZ_S];
-    for (int pi = 0; pi < OZ_S; pi++) pos_of_plane[oz_order(pi)] = pi;
+    for (int kb = 0; kb < 64; kb++)
+        for (int l = 0; l < 32; l++) *o++ = env_W[4][(size_t)(l >> 2) * 256 + kb * 4 + (l & 3)];
+    for (int k = 0; k < 256; k++) *o++ = env_W[4][(size_t)8 * 256 + k];
     for (int layer = 0; layer < 3; layer++) {
         const double* W = env_W[layer + 1];
         for (int r = 0; r < 256; r++) {
@@ -630,16 +732,9 @@ inline void pack_mlp_oz_weights(const double* const env_W[5], const double* cons
             if (mx > 0.0) std::frexp(mx, &e);  // mx < 2^e
             const int Er = e + 1;
             rowscale[layer * 256 + r] = std::ldexp(1.0, Er - 7 * OZ_S - 7);
-            const int mb = r / 128, rr = r % 128;
             for (int k = 0; k < 256; k++) {
                 const long long q = std::llrint(std::ldexp(W[(size_t)r * 256 + k], 7 * OZ_S - Er)) + oz_bias_const();
-                for (int t = 0; t < OZ_S; t++) {
-                    const int i = OZ_S - 1 - t;
-                    const int d = (t < OZ_S - 1) ? (int)((q >> (7 * t)) & 127) - 64 : (int)(q >> (7 * (OZ_S - 1)));
-                    const size_t chunk = (size_t)layer * OZ_CHUNKS_PER_LAYER + (size_t)(mb * OZ_S + pos_of_plane[i]) * OZ_CPP + k / OZ_KCH;
-                    const int kk = k % OZ_KCH;
-                    qpack[chunk * OZ_CHUNK + (rr % 8) * 16 + (rr / 8) * 128 + (kk % 16) + (kk / 16) * 2048] = (uint8_t)(int8_t)d;
-                }
+                for (int t = 0; t < OZ_S; t++) qpack[oz_wq_index(layer, r, k, OZ_S - 1 - t)] = (uint8_t)(int8_t)oz_digit(q, t);
             }
         }
     }

@@ -355,9 +355,9 @@ static int create_impl(mpcc_cuda_handle* h, const mpcc_cuda_config* cfg) {
     A(h->alloc(&h->d_status, B)); A(h->alloc(&h->d_iters, B)); A(h->alloc(&h->d_ok, B)); A(h->alloc(&h->d_qp_iters, B)); A(h->alloc(&h->d_qp_fail, B)); A(h->alloc(&h->d_accept, B)); A(h->alloc(&h->d_sqp_ns, 4 * B)); A(h->alloc(&h->d_hist, B)); A(h->alloc(&h->d_order, B + 1));
     A(h->alloc(&h->d_wpack, (size_t)MLP_NCHUNK * MLP_CHUNK_D)); A(h->alloc(&h->d_bias, MLP_BIAS_TOTAL));
     A(h->alloc(&h->d_w_out_env, 9 * 256)); A(h->alloc(&h->d_w_out_self, 64));
-    A(h->alloc(&h->d_oz_dpack, (size_t)OZ_NDCHUNK * OZ_DCHUNK_D)); A(h->alloc(&h->d_oz_rowscale, 3 * 256)); A(h->alloc(&h->d_oz_wq, (size_t)OZ_CHUNKS_PER_TILE * OZ_CHUNK));
+    A(h->alloc(&h->d_oz_dpack, (size_t)OZ_NDCHUNK * OZ_DCHUNK_D + OZ_WOUT_D)); A(h->alloc(&h->d_oz_rowscale, 3 * 256)); A(h->alloc(&h->d_oz_wq, (size_t)OZ_CHUNKS_PER_TILE * OZ_CHUNK));
     h->mlp_oz = (h->cfg.reserved & 8) == 0;  // default: the int8-split tcgen05 kernel; bit 3 selects the fp64 DMMA kernel (k_mlp)
-    if (h->cfg.reserved & 16) A(h->alloc(&h->d_oz_dbg, 8));
+    if (h->cfg.reserved & 16) A(h->alloc(&h->d_oz_dbg, 64));
     if (ae != cudaSuccess) return fail(MPCC_ERR_CUDA, std::string("device allocation failed: ") + cudaGetErrorString(ae));
     std::vector<double> dummy(B * 4);
     for (size_t b = 0; b < B; b++) { dummy[4 * b] = 3; dummy[4 * b + 1] = 3; dummy[4 * b + 2] = 3; dummy[4 * b + 3] = 0; }  // mpc.cpp:97-100
@@ -420,7 +420,7 @@ int mpcc_cuda_upload_nn(mpcc_cuda_handle* h, const double* self_w, const double*
     CK(cudaMemcpyAsync(h->d_bias, bias.data(), bias.size() * 8, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_w_out_env, eW[4], 9 * 256 * 8, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_w_out_self, sW[2], 64 * 8, cudaMemcpyHostToDevice, h->stream));
-    std::vector<double> oz_d((size_t)OZ_NDCHUNK * OZ_DCHUNK_D), oz_rs(3 * 256);
+    std::vector<double> oz_d((size_t)OZ_NDCHUNK * OZ_DCHUNK_D + OZ_WOUT_D), oz_rs(3 * 256);
     std::vector<uint8_t> oz_q((size_t)OZ_CHUNKS_PER_TILE * OZ_CHUNK);
     pack_mlp_oz_weights(eW, sW, oz_d.data(), oz_q.data(), oz_rs.data());
     CK(cudaMemcpyAsync(h->d_oz_dpack, oz_d.data(), oz_d.size() * 8, cudaMemcpyHostToDevice, h->stream));
@@ -792,10 +792,14 @@ int mpcc_cuda_eval_robot_data(mpcc_cuda_handle* h, const double* q, const double
     CK(cudaMemcpyAsync(rb_out, d_out, (size_t)n * RB_DOUBLES * 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     if (h->d_oz_dbg) {  // diagnostics (reserved bit 4): cycles of CTA 0 of k_mlp_oz per phase
-        long long t[8];
+        long long t[64];
         CK(cudaMemcpy(t, h->d_oz_dbg, sizeof(t), cudaMemcpyDeviceToHost));
         fprintf(stderr, "k_mlp_oz CTA 0, %lld tiles: cycles per tile: first layers %lld | split %lld | MMA passes %lld | epilogues %lld | env output %lld | self net %lld || issuer waiting for weight chunks %lld\n", t[6],
                 t[0] / t[6], t[1] / t[6], t[2] / t[6], t[3] / t[6], t[4] / t[6], t[5] / t[6], t[7] / t[6]);
+        const long long z = t[8];
+        fprintf(stderr, "  trace (tile 1, layer 0; cycles after the layer started): issuer: split done %lld | pass 0 issued %lld | pass 1 issued %lld | barrier passed %lld ; producer done %lld ; "
+                        "epilogue pass 0: group 0 ready %lld, last group ready %lld, sweep 0 read %lld, sweep 1 read (accumulators released) %lld, write-backs done %lld %lld | pass 1: %lld %lld %lld %lld %lld %lld | done %lld\n",
+                t[9] - z, t[10] - z, t[11] - z, t[12] - z, t[24] - z, t[40] - z, t[41] - z, t[42] - z, t[43] - z, t[44] - z, t[45] - z, t[46] - z, t[47] - z, t[48] - z, t[49] - z, t[50] - z, t[51] - z, t[55] - z);
     }
     return MPCC_OK;
 }

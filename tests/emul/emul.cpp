@@ -5,6 +5,7 @@
 #include "../../mpcc_manipulator_b200/csrc/sqp_warp.cuh"
 #include "../../mpcc_manipulator_b200/csrc/host/track_fit.h"
 #include "../../mpcc_manipulator_b200/csrc/dev_track_fit.cuh"
+#include "../../mpcc_manipulator_b200/csrc/mlp_oz_kernel.cuh"
 #include <cstring>
 #include <vector>
 
@@ -160,5 +161,59 @@ int emu_solve_qp(const double* params, const double* table, double Ts, int N, co
     }
     *iters = qs.iters; res3[0] = qs.res_dual; res3[1] = qs.res_prim; res3[2] = qs.gap;
     return qs.ok;
+}
+}
+
+// ---- int8-split layer of the MLP kernel (mlp_oz_kernel.cuh): the host packing (pack_mlp_oz_weights) and the scalar arithmetic the kernel uses
+//      (oz_col_scales, oz_quantize, oz_digit), with the tensor-core products restated as plain int32 sums ----
+extern "C" {
+int emu_oz_slices() { return OZ_S; }
+// Y[256][ncol] = W[256][256] X[256][ncol] through the split: digits of W from the packed stream, digits of X per column, exact int32 group sums,
+// int64 Horner, one rounding.  Also returns the largest |digit| seen (must be <= 64) and the largest |group sum| (must stay below 2^23).
+void emu_oz_layer(const double* W, const double* X, int ncol, double* Y, int* max_digit, long long* max_group) {
+    std::vector<double> zero30(256 * 30, 0.0), zero21(256 * 21, 0.0), zero256(256 * 256, 0.0), zero9(9 * 256, 0.0), zero64(64 * 256, 0.0), zero1(64, 0.0);
+    const double* eW[5] = {zero30.data(), W, zero256.data(), zero256.data(), zero9.data()};
+    const double* sW[3] = {zero21.data(), zero64.data(), zero1.data()};
+    std::vector<double> dpack((size_t)OZ_NDCHUNK * OZ_DCHUNK_D + OZ_WOUT_D), rowscale(3 * 256);
+    std::vector<uint8_t> qpack((size_t)OZ_CHUNKS_PER_TILE * OZ_CHUNK);
+    pack_mlp_oz_weights(eW, sW, dpack.data(), qpack.data(), rowscale.data());
+    int md = 0;
+    long long mg = 0;
+    std::vector<int> b((size_t)OZ_S * 256);
+    for (int c = 0; c < ncol; c++) {
+        double mx = 0.0;
+        for (int k = 0; k < 256; k++) mx = std::fmax(mx, std::fabs(X[(size_t)k * ncol + c]));
+        unsigned long long bits;
+        std::memcpy(&bits, &mx, 8);
+        double sc, cs;
+        oz_col_scales((uint32_t)(bits >> 32) & 0x7FFFFFFFu, sc, cs);
+        for (int k = 0; k < 256; k++) {
+            const long long q = oz_quantize(X[(size_t)k * ncol + c], sc);
+            for (int t = 0; t < OZ_S; t++) {
+                const int d = oz_digit(q, t);
+                b[(size_t)(OZ_S - 1 - t) * 256 + k] = d;
+                md = std::max(md, std::abs(d));
+            }
+        }
+        for (int r = 0; r < 256; r++) {
+            long long S = 0;
+            for (int g = 0; g < OZ_S; g++) {
+                long long G = 0;
+                for (int i = 0; i <= g; i++) {
+                    const int j = g - i;
+                    for (int k = 0; k < 256; k++) {
+                        const int a = (int)(int8_t)qpack[oz_wq_index(0, r, k, i)];
+                        md = std::max(md, std::abs(a));
+                        G += (long long)a * b[(size_t)j * 256 + k];
+                    }
+                }
+                mg = std::max(mg, (long long)std::llabs(G));
+                S = S * 128 + G;
+            }
+            Y[(size_t)r * ncol + c] = ((double)S * rowscale[r]) * cs;
+        }
+    }
+    *max_digit = md;
+    *max_group = mg;
 }
 }

@@ -229,10 +229,10 @@ __device__ __forceinline__ void utccp_128x256b(uint32_t tmem_dst, uint64_t sdesc
     asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;\n" ::"r"(tmem_dst), "l"(sdesc) : "memory");
 }
 template <int S>
-__global__ void __launch_bounds__(128, 1) k_ts(const uint8_t* __restrict__ Ag, const uint8_t* __restrict__ Bg, int32_t* __restrict__ Dg, uint32_t* __restrict__ Adump,
+__global__ void __launch_bounds__(512, 1) k_ts(const uint8_t* __restrict__ Ag, const uint8_t* __restrict__ Bg, int32_t* __restrict__ Dg, uint32_t* __restrict__ Adump,
                                                long long* __restrict__ cycles, int a_bytes, int b_bytes, int mode, int reps) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ uint64_t bar;
+    __shared__ uint64_t bar, bar2;
     __shared__ uint32_t tmem_base_s;
     unsigned char* As = smem;
     unsigned char* Bs = smem + a_bytes;
@@ -241,6 +241,7 @@ __global__ void __launch_bounds__(128, 1) k_ts(const uint8_t* __restrict__ Ag, c
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&bar2)) : "memory");
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&bar)) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
@@ -255,7 +256,7 @@ __global__ void __launch_bounds__(128, 1) k_ts(const uint8_t* __restrict__ Ag, c
     constexpr uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
     const uint32_t tmem_a0 = tmem_base + 448;
     uint32_t parity = 0;
-    if (mode == 0) {  // one product, K = 64: two copies + two MMAs
+    if ((mode & 1) == 0) {  // one product, K = 64: two copies + two MMAs
         if (warp == 0 && elect_one()) {
             const uint64_t ad0 = make_desc(smem_u32(As), 2048, 128), bd0 = make_desc(smem_u32(Bs), 128, 8 * 128);
             for (int ks = 0; ks < 2; ks++) utccp_128x256b(tmem_a0 + ks * 8, ad0 + (uint64_t)((ks * 4096) >> 4));
@@ -301,8 +302,10 @@ __global__ void __launch_bounds__(128, 1) k_ts(const uint8_t* __restrict__ Ag, c
                     for (int kc = 0; kc < 4; kc++, chunk++) {
                         const uint64_t ad = ad0 + (uint64_t)(((chunk % 6) * 8192) >> 4);
                         const uint32_t ta = tmem_a0 + (chunk & 3) * 16;
+                        if (mode & 4) asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                         utccp_128x256b(ta, ad);
                         utccp_128x256b(ta + 8, ad + (uint64_t)(4096 >> 4));
+                        if (mode & 2) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(&bar2)) : "memory");
                         for (int j = 0; j + i < S; j++) {
                             const uint64_t bd = bd0 + (uint64_t)((j * 64 * 256 + kc * 1024) >> 4);
                             const uint32_t d = tmem_base + (i + j) * 64;
@@ -454,6 +457,18 @@ int main() {
         long long c[2];
         CK(cudaMemcpy(c, dC, 16, cudaMemcpyDeviceToHost));
         printf("rate, A from TMEM: one pass (S = 7: 28 chunks = 56 copies + 224 MMAs of 128 x 64 x 32): %.0f cycles per pass, %.1f per MMA\n", (double)c[0] / 8, (double)c[0] / 8 / 224);
+        for (int nt : {256, 512}) {
+            k_ts<7><<<1, nt, a_bytes + b_bytes>>>(dA2, dB2, dD, dAd, dC, a_bytes, b_bytes, 1, 8);
+            CK(cudaDeviceSynchronize());
+            CK(cudaMemcpy(c, dC, 16, cudaMemcpyDeviceToHost));
+            printf("  with %d threads in the CTA (all but one spin on the completion barrier): %.0f cycles per pass\n", nt, (double)c[0] / 8);
+        }
+        for (int mode : {3, 5, 7}) {
+            k_ts<7><<<1, 128, a_bytes + b_bytes>>>(dA2, dB2, dD, dAd, dC, a_bytes, b_bytes, mode, 8);
+            CK(cudaDeviceSynchronize());
+            CK(cudaMemcpy(c, dC, 16, cudaMemcpyDeviceToHost));
+            printf("  + per chunk:%s%s: %.0f cycles per pass\n", (mode & 2) ? " tcgen05.commit" : "", (mode & 4) ? " tcgen05.fence::after_thread_sync" : "", (double)c[0] / 8);
+        }
     }
     return 0;
 }
