@@ -222,48 +222,49 @@ __device__ __noinline__ long long oz_issue_pass(uint32_t tmem, uint32_t ring_add
     tmem = __shfl_sync(0xffffffffu, tmem, 0); ring_addr = __shfl_sync(0xffffffffu, ring_addr, 0); planes_addr = __shfl_sync(0xffffffffu, planes_addr, 0);
     bar_full = __shfl_sync(0xffffffffu, bar_full, 0); bar_empty = __shfl_sync(0xffffffffu, bar_empty, 0); bar_group = __shfl_sync(0xffffffffu, bar_group, 0);
     bar_tfree = __shfl_sync(0xffffffffu, bar_tfree, 0); n = __shfl_sync(0xffffffffu, n, 0); tfree_wait = __shfl_sync(0xffffffffu, tfree_wait, 0);
+    // All 32 lanes of warp 0 walk the chunks and wait together (converged); one elected lane issues.  This is the canonical shape (wait by the
+    // warp, elect, issue): a wait loop INSIDE a single-thread region makes the compiler wrap every tcgen05.mma in an election loop (+40 cycles per
+    // MMA), and re-electing with a one-lane mask after each wait costs ~80 cycles per chunk.
     long long waited = 0;
-    if (oz_elect_one()) {
-        const uint32_t self_mask = 1u << (threadIdx.x & 31);
-        const long long tw0 = clock64();
-        if (tfree_wait) oz_mbar_wait_asm(bar_tfree, tfree_wait - 1);  // the epilogue warps have read the previous pass's accumulators
-        waited = clock64() - tw0;
-        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        uint32_t slot = n % OZ_NSLOT, ph = (n / OZ_NSLOT) & 1;
-        const uint64_t bd0 = oz_desc(planes_addr, 128, 4096);
+    if (tfree_wait) oz_mbar_wait_asm(bar_tfree, tfree_wait - 1);
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    uint32_t slot = n % OZ_NSLOT, ph = (n / OZ_NSLOT) & 1;
+    const uint64_t bd0 = oz_desc(planes_addr, 128, 4096);
 #pragma unroll
-        for (int i = 0; i < OZ_S; i++) {
+    for (int i = 0; i < OZ_S; i++) {
 #pragma unroll
-            for (int kc = 0; kc < OZ_CPP; kc++) {
+        for (int kc = 0; kc < OZ_CPP; kc++) {
+            if (!no_stream) {
                 const long long tf0 = clock64();
-                if (!no_stream) oz_mbar_wait_asm(bar_full + 8 * slot, ph);
+                oz_mbar_wait_asm(bar_full + 8 * slot, ph);
                 waited += clock64() - tf0;
-                if (!no_fence) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // the chunk was written through the generic proxy (cp.async)
-                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                const uint64_t ad = oz_desc(ring_addr + slot * OZ_CHUNK, 2048, 128);
-                if (oz_elect_mask(self_mask)) {  // re-establishes "one thread" for the compiler after the wait loop
-                    // the chunk goes to TMEM once (tcgen05.cp, 8 columns per 32-k step; 4 rotating buffers behind the accumulators) and the MMAs take
-                    // A from there: shared memory is read once per chunk instead of once per MMA, and the ring slot is free as soon as the copy is
-                    // done.  Copies and MMAs execute in issue order, so a buffer is not overwritten before the MMAs issued earlier have read it.
-                    const uint32_t ta = tmem + OZ_S * 64 + ((i * OZ_CPP + kc) & 3) * (OZ_KCH / 4);
-#pragma unroll
-                    for (int ks = 0; ks < OZ_KCH / 32; ks++) oz_utccp(ta + ks * 8, ad + (uint64_t)((ks * 4096) >> 4));
-                    oz_commit(bar_empty + 8 * slot);
-#pragma unroll
-                    for (int j = 0; j + i < OZ_S; j++) {  // accumulator g = i + j
-                        const uint64_t bd = bd0 + (uint64_t)((j * OZ_PLANE + kc * (OZ_KCH * 16)) >> 4);
-#pragma unroll
-                        for (int ks = 0; ks < OZ_KCH / 32; ks++)
-                            oz_mma_i8_ts(tmem + (i + j) * 64, ta + ks * 8, bd + (uint64_t)((ks * 512) >> 4), IDESC, (i > 0 || kc > 0 || ks > 0) ? 1u : 0u);
-                    }
-                    if (kc == OZ_CPP - 1) oz_commit(bar_group + 8 * i);
-                }
-                slot = (slot + 1 == (uint32_t)OZ_NSLOT) ? 0u : slot + 1;
-                ph ^= (slot == 0) ? 1u : 0u;
             }
+            if (!no_fence) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // the chunk was written through the generic proxy (cp.async)
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            const uint64_t ad = oz_desc(ring_addr + slot * OZ_CHUNK, 2048, 128);
+            if (oz_elect_one()) {
+                // the chunk goes to TMEM once (tcgen05.cp, 8 columns per 32-k step; 4 rotating buffers behind the accumulators) and the MMAs take
+                // A from there: shared memory is read once per chunk instead of once per MMA, and the ring slot is free as soon as the copy is
+                // done.  Copies and MMAs execute in issue order, so a buffer is not overwritten before the MMAs issued earlier have read it.
+                const uint32_t ta = tmem + OZ_S * 64 + ((i * OZ_CPP + kc) & 3) * (OZ_KCH / 4);
+#pragma unroll
+                for (int ks = 0; ks < OZ_KCH / 32; ks++) oz_utccp(ta + ks * 8, ad + (uint64_t)((ks * 4096) >> 4));
+                oz_commit(bar_empty + 8 * slot);
+#pragma unroll
+                for (int j = 0; j + i < OZ_S; j++) {  // accumulator g = i + j
+                    const uint64_t bd = bd0 + (uint64_t)((j * OZ_PLANE + kc * (OZ_KCH * 16)) >> 4);
+#pragma unroll
+                    for (int ks = 0; ks < OZ_KCH / 32; ks++)
+                        oz_mma_i8_ts(tmem + (i + j) * 64, ta + ks * 8, bd + (uint64_t)((ks * 512) >> 4), IDESC, (i > 0 || kc > 0 || ks > 0) ? 1u : 0u);
+                }
+                if (kc == OZ_CPP - 1) oz_commit(bar_group + 8 * i);
+            }
+            __syncwarp();
+            slot = (slot + 1 == (uint32_t)OZ_NSLOT) ? 0u : slot + 1;
+            ph ^= (slot == 0) ? 1u : 0u;
         }
     }
-    __syncwarp();
+    return waited;
 }
 
 
@@ -561,13 +562,16 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp_oz(MlpOzArgs oa) {
                         const uint32_t pass_first = tile_first + (uint32_t)((layer * 2 + mb) * OZ_CHUNKS_PER_PASS);
                         if (warp == 0) {
                             // ---- MMA issuer ----
+                            if (layer == 0) { OZ_MARK(0, 3 * mb) }
                             dbg_wait += oz_issue_pass(tmem, ring_addr, planes_addr, bar_full, bar_empty, bar_group, bar_tfree, pass_first, 0u, no_stream, (oa.dbg_flags & 2) != 0);
+                            if (layer == 0) { OZ_MARK(0, 3 * mb + 1) }
                         } else if (producer && !no_stream) {
                             // ---- weight-digit stream: the rest of this pass's chunks and the first NSLOT of the next pass's (they land during the epilogue / split) ----
                             const uint32_t pb = pass_first + OZ_NSLOT, pe = (pb + OZ_CHUNKS_PER_PASS < tile_end) ? pb + OZ_CHUNKS_PER_PASS : tile_end;
                             oz_produce_range(oa.wq, ring, bar_full, bar_empty, pb, pe, tile_first, (uint32_t)(warp - 1), (uint32_t)lane);
                         }
                         if (warp == 0) oz_mbar_wait(bar_group + 8 * (OZ_S - 1), n_pass & 1u);  // the last plane's commit: every MMA of the pass is done
+                        if (warp == 0 && layer == 0) { OZ_MARK(0, 3 * mb + 2) }
                         n_pass++;
                         __syncthreads();  // the other warps wait in the hardware barrier, not by polling
                         if (layer == 2 && mb == 1) {  // the digit planes are dead: the output layer's weights (A fragments) land above the tile during the epilogue

@@ -796,10 +796,8 @@ int mpcc_cuda_eval_robot_data(mpcc_cuda_handle* h, const double* q, const double
         CK(cudaMemcpy(t, h->d_oz_dbg, sizeof(t), cudaMemcpyDeviceToHost));
         fprintf(stderr, "k_mlp_oz CTA 0, %lld tiles: cycles per tile: first layers %lld | split %lld | MMA passes %lld | epilogues %lld | env output %lld | self net %lld || issuer waiting for weight chunks %lld\n", t[6],
                 t[0] / t[6], t[1] / t[6], t[2] / t[6], t[3] / t[6], t[4] / t[6], t[5] / t[6], t[7] / t[6]);
-        const long long z = t[8];
-        fprintf(stderr, "  trace (tile 1, layer 0; cycles after the layer started): issuer: split done %lld | pass 0 issued %lld | pass 1 issued %lld | barrier passed %lld ; producer done %lld ; "
-                        "epilogue pass 0: group 0 ready %lld, last group ready %lld, sweep 0 read %lld, sweep 1 read (accumulators released) %lld, write-backs done %lld %lld | pass 1: %lld %lld %lld %lld %lld %lld | done %lld\n",
-                t[9] - z, t[10] - z, t[11] - z, t[12] - z, t[24] - z, t[40] - z, t[41] - z, t[42] - z, t[43] - z, t[44] - z, t[45] - z, t[46] - z, t[47] - z, t[48] - z, t[49] - z, t[50] - z, t[51] - z, t[55] - z);
+        fprintf(stderr, "  trace (tile 1, layer 0): pass 0: issue %lld, until complete %lld | epilogue + barrier %lld | pass 1: issue %lld, until complete %lld ; chunk waits of the issuer per tile %lld\n",
+                t[9] - t[8], t[10] - t[8], t[11] - t[10], t[12] - t[11], t[13] - t[11], t[7] / t[6]);
     }
     return MPCC_OK;
 }

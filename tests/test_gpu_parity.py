@@ -75,6 +75,55 @@ def test_relu_mask_agreement(M, O, nn, ee_home, rng):
     mpc.close()
 
 
+MLP_FP64_KERNEL = 8   # mpcc_cuda_config.reserved bit 3: the fp64 DMMA kernel (k_mlp) instead of the int8-split tcgen05 kernel (k_mlp_oz, the default)
+
+
+def test_robot_data_int8_split_vs_fp64_kernel(M, O, nn, ee_home, rng):
+    """Both MLP kernels on the same inputs: the default one runs the three 256 x 256 env layers as int8 digit products on tcgen05
+    (csrc/mlp_oz_kernel.cuh), the other one is the fp64 DMMA kernel.  Everything outside those three layers is shared code, so the self-net
+    block must be bit-identical; the env block must agree to the split's error (1e-12 of the block's scale: three layers of <= 7e-15 each plus
+    the fp64 kernel's own summation noise) and both must meet the 1e-9 bar against the oracle.  Sample counts that are not a multiple of the
+    8-sample tile and of the 148-CTA grid, obstacles far / near / zero radius, joint angles up to the limits."""
+    for n, B, N in ((1, 1, 2), (13, 7, 3), (1999, 64, 40), (4096, 1024, 3)):
+        q = rng.uniform(-2.8, 2.8, (n, 7))
+        obs = np.c_[rng.uniform(-1.0, 1.0, (n, 3)), rng.uniform(0.0, 0.5, n)]
+        obs[::7] = [3.0, 3.0, 3.0, 0.0]           # the dummy obstacle of mpc.cpp:97-100
+        out = {}
+        for name, flags in (("split", 0), ("fp64", MLP_FP64_KERNEL)):
+            mpc = M.BatchMPC(B, N, flags=flags)
+            mpc.load_nn()
+            out[name] = mpc.eval_robot_data(q, obs)
+            mpc.close()
+        a, b = out["split"], out["fp64"]
+        assert np.array_equal(a[:, :78], b[:, :78])                       # kinematics, self net, obstacle radius: the same code
+        assert rel_err(a[:, 78:87], b[:, 78:87]) < 1e-12 and rel_err(a[:, 87:150], b[:, 87:150]) < 1e-12
+        m = min(n, 48)
+        ref = np.stack([nn.robot_data(q[i], obs[i]) for i in range(m)])
+        for x in (a, b):
+            assert rel_err(x[:m, 78:87], ref[:, 78:87]) < REL and rel_err(x[:m, 87:150], ref[:, 87:150]) < REL
+
+
+def test_cycle_same_result_with_either_mlp_kernel(M, O, ee_home, rng):
+    """One control cycle from identical inputs with each MLP kernel.  Their RobotData differ by 1e-13; the SQP sees that only where a filter
+    decision is a tie (after a full step both constraint violations are solver noise, so accept / reject is a coin flip of the last
+    bits -- also between two summation orders of the fp64 kernel).  Instances whose line-search decisions coincide must agree in status,
+    iteration count and applied control to the QP tolerance; that must be the clear majority."""
+    B, N = 64, 10
+    x0 = np.tile(np.r_[O.Q_HOME, 0.0, 0.0], (B, 1)); x0[:, :7] += rng.uniform(-0.05, 0.05, (B, 7))
+    res = {}
+    for name, flags in (("split", 0), ("fp64", MLP_FP64_KERNEL)):
+        mpc = make_mpc(M, B, N, ee_home, flags=flags)
+        r = mpc.run_cycle(x0, np.zeros((B, 8)))
+        res[name] = (r["status"].copy(), r["iters"].copy(), r["u0"].copy(), mpc.decisions().copy())
+        mpc.close()
+    TU = np.array([2.175, 2.175, 2.175, 2.175, 2.61, 2.61, 2.61, 5.0])
+    (sa, ia, ua, da), (sb, ib, ub, db) = res["split"], res["fp64"]
+    same = (da == db) & (ia == ib)
+    assert same.mean() > 0.5, same.mean()
+    assert np.array_equal(sa[same], sb[same])
+    assert (np.abs(ua[same] - ub[same]) / TU).max() < 1e-4
+
+
 def test_track_eval_vs_golden(M, ee_home):
     g = np.load(G / "track_eval.npz")
     mpc = make_mpc(M, 8, 10, ee_home)

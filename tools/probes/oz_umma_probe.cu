@@ -234,8 +234,8 @@ __global__ void __launch_bounds__(512, 1) k_ts(const uint8_t* __restrict__ Ag, c
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ uint64_t bar, bar2;
     __shared__ uint32_t tmem_base_s;
-    unsigned char* As = smem;
-    unsigned char* Bs = smem + a_bytes;
+    unsigned char* As = (mode & 16) ? smem + 180224 : smem;
+    unsigned char* Bs = (mode & 16) ? smem + 65536 : smem + a_bytes;
     for (int i = threadIdx.x * 16; i < a_bytes; i += blockDim.x * 16) *reinterpret_cast<uint4*>(As + i) = *reinterpret_cast<const uint4*>(Ag + i);
     for (int i = threadIdx.x * 16; i < b_bytes; i += blockDim.x * 16) *reinterpret_cast<uint4*>(Bs + i) = *reinterpret_cast<const uint4*>(Bg + i);
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
@@ -426,7 +426,7 @@ int main() {
         CK(cudaMalloc(&dA, A.size())); CK(cudaMalloc(&dB, B.size())); CK(cudaMalloc(&dD, M * N * 4)); CK(cudaMalloc(&dAd, 128 * 16 * 4)); CK(cudaMalloc(&dC, 16));
         CK(cudaMemcpy(dA, A.data(), A.size(), cudaMemcpyHostToDevice)); CK(cudaMemcpy(dB, B.data(), B.size(), cudaMemcpyHostToDevice));
         CK(cudaMemset(dD, 0xff, M * N * 4));
-        CK(cudaFuncSetAttribute(k_ts<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CK(cudaFuncSetAttribute(k_ts<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 230912));
         k_ts<7><<<1, 128, A.size() + B.size()>>>(dA, dB, dD, dAd, dC, (int)A.size(), (int)B.size(), 0, 1);
         CK(cudaDeviceSynchronize());
         std::vector<int32_t> D(M * N); std::vector<uint32_t> Ad(128 * 16);
@@ -457,6 +457,18 @@ int main() {
         long long c[2];
         CK(cudaMemcpy(c, dC, 16, cudaMemcpyDeviceToHost));
         printf("rate, A from TMEM: one pass (S = 7: 28 chunks = 56 copies + 224 MMAs of 128 x 64 x 32): %.0f cycles per pass, %.1f per MMA\n", (double)c[0] / 8, (double)c[0] / 8 / 224);
+        {
+            k_ts<7><<<1, 128, 230912>>>(dA2, dB2, dD, dAd, dC, a_bytes, b_bytes, 17, 8);
+            CK(cudaDeviceSynchronize());
+            CK(cudaMemcpy(c, dC, 16, cudaMemcpyDeviceToHost));
+            printf("  with the kernel's shared-memory map (ring at 176 KB, planes at 64 KB): %.0f cycles per pass\n", (double)c[0] / 8);
+        }
+        for (int grid : {16, 148}) {
+            k_ts<7><<<grid, 128, a_bytes + b_bytes>>>(dA2, dB2, dD, dAd, dC, a_bytes, b_bytes, 1, 64);
+            CK(cudaDeviceSynchronize());
+            CK(cudaMemcpy(c, dC, 16, cudaMemcpyDeviceToHost));
+            printf("  the same pass on %d SMs at once (64 repetitions, cycles of whichever CTA wrote last): %.0f cycles per pass\n", grid, (double)c[0] / 64);
+        }
         for (int nt : {256, 512}) {
             k_ts<7><<<1, nt, a_bytes + b_bytes>>>(dA2, dB2, dD, dAd, dC, a_bytes, b_bytes, 1, 8);
             CK(cudaDeviceSynchronize());
