@@ -59,9 +59,10 @@ constexpr int OZ_NDCHUNK = 16;
 constexpr int OZ_WOUT_D = 9 * 256;      // env output layer, appended to the DMMA stream: rows 0..7 in A-fragment order | row 8
 constexpr int OZ_OFF_WOUT = 131072;     // its place in shared memory: above the fp64 tile, in the (by then dead) digit planes
 static_assert(OZ_OFF_WOUT + OZ_WOUT_D * 8 <= OZ_OFF_RING, "output-layer weights must fit between the tile and the ring");
-// weight plane consumed at position pi of a pass: ascending, so that accumulator g (products i + j = g) is complete as soon as plane g is done
-// and the epilogue warps can fold it into their Horner sums while the later planes are still being multiplied
-constexpr int oz_order(int pi) { return pi; }
+// weight plane consumed at position pi of a pass: heavy (low i: S - i products) and light planes alternate, so that the weight stream's demand
+// per unit of tensor time is even (ascending order leaves the light planes at the end of every pass, where the stream cannot keep up)
+constexpr int oz_order(int pi) { return (pi & 1) ? OZ_S - 1 - pi / 2 : pi / 2; }
+constexpr int oz_pos_of_plane(int i) { return (2 * i < OZ_S) ? 2 * i : 2 * (OZ_S - 1 - i) + 1; }
 constexpr long long oz_bias_const() {  // 64 on each of the lower S - 1 digits: makes them unsigned fields (the top digit stays signed)
     long long c = 0;
     for (int t = 0; t < OZ_S - 1; t++) c += 64LL << (7 * t);
@@ -113,7 +114,7 @@ OZ_HD int oz_digit(long long q, int t) { return (t < OZ_S - 1) ? (int)((q >> (7 
 // where digit plane i of W[r][k] sits in the packed stream (byte index)
 inline size_t oz_wq_index(int layer, int r, int k, int i) {
     const int mb = r / 128, rr = r % 128, kk = k % OZ_KCH;
-    const size_t chunk = (size_t)layer * OZ_CHUNKS_PER_LAYER + (size_t)(mb * OZ_S + i) * OZ_CPP + k / OZ_KCH;
+    const size_t chunk = (size_t)layer * OZ_CHUNKS_PER_LAYER + (size_t)(mb * OZ_S + oz_pos_of_plane(i)) * OZ_CPP + k / OZ_KCH;
     return chunk * OZ_CHUNK + (rr % 8) * 16 + (rr / 8) * 128 + (kk % 16) + (kk / 16) * 2048;
 }
 
@@ -222,48 +223,49 @@ __device__ __noinline__ long long oz_issue_pass(uint32_t tmem, uint32_t ring_add
     tmem = __shfl_sync(0xffffffffu, tmem, 0); ring_addr = __shfl_sync(0xffffffffu, ring_addr, 0); planes_addr = __shfl_sync(0xffffffffu, planes_addr, 0);
     bar_full = __shfl_sync(0xffffffffu, bar_full, 0); bar_empty = __shfl_sync(0xffffffffu, bar_empty, 0); bar_group = __shfl_sync(0xffffffffu, bar_group, 0);
     bar_tfree = __shfl_sync(0xffffffffu, bar_tfree, 0); n = __shfl_sync(0xffffffffu, n, 0); tfree_wait = __shfl_sync(0xffffffffu, tfree_wait, 0);
-    // All 32 lanes of warp 0 walk the chunks and wait together (converged); one elected lane issues.  This is the canonical shape (wait by the
-    // warp, elect, issue): a wait loop INSIDE a single-thread region makes the compiler wrap every tcgen05.mma in an election loop (+40 cycles per
-    // MMA), and re-electing with a one-lane mask after each wait costs ~80 cycles per chunk.
+    // One elected lane walks the chunks, waits and issues; the other lanes park at the final __syncwarp.  After every wait the lane re-elects
+    // itself with a one-lane mask: a wait loop inside a single-thread region otherwise makes the compiler wrap every tcgen05.mma in an election
+    // loop (+40 cycles per MMA).  (Measured: the whole warp waiting converged and electing per chunk, the canonical shape, is 10 % slower here.)
     long long waited = 0;
-    if (tfree_wait) oz_mbar_wait_asm(bar_tfree, tfree_wait - 1);
-    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-    uint32_t slot = n % OZ_NSLOT, ph = (n / OZ_NSLOT) & 1;
-    const uint64_t bd0 = oz_desc(planes_addr, 128, 4096);
+    if (oz_elect_one()) {
+        const uint32_t self_mask = 1u << (threadIdx.x & 31);
+        if (tfree_wait) oz_mbar_wait_asm(bar_tfree, tfree_wait - 1);
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        uint32_t slot = n % OZ_NSLOT, ph = (n / OZ_NSLOT) & 1;
+        const uint64_t bd0 = oz_desc(planes_addr, 128, 4096);
 #pragma unroll
-    for (int i = 0; i < OZ_S; i++) {
+        for (int pi = 0; pi < OZ_S; pi++) {
+            const int i = oz_order(pi);
 #pragma unroll
-        for (int kc = 0; kc < OZ_CPP; kc++) {
-            if (!no_stream) {
-                const long long tf0 = clock64();
-                oz_mbar_wait_asm(bar_full + 8 * slot, ph);
-                waited += clock64() - tf0;
-            }
-            if (!no_fence) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // the chunk was written through the generic proxy (cp.async)
-            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-            const uint64_t ad = oz_desc(ring_addr + slot * OZ_CHUNK, 2048, 128);
-            if (oz_elect_one()) {
-                // the chunk goes to TMEM once (tcgen05.cp, 8 columns per 32-k step; 4 rotating buffers behind the accumulators) and the MMAs take
-                // A from there: shared memory is read once per chunk instead of once per MMA, and the ring slot is free as soon as the copy is
-                // done.  Copies and MMAs execute in issue order, so a buffer is not overwritten before the MMAs issued earlier have read it.
-                const uint32_t ta = tmem + OZ_S * 64 + ((i * OZ_CPP + kc) & 3) * (OZ_KCH / 4);
+            for (int kc = 0; kc < OZ_CPP; kc++) {  // (rolling this loop -- a quarter of the code -- is 10 % slower, rolling all of them 20 %)
+                if (!no_stream) oz_mbar_wait_asm(bar_full + 8 * slot, ph);
+                if (!no_fence) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // the chunk was written through the generic proxy (cp.async)
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                const uint64_t ad = oz_desc(ring_addr + slot * OZ_CHUNK, 2048, 128);
+                if (oz_elect_mask(self_mask)) {
+                    // the chunk goes to TMEM once (tcgen05.cp, 8 columns per 32-k step; 4 rotating buffers behind the accumulators) and the MMAs take
+                    // A from there: shared memory is read once per chunk instead of once per MMA, and the ring slot is free as soon as the copy is
+                    // done.  Copies and MMAs execute in issue order, so a buffer is not overwritten before the MMAs issued earlier have read it.
+                    const uint32_t ta = tmem + OZ_S * 64 + ((pi * OZ_CPP + kc) & 3) * (OZ_KCH / 4);
 #pragma unroll
-                for (int ks = 0; ks < OZ_KCH / 32; ks++) oz_utccp(ta + ks * 8, ad + (uint64_t)((ks * 4096) >> 4));
-                oz_commit(bar_empty + 8 * slot);
+                    for (int ks = 0; ks < OZ_KCH / 32; ks++) oz_utccp(ta + ks * 8, ad + (uint64_t)((ks * 4096) >> 4));
+                    oz_commit(bar_empty + 8 * slot);
 #pragma unroll
-                for (int j = 0; j + i < OZ_S; j++) {  // accumulator g = i + j
-                    const uint64_t bd = bd0 + (uint64_t)((j * OZ_PLANE + kc * (OZ_KCH * 16)) >> 4);
+                    for (int j = 0; j + i < OZ_S; j++) {  // accumulator g = i + j
+                        const uint64_t bd = bd0 + (uint64_t)((j * OZ_PLANE + kc * (OZ_KCH * 16)) >> 4);
 #pragma unroll
-                    for (int ks = 0; ks < OZ_KCH / 32; ks++)
-                        oz_mma_i8_ts(tmem + (i + j) * 64, ta + ks * 8, bd + (uint64_t)((ks * 512) >> 4), IDESC, (i > 0 || kc > 0 || ks > 0) ? 1u : 0u);
+                        for (int ks = 0; ks < OZ_KCH / 32; ks++)
+                            oz_mma_i8_ts(tmem + (i + j) * 64, ta + ks * 8, bd + (uint64_t)((ks * 512) >> 4), IDESC, (pi > 0 || kc > 0 || ks > 0) ? 1u : 0u);  // plane 0 comes first and starts every accumulator
+                    }
+                    if (kc == OZ_CPP - 1) oz_commit(bar_group + 8 * pi);  // the last position's commit says: pass complete
                 }
-                if (kc == OZ_CPP - 1) oz_commit(bar_group + 8 * i);
+                slot = (slot + 1 == (uint32_t)OZ_NSLOT) ? 0u : slot + 1;
+                ph ^= (slot == 0) ? 1u : 0u;
             }
-            __syncwarp();
-            slot = (slot + 1 == (uint32_t)OZ_NSLOT) ? 0u : slot + 1;
-            ph ^= (slot == 0) ? 1u : 0u;
         }
     }
+    __syncwarp();
+    for (int o = 16; o; o >>= 1) { const long long w2 = __shfl_xor_sync(0xffffffffu, waited, o); waited = w2 > waited ? w2 : waited; }
     return waited;
 }
 
@@ -480,6 +482,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp_oz(MlpOzArgs oa) {
         const uint32_t tile_first = tile_iter * OZ_CHUNKS_PER_TILE, tile_end = tile_first + OZ_CHUNKS_PER_TILE;
         for (int net = 0; net < 2; net++) {  // 0: env, 1: self
             // ---- encoded inputs z = [x, sin x, cos x] of the 8 samples: Zs [k 32][sample 8] (in the idle X tile) ----
+            if (warp == 0) { OZ_MARK(1, 5 * net + 0) }
             __syncthreads();
             double* Zs = Xd;
             {
@@ -495,6 +498,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp_oz(MlpOzArgs oa) {
                 }
             }
             __syncthreads();
+            if (warp == 0) { OZ_MARK(1, 5 * net + 1) }
             // ---- first layer on DFMA (4 chunks of 8 encoded inputs) ----
             {
                 double acc[4][8][2];
@@ -515,6 +519,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp_oz(MlpOzArgs oa) {
                 OZ_L0_CHUNK(16, false)
                 OZ_L0_CHUNK(24, true)
 #undef OZ_L0_CHUNK
+                if (warp == 0) { OZ_MARK(1, 5 * net + 2) }
                 const double* bias = a.bias + ((net == 0) ? MLP_BIAS_ENV : MLP_BIAS_SELF0);
                 double bv[4];
 #pragma unroll
@@ -541,15 +546,27 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp_oz(MlpOzArgs oa) {
                         }
                     }
                 if (net == 0) {
+                    // column maxima over the warp's 32 neurons: butterfly over the 8 lanes (fr) that hold the same two samples, then lane (fr, fq)
+                    // publishes two of the 16 columns of its samples -- two conflict-free shared-memory atomics per warp
+                    uint32_t keep0 = 0, keep1 = 0;
 #pragma unroll
                     for (int e = 0; e < 2; e++)
 #pragma unroll
                         for (int c = 0; c < 8; c++) {
-                            const uint32_t m = __reduce_max_sync(0x11111111u << fq, cm[e][c]);  // the 8 lanes (fr) that hold this sample
-                            if (fr == 0) atomicMax(&colmax[8 * (2 * fq + e) + c], m);
+                            uint32_t m = cm[e][c];
+                            m = max(m, __shfl_xor_sync(0xffffffffu, m, 4));
+                            m = max(m, __shfl_xor_sync(0xffffffffu, m, 8));
+                            m = max(m, __shfl_xor_sync(0xffffffffu, m, 16));
+                            if (8 * e + c == 2 * fr) keep0 = m;
+                            if (8 * e + c == 2 * fr + 1) keep1 = m;
                         }
+                    // column index 2 fr (+1) of this lane's sample pair: e = fr >> 2, c = (2 fr) & 7 (+1)
+                    atomicMax(&colmax[8 * (2 * fq + (fr >> 2)) + ((2 * fr) & 7)], keep0);
+                    atomicMax(&colmax[8 * (2 * fq + (fr >> 2)) + ((2 * fr) & 7) + 1], keep1);
                 }
+                if (warp == 0) { OZ_MARK(1, 5 * net + 3) }
                 __syncthreads();  // the first layer's output and its column maxima are in place
+                if (warp == 0) { OZ_MARK(1, 5 * net + 4) }
                 OZ_DBG(0)
             }
             if (net == 0) {

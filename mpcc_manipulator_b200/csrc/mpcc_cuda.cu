@@ -798,6 +798,8 @@ int mpcc_cuda_eval_robot_data(mpcc_cuda_handle* h, const double* q, const double
                 t[0] / t[6], t[1] / t[6], t[2] / t[6], t[3] / t[6], t[4] / t[6], t[5] / t[6], t[7] / t[6]);
         fprintf(stderr, "  trace (tile 1, layer 0): pass 0: issue %lld, until complete %lld | epilogue + barrier %lld | pass 1: issue %lld, until complete %lld ; chunk waits of the issuer per tile %lld\n",
                 t[9] - t[8], t[10] - t[8], t[11] - t[10], t[12] - t[11], t[13] - t[11], t[7] / t[6]);
+        fprintf(stderr, "  first layers (tile 1): env: staging %lld | 4 chunks of DFMA %lld | epilogue + column maxima %lld | barrier %lld ;  self: staging %lld | DFMA %lld | epilogue %lld | barrier %lld\n",
+                t[25] - t[24], t[26] - t[25], t[27] - t[26], t[28] - t[27], t[30] - t[29], t[31] - t[30], t[32] - t[31], t[33] - t[32]);
     }
     return MPCC_OK;
 }
