@@ -65,7 +65,10 @@ typedef struct {
     int32_t sqp_kernel;   /* must be 0 (one SQP kernel ships: a warp per instance) */
     int32_t reserved;     /* diagnostics: bit 0 = no exclusive-SM launch for recent long runners (scheduling only, same results);
                            * bit 1 = always the warp-per-instance SQP kernel, bit 2 = always the CTA-per-instance one
-                           * (default: CTA per instance when batch <= 2 x SMs -- the latency path --, else warp per instance) */
+                           * (default: CTA per instance when batch <= 2 x SMs -- the latency path --, else warp per instance);
+                           * bit 3 = collision networks entirely in fp64 (k_mlp: mma.sync.m8n8k4.f64) instead of the default kernel, which runs their
+                           * three 256 x 256 layers as exact int8 digit products on tcgen05 (k_mlp_oz; results within 1e-13 of each other);
+                           * bit 4 = print the per-phase cycle counts of that kernel's CTA 0 to stderr after mpcc_cuda_eval_robot_data */
 } mpcc_cuda_config;
 
 typedef struct mpcc_cuda_handle mpcc_cuda_handle;
