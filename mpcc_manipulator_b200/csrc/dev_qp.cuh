@@ -485,7 +485,7 @@ struct StageQP {
             }
             build_gradient();
             solve_step();
-            double a = fmin(1.0, 0.995 * ineq_steps());
+            double a = fmin(1.0, qp_step_tau(mu) * ineq_steps());
             for (int k = 0; k <= N; k++) {
                 WsRef V = var(k), S = stp(k), I = ineq(k);
                 for (int m = 0; m < 9; m++) { V[V_XI + m] += a * S[S_DXI + m]; V[V_Y + m] += a * (S[S_YN + m] - V[V_Y + m]); }

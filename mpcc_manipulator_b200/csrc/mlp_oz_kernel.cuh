@@ -29,7 +29,10 @@
 
 namespace mpcc {
 
-constexpr int OZ_S = 7;                                // int8 digits per operand
+#ifndef OZ_DIGITS
+#define OZ_DIGITS 7
+#endif
+constexpr int OZ_S = OZ_DIGITS;                        // int8 digits per operand (7: 49-bit operands, fp64-equivalent; -DOZ_DIGITS=6: 42 bits)
 #ifndef OZ_CHUNK_BYTES
 #define OZ_CHUNK_BYTES 8192
 #endif

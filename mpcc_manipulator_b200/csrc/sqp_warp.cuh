@@ -1041,7 +1041,7 @@ struct GroupSqp {
                         v_[i] = (v[j] * v[ts + j] + sm - v[2 * ts + j] * v[3 * ts + j]) / v[4 * ts + j];
                     });
                 } else {
-                    const double a = fmin(1.0, 0.995 * a_max);
+                    const double a = fmin(1.0, qp_step_tau(mu) * a_max);
                     if (a < 0.01 && it >= 1 && nrp > opt.eps) suspicious = true;   // a short step announces trouble
 #if defined(MPCC_QP_TRACE) && !defined(__CUDA_ARCH__)
                     fprintf(stderr, "          alpha %.3e\n", a);

@@ -654,7 +654,9 @@ def test_cta_kernel_agrees_with_warp_kernel(M, O, ee_home, rng):
             assert err[same].max() < 1e-7, err[same].max()     # same branch: same arithmetic up to reduction order
             n_same += int(same.sum()); n_tot += B
             u = ra["u0"]; x = a.sim_time_step(ra["x0"], u, 0.01)
-        assert n_same >= 0.85 * n_tot, (n_same, n_tot)
+        # (the interior point's tail is superlinear since the adaptive fraction-to-boundary rule: the two lane counts may stop one iteration apart,
+        #  the solutions then differ by the termination slack and more noise-level ties split: 80 % stay together, 85 % before)
+        assert n_same >= 0.7 * n_tot, (n_same, n_tot)
         assert a.stats()["launches"] == 6 and b.stats()["launches"] == 4
         a.close(); b.close()
 

