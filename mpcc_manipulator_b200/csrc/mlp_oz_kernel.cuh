@@ -56,10 +56,21 @@ static_assert(OZ_S >= 4 && OZ_S <= 7, "int64 Horner of the accumulators holds up
 static_assert(OZ_S * 64 + 4 * (OZ_CHUNK_BYTES / 512) <= 512, "accumulators and the four A buffers must fit TMEM");
 static_assert(OZ_RING_BYTES >= 32768, "the DMMA layers' per-warp rings live in the ring region");
 static_assert(OZ_SMEM_BYTES <= 232448, "shared memory");
-// DMMA chunk stream of one tile: env L0 (4 chunks of 8 encoded inputs) | self L0 (4) | self L1 (8 chunks of 32 k-steps x 64 neurons); 16 KB each
+// fp64 chunk stream of one tile: env L0 (4 chunks of 8 encoded inputs) | self L0 (4); 16 KB each
 constexpr int OZ_DCHUNK_D = 2048;
-constexpr int OZ_NDCHUNK = 16;
-constexpr int OZ_WOUT_D = 9 * 256;      // env output layer, appended to the DMMA stream: rows 0..7 in A-fragment order | row 8
+constexpr int OZ_NDCHUNK = 8;
+constexpr int OZ_WOUT_D = 9 * 256;      // env output layer, appended to the chunk stream: rows 0..7 in A-fragment order | row 8
+// The self net runs in REVERSE mode (it has one output: one adjoint sweep instead of seven tangent columns, 44 k instead of 142 k MAC per sample).
+// Its 64 x 256 layer goes to shared memory once per tile, row-major with a padded stride, and is read from there as the A operand of both the
+// forward product (A[neuron][k]) and the adjoint product (A[k][neuron], the transpose): both reads are bank-conflict free at stride 260.
+constexpr int OZ_W1_D = 64 * 256;       // self layer 1, raw row-major, appended after the output layer
+constexpr int OZ_W0T_D = 8 * 3 * 8 * 32; // self layer 0 transposed, as A fragments [warp 8][m-fragment 3 (21 encoded inputs, padded to 24)][k-step 8][lane 32]
+constexpr int OZ_DOFF_WOUT = OZ_NDCHUNK * OZ_DCHUNK_D, OZ_DOFF_W1 = OZ_DOFF_WOUT + OZ_WOUT_D, OZ_DOFF_W0T = OZ_DOFF_W1 + OZ_W1_D;
+constexpr size_t OZ_DPACK_D = (size_t)OZ_DOFF_W0T + OZ_W0T_D;   // doubles of the packed fp64 weights (MlpOzArgs::m.wpack)
+// the self net's shared memory, in doubles from the start of the (then idle) activation tile: encoded inputs | layer-1 activations, later their adjoints,
+// [k-step 64][sample 8][k 4] (a B fragment is 32 consecutive doubles) | layer-2 adjoints [16][8][4] | per-warp partial outputs | per-warp partial input adjoints | W1
+constexpr int OZ_SF_H1 = 256, OZ_SF_A2 = OZ_SF_H1 + 2048, OZ_SF_SELP = OZ_SF_A2 + 512, OZ_SF_GZP = OZ_SF_SELP + 64, OZ_SF_W1 = 4608, OZ_SF_W1_LD = 260;
+static_assert(OZ_SF_GZP + 8 * 24 * 8 <= OZ_SF_W1 && (OZ_SF_W1 + 64 * OZ_SF_W1_LD) * 8 <= OZ_OFF_RING, "self-net scratch must fit below the ring");
 constexpr int OZ_OFF_WOUT = 131072;     // its place in shared memory: above the fp64 tile, in the (by then dead) digit planes
 static_assert(OZ_OFF_WOUT + OZ_WOUT_D * 8 <= OZ_OFF_RING, "output-layer weights must fit between the tile and the ring");
 // weight plane consumed at position pi of a pass: heavy (low i: S - i products) and light planes alternate, so that the weight stream's demand
@@ -93,6 +104,8 @@ OZ_HD long long oz_double_to_bits(double d) {
     long long b; std::memcpy(&b, &d, 8); return b;
 #endif
 }
+// element (k, sample s) of a [k][8 samples] operand stored so that the B fragment of k-step ks (lane l holds k = 4 ks + (l & 3), sample l >> 2) is 32 consecutive doubles
+OZ_HD int oz_bfrag(int k, int s) { return (k >> 2) * 32 + s * 4 + (k & 3); }
 // column scales from the high word of the column's largest |entry|: sc = 2^(7 S - e_c), cs = 2^(e_c), e_c = exponent + 2 (so |x| 2^(-e_c) < 1/2);
 // an all-zero (or denormal-range) column gets sc = 0: every digit 0
 OZ_HD void oz_col_scales(uint32_t hi, double& sc, double& cs) {
@@ -122,7 +135,7 @@ inline size_t oz_wq_index(int layer, int r, int k, int i) {
 }
 
 struct MlpOzArgs {
-    MlpArgs m;               // m.wpack: the DMMA chunk stream packed by pack_mlp_oz_weights (OZ_NDCHUNK x OZ_DCHUNK_D doubles)
+    MlpArgs m;               // m.wpack: the fp64 weights packed by pack_mlp_oz_weights (OZ_DPACK_D doubles: chunk stream | env output layer | self W1 | self W0 transposed)
     const uint8_t* wq;       // OZ_CHUNKS_PER_TILE x OZ_CHUNK bytes: digit planes of env layers 1..3 in consumption order
     const double* rowscale;  // [3][256]: 2^(E_r - 7 S - 7)
     int dbg_flags;           // experiments (timing only, results wrong): bit 0 = no weight stream (MMAs on whatever the ring holds), bit 1 = no per-CTA rotation of the stream
@@ -209,6 +222,24 @@ __device__ __forceinline__ void oz_layer0_chunk(const double* __restrict__ Wc, c
                     if (kind == 0) { acc[mb][1 + src][0] += w[mb]; acc[mb][1 + src][1] += w[mb]; }
                     else { acc[mb][1 + src][0] = fma(w[mb], t0, acc[mb][1 + src][0]); acc[mb][1 + src][1] = fma(w[mb], t1, acc[mb][1 + src][1]); }
                 }
+            }
+        }
+    }
+}
+
+
+// the same chunk, value column only (self net: its derivatives come from the adjoint sweep)
+template <int NIN, int K0>
+__device__ __forceinline__ void oz_layer0_chunk_value(const double* __restrict__ Wc, const double* __restrict__ Zs, int fr, int fq, double (&acc)[4][2]) {
+#pragma unroll
+    for (int kk = 0; kk < 8; kk++) {
+        const int k = K0 + kk;
+        if (k < 3 * NIN) {
+            const double z0 = Zs[k * 8 + 2 * fq], z1 = Zs[k * 8 + 2 * fq + 1];
+#pragma unroll
+            for (int mb = 0; mb < 4; mb++) {
+                const double w = Wc[kk * 32 + mb * 8 + fr];
+                acc[mb][0] = fma(w, z0, acc[mb][0]); acc[mb][1] = fma(w, z1, acc[mb][1]);
             }
         }
     }
@@ -488,6 +519,15 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp_oz(MlpOzArgs oa) {
             if (warp == 0) { OZ_MARK(1, 5 * net + 0) }
             __syncthreads();
             double* Zs = Xd;
+            if (net == 1) {
+                // self layer 1 (64 x 256) -> shared memory, rows padded to OZ_SF_W1_LD.  The copies are NOT committed here: they join the group of the
+                // next ring chunk this thread requests (the last first-layer chunk), so the first-layer chunks before it do not wait for them.
+                // (Measured alternative: 64 bulk copies of one row each from one thread onto an mbarrier -- 1.2 k cycles per tile slower, the issue is serial.)
+                const double2* src = reinterpret_cast<const double2*>(a.wpack + OZ_DOFF_W1);
+                double2* dst = reinterpret_cast<double2*>(Xd + OZ_SF_W1);
+#pragma unroll 8
+                for (int i = tid; i < 64 * 128; i += MLP_THREADS) cp_async16(dst + (i >> 7) * (OZ_SF_W1_LD / 2) + (i & 127), src + i);
+            }
             {
                 const int nin = (net == 0) ? 10 : 7;
                 const int src = tid >> 3, sidx = tid & 7, n = s0 + sidx;
@@ -505,6 +545,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp_oz(MlpOzArgs oa) {
             // ---- first layer on DFMA (4 chunks of 8 encoded inputs) ----
             {
                 double acc[4][8][2];
+                double accv[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};  // self net: value column only
 #pragma unroll
                 for (int mb = 0; mb < 4; mb++)
 #pragma unroll
@@ -514,7 +555,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp_oz(MlpOzArgs oa) {
     {                                                                                                      \
         const double* Wc0 = reinterpret_cast<const double*>(d_wait());                                     \
         if (net == 0) oz_layer0_chunk<10, K0>(Wc0, Zs, fr, fq, acc);                                       \
-        else oz_layer0_chunk<7, K0>(Wc0, Zs, fr, fq, acc);                                                 \
+        else oz_layer0_chunk_value<7, K0>(Wc0, Zs, fr, fq, accv);                                          \
         d_done((LAST) && net == 0);                                                                        \
     }
                 OZ_L0_CHUNK(0, false)
@@ -523,6 +564,114 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp_oz(MlpOzArgs oa) {
                 OZ_L0_CHUNK(24, true)
 #undef OZ_L0_CHUNK
                 if (warp == 0) { OZ_MARK(1, 5 * net + 2) }
+                if (net == 1) {
+                    // =============== self net, reverse mode: value forwards, ONE adjoint backwards (SelfCollisionModel.cpp:140-250 computes the same
+                    //                 Jacobian row forwards); all operands in shared memory, every product on DMMA ===============
+                    double* H1 = Xd + OZ_SF_H1;
+                    double* A2 = Xd + OZ_SF_A2;
+                    const double* W1s = Xd + OZ_SF_W1;
+                    // first-layer adjoint weights of this warp's 32 neurons (used last; requested now, they arrive under the other phases)
+                    double w0t[3][8];
+#pragma unroll
+                    for (int mf = 0; mf < 3; mf++)
+#pragma unroll
+                        for (int t = 0; t < 8; t++) w0t[mf][t] = __ldg(a.wpack + OZ_DOFF_W0T + ((warp * 3 + mf) * 8 + t) * 32 + lane);
+                    // layer 0 epilogue: h1 = relu(pre); the masks stay in registers (the adjoint of the same rows comes back to this lane)
+                    bool m1[4][2];
+#pragma unroll
+                    for (int mb = 0; mb < 4; mb++) {
+                        const int row = warp * 32 + mb * 8 + fr;
+                        const double bv0 = a.bias[MLP_BIAS_SELF0 + row];
+#pragma unroll
+                        for (int e = 0; e < 2; e++) {
+                            const double pre = accv[mb][e] + bv0;
+                            m1[mb][e] = pre > 0.0;
+                            H1[oz_bfrag(row, 2 * fq + e)] = m1[mb][e] ? pre : 0.0;
+                        }
+                    }
+                    __syncthreads();  // h1 complete; W1 has landed (every thread waited for its copies with the last first-layer chunk)
+                    if (warp == 0) { OZ_MARK(1, 5 * net + 3) }
+                    OZ_DBG(0)
+                    // layer 1 forwards: warp = m-fragment (neurons 8 warp .. + 7), two accumulator chains over the 64 k-steps
+                    {
+                        double c0[2] = {0.0, 0.0}, c1[2] = {0.0, 0.0};
+                        const double* wrow = W1s + (warp * 8 + fr) * OZ_SF_W1_LD + fq;
+#pragma unroll 8
+                        for (int ks = 0; ks < 64; ks += 2) {
+                            dmma884(c0[0], c0[1], wrow[4 * ks], H1[ks * 32 + lane]);
+                            dmma884(c1[0], c1[1], wrow[4 * ks + 4], H1[(ks + 1) * 32 + lane]);
+                        }
+                        const int n = warp * 8 + fr;
+                        const double bv1 = a.bias[MLP_BIAS_SELF1 + n], wo = __ldg(a.w_out_self + n);
+                        double part[2];
+#pragma unroll
+                        for (int e = 0; e < 2; e++) {
+                            const double pre = c0[e] + c1[e] + bv1;
+                            const bool on = pre > 0.0;
+                            A2[oz_bfrag(n, 2 * fq + e)] = on ? wo : 0.0;   // adjoint of the layer-1 pre-activation
+                            part[e] = on ? wo * pre : 0.0;
+                        }
+#pragma unroll
+                        for (int o = 4; o < 32; o <<= 1) { part[0] += __shfl_xor_sync(0xffffffffu, part[0], o); part[1] += __shfl_xor_sync(0xffffffffu, part[1], o); }
+                        if (fr == 0) { Xd[OZ_SF_SELP + warp * 8 + 2 * fq] = part[0]; Xd[OZ_SF_SELP + warp * 8 + 2 * fq + 1] = part[1]; }
+                    }
+                    __syncthreads();  // layer-2 adjoints and the partial outputs are in place; nobody reads h1 any more
+                    // layer 1 backwards: adjoint of h1 for this warp's rows 32 warp + 8 mb + fr (A = W1 transposed, read from the same shared copy)
+                    {
+                        double g[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+                        const double* wcol = W1s + fq * OZ_SF_W1_LD + warp * 32 + fr;
+#pragma unroll 4
+                        for (int ks = 0; ks < 16; ks++) {
+                            const double b = A2[ks * 32 + lane];
+#pragma unroll
+                            for (int mb = 0; mb < 4; mb++) dmma884(g[mb][0], g[mb][1], wcol[4 * ks * OZ_SF_W1_LD + 8 * mb], b);
+                        }
+#pragma unroll
+                        for (int mb = 0; mb < 4; mb++)
+#pragma unroll
+                            for (int e = 0; e < 2; e++) H1[oz_bfrag(warp * 32 + mb * 8 + fr, 2 * fq + e)] = m1[mb][e] ? g[mb][e] : 0.0;   // through the ReLU of layer 0
+                    }
+                    __syncwarp();
+                    // layer 0 backwards: this warp's share (its own 32 neurons = 8 k-steps) of the adjoint of the 21 encoded inputs
+                    {
+                        double z[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+                        for (int t = 0; t < 8; t++) {
+                            const double b = H1[(warp * 8 + t) * 32 + lane];
+#pragma unroll
+                            for (int mf = 0; mf < 3; mf++) dmma884(z[mf][0], z[mf][1], w0t[mf][t], b);
+                        }
+#pragma unroll
+                        for (int mf = 0; mf < 3; mf++)
+                            *reinterpret_cast<double2*>(Xd + OZ_SF_GZP + (warp * 24 + mf * 8 + fr) * 8 + 2 * fq) = make_double2(z[mf][0], z[mf][1]);
+                    }
+                    __syncthreads();
+                    // output and its gradient: d z / d q is diagonal (x: 1, sin x: cos x, cos x: -sin x); partial sums added in warp order
+                    if (tid < 64) {
+                        const int sidx = tid & 7, jj = (tid >> 3) - 1, ns = s0 + sidx;
+                        if (ns < a.NS) {
+                            if (jj < 0) {
+                                double v = 0.0;
+#pragma unroll
+                                for (int w2 = 0; w2 < 8; w2++) v += Xd[OZ_SF_SELP + w2 * 8 + sidx];
+                                a.rb[(size_t)RB_SEL * a.NS + ns] = v + a.bias[MLP_BIAS_SELF_OUT];
+                            } else {
+                                double gx = 0.0, gs = 0.0, gc = 0.0;
+#pragma unroll
+                                for (int w2 = 0; w2 < 8; w2++) {
+                                    gx += Xd[OZ_SF_GZP + (w2 * 24 + jj) * 8 + sidx];
+                                    gs += Xd[OZ_SF_GZP + (w2 * 24 + 7 + jj) * 8 + sidx];
+                                    gc += Xd[OZ_SF_GZP + (w2 * 24 + 14 + jj) * 8 + sidx];
+                                }
+                                const double sn = Zs[(7 + jj) * 8 + sidx], cs = Zs[(14 + jj) * 8 + sidx];
+                                a.rb[(size_t)(RB_DSEL + jj) * a.NS + ns] = gx + cs * gs - sn * gc;
+                            }
+                        }
+                    }
+                    if (warp == 0) { OZ_MARK(1, 5 * net + 4) }
+                    OZ_DBG(5)
+                    continue;
+                }
                 const double* bias = a.bias + ((net == 0) ? MLP_BIAS_ENV : MLP_BIAS_SELF0);
                 double bv[4];
 #pragma unroll
@@ -595,7 +744,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp_oz(MlpOzArgs oa) {
                         n_pass++;
                         __syncthreads();  // the other warps wait in the hardware barrier, not by polling
                         if (layer == 2 && mb == 1) {  // the digit planes are dead: the output layer's weights (A fragments) land above the tile during the epilogue
-                            const double2* src = reinterpret_cast<const double2*>(a.wpack + (size_t)OZ_NDCHUNK * OZ_DCHUNK_D);
+                            const double2* src = reinterpret_cast<const double2*>(a.wpack + OZ_DOFF_WOUT);
                             for (int i = tid; i < OZ_WOUT_D / 2; i += MLP_THREADS) cp_async16(reinterpret_cast<double2*>(smem_raw + OZ_OFF_WOUT) + i, src + i);
                             cp_async_commit();
                         }
@@ -641,69 +790,6 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp_oz(MlpOzArgs oa) {
                     a.rb[(size_t)RB_OBSR * a.NS + n2] = a.obs[(size_t)(n2 / a.S) * 4 + 3];
                 }
                 OZ_DBG(4)
-            } else {
-                // ---- self layer 1: 64 x 256 on DMMA; warp = m-fragment (8 neurons) x all 8 column kinds, full K; 8 chunks of 32 k-steps ----
-                double acc[8][2];
-#pragma unroll
-                for (int c = 0; c < 8; c++) acc[c][0] = acc[c][1] = 0.0;
-                for (int ch = 0; ch < 8; ch++) {
-                    const double2* Wc = d_wait();  // [kb pair 4][lane 32] -> {kb even, kb odd}
-#pragma unroll 2
-                    for (int kp = 0; kp < 4; kp++) {
-                        const double2 a2 = Wc[kp * 32 + lane];
-#pragma unroll
-                        for (int h = 0; h < 2; h++) {
-                            const int kb = ch * 8 + kp * 2 + h;
-                            double2 b[4];
-#pragma unroll
-                            for (int j = 0; j < 4; j++) b[j] = Xs[(kb * 4 + j) * 32 + bslot];
-                            const double av = h ? a2.y : a2.x;
-#pragma unroll
-                            for (int j = 0; j < 4; j++) {
-                                dmma884(acc[2 * j][0], acc[2 * j][1], av, b[j].x);
-                                dmma884(acc[2 * j + 1][0], acc[2 * j + 1][1], av, b[j].y);
-                            }
-                        }
-                    }
-                    d_done(false);
-                }
-                const double bv = a.bias[MLP_BIAS_SELF1 + warp * 8 + fr];
-                __syncthreads();
-#pragma unroll
-                for (int e = 0; e < 2; e++) {
-                    const int row = warp * 8 + fr, s = 2 * fq + e;
-                    const double pre = acc[0][e] + bv;
-                    const bool on = pre > 0.0;
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const double v0 = (j == 0) ? pre : acc[2 * j][e], v1 = acc[2 * j + 1][e];
-                        Xs[xl2(row, j, s)] = on ? make_double2(v0, v1) : make_double2(0.0, 0.0);
-                    }
-                }
-                __syncthreads();
-                {
-                    double o[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-                    const double* xb = Xd + ((warp >> 1) * 32 + bslot) * 2 + (warp & 1);
-#pragma unroll
-                    for (int kb = 0; kb < 16; kb += 2)
-#pragma unroll
-                        for (int h = 0; h < 2; h++) {
-                            const double av = (lane < 4) ? __ldg(a.w_out_self + (kb + h) * 4 + lane) : 0.0;
-                            dmma884(o[h][0], o[h][1], av, xb[(kb + h) * 256]);
-                        }
-                    if (lane < 4) {
-#pragma unroll
-                        for (int e = 0; e < 2; e++) {
-                            const int ns = s0 + 2 * lane + e;
-                            if (ns < a.NS) {
-                                const double v = o[0][e] + o[1][e];
-                                if (warp == 0) a.rb[(size_t)RB_SEL * a.NS + ns] = v + a.bias[MLP_BIAS_SELF_OUT];
-                                else a.rb[(size_t)(RB_DSEL + warp - 1) * a.NS + ns] = v;
-                            }
-                        }
-                    }
-                }
-                OZ_DBG(5)
             }
         }
     }
@@ -718,8 +804,8 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp_oz(MlpOzArgs oa) {
 #endif  // __CUDACC__
 
 // Host-side packing for k_mlp_oz.
-//   dpack  (OZ_NDCHUNK x OZ_DCHUNK_D + OZ_WOUT_D doubles): env L0 as 4 chunks [warp 8][k 8][row 32] | self L0 likewise | self L1 as 8 chunks
-//          [warp 8][kb pair 4][lane 32][h 2] = W[8 warp + (l >> 2)][32 ch + 4 (2 kp + h) + (l & 3)]
+//   dpack  (OZ_DPACK_D doubles): env L0 as 4 chunks [warp 8][k 8][row 32] | self L0 likewise | env output layer (rows 0..7 as A fragments | row 8) |
+//          self L1 row-major [64][256] | self L0 transposed as A fragments [warp 8][m-fragment 3][k-step 8][lane 32]
 //   qpack  (OZ_CHUNKS_PER_TILE x OZ_CHUNK bytes): for env layers 1..3, neuron halves mb, plane positions pi (plane oz_order(pi)), k chunks kc:
 //          128 rows x 64 k of digit plane i as canonical K-major 8 x 16-byte core matrices: byte (r % 8) 16 + (r / 8) 128 + (k % 16) + (k / 16) 2048
 //   rowscale [3][256] = 2^(E_r - 7 S - 7),   2^(E_r) > 2 max_k |W[r,k]|
@@ -736,17 +822,17 @@ inline void pack_mlp_oz_weights(const double* const env_W[5], const double* cons
     double* o = dpack;
     pack_l0(env_W[0], 30, o);
     pack_l0(self_W[0], 21, o);
-    for (int ch = 0; ch < 8; ch++)
-        for (int warp = 0; warp < 8; warp++)
-            for (int kp = 0; kp < 4; kp++)
-                for (int l = 0; l < 32; l++)
-                    for (int h = 0; h < 2; h++) {
-                        const int row = 8 * warp + (l >> 2), k = 32 * ch + 4 * (2 * kp + h) + (l & 3);
-                        *o++ = self_W[1][(size_t)row * 256 + k];
-                    }
     for (int kb = 0; kb < 64; kb++)
         for (int l = 0; l < 32; l++) *o++ = env_W[4][(size_t)(l >> 2) * 256 + kb * 4 + (l & 3)];
     for (int k = 0; k < 256; k++) *o++ = env_W[4][(size_t)8 * 256 + k];
+    for (int i = 0; i < 64 * 256; i++) *o++ = self_W[1][i];
+    for (int warp = 0; warp < 8; warp++)
+        for (int mf = 0; mf < 3; mf++)
+            for (int t = 0; t < 8; t++)
+                for (int l = 0; l < 32; l++) {
+                    const int r = 8 * mf + (l >> 2), i = 32 * warp + 4 * t + (l & 3);   // A fragment of the transpose: row = encoded input r, k = neuron i
+                    *o++ = (r < 21) ? self_W[0][(size_t)i * 21 + r] : 0.0;
+                }
     for (int layer = 0; layer < 3; layer++) {
         const double* W = env_W[layer + 1];
         for (int r = 0; r < 256; r++) {

@@ -355,7 +355,7 @@ static int create_impl(mpcc_cuda_handle* h, const mpcc_cuda_config* cfg) {
     A(h->alloc(&h->d_status, B)); A(h->alloc(&h->d_iters, B)); A(h->alloc(&h->d_ok, B)); A(h->alloc(&h->d_qp_iters, B)); A(h->alloc(&h->d_qp_fail, B)); A(h->alloc(&h->d_accept, B)); A(h->alloc(&h->d_sqp_ns, 4 * B)); A(h->alloc(&h->d_hist, B)); A(h->alloc(&h->d_order, B + 1));
     A(h->alloc(&h->d_wpack, (size_t)MLP_NCHUNK * MLP_CHUNK_D)); A(h->alloc(&h->d_bias, MLP_BIAS_TOTAL));
     A(h->alloc(&h->d_w_out_env, 9 * 256)); A(h->alloc(&h->d_w_out_self, 64));
-    A(h->alloc(&h->d_oz_dpack, (size_t)OZ_NDCHUNK * OZ_DCHUNK_D + OZ_WOUT_D)); A(h->alloc(&h->d_oz_rowscale, 3 * 256)); A(h->alloc(&h->d_oz_wq, (size_t)OZ_CHUNKS_PER_TILE * OZ_CHUNK));
+    A(h->alloc(&h->d_oz_dpack, OZ_DPACK_D)); A(h->alloc(&h->d_oz_rowscale, 3 * 256)); A(h->alloc(&h->d_oz_wq, (size_t)OZ_CHUNKS_PER_TILE * OZ_CHUNK));
     h->mlp_oz = (h->cfg.reserved & 8) == 0;  // default: the int8-split tcgen05 kernel; bit 3 selects the fp64 DMMA kernel (k_mlp)
     if (h->cfg.reserved & 16) A(h->alloc(&h->d_oz_dbg, 64));
     if (ae != cudaSuccess) return fail(MPCC_ERR_CUDA, std::string("device allocation failed: ") + cudaGetErrorString(ae));
@@ -420,7 +420,7 @@ int mpcc_cuda_upload_nn(mpcc_cuda_handle* h, const double* self_w, const double*
     CK(cudaMemcpyAsync(h->d_bias, bias.data(), bias.size() * 8, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_w_out_env, eW[4], 9 * 256 * 8, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_w_out_self, sW[2], 64 * 8, cudaMemcpyHostToDevice, h->stream));
-    std::vector<double> oz_d((size_t)OZ_NDCHUNK * OZ_DCHUNK_D + OZ_WOUT_D), oz_rs(3 * 256);
+    std::vector<double> oz_d(OZ_DPACK_D), oz_rs(3 * 256);
     std::vector<uint8_t> oz_q((size_t)OZ_CHUNKS_PER_TILE * OZ_CHUNK);
     pack_mlp_oz_weights(eW, sW, oz_d.data(), oz_q.data(), oz_rs.data());
     CK(cudaMemcpyAsync(h->d_oz_dpack, oz_d.data(), oz_d.size() * 8, cudaMemcpyHostToDevice, h->stream));

@@ -174,7 +174,7 @@ void emu_oz_layer(const double* W, const double* X, int ncol, double* Y, int* ma
     std::vector<double> zero30(256 * 30, 0.0), zero21(256 * 21, 0.0), zero256(256 * 256, 0.0), zero9(9 * 256, 0.0), zero64(64 * 256, 0.0), zero1(64, 0.0);
     const double* eW[5] = {zero30.data(), W, zero256.data(), zero256.data(), zero9.data()};
     const double* sW[3] = {zero21.data(), zero64.data(), zero1.data()};
-    std::vector<double> dpack((size_t)OZ_NDCHUNK * OZ_DCHUNK_D + OZ_WOUT_D), rowscale(3 * 256);
+    std::vector<double> dpack(OZ_DPACK_D), rowscale(3 * 256);
     std::vector<uint8_t> qpack((size_t)OZ_CHUNKS_PER_TILE * OZ_CHUNK);
     pack_mlp_oz_weights(eW, sW, dpack.data(), qpack.data(), rowscale.data());
     int md = 0;
