@@ -68,7 +68,9 @@ typedef struct {
                            * (default: CTA per instance when batch <= 2 x SMs -- the latency path --, else warp per instance);
                            * bit 3 = collision networks entirely in fp64 (k_mlp: mma.sync.m8n8k4.f64) instead of the default kernel, which runs their
                            * three 256 x 256 layers as exact int8 digit products on tcgen05 (k_mlp_oz; results within 1e-13 of each other);
-                           * bit 4 = print the per-phase cycle counts of that kernel's CTA 0 to stderr after mpcc_cuda_eval_robot_data */
+                           * bit 4 = print the per-phase cycle counts of that kernel's CTA 0 to stderr after mpcc_cuda_eval_robot_data;
+                           * bit 8 = mpcc_cuda_run_cycle always copies mpc_horizon behind the kernel (default: a PINNED `horizon` buffer is written
+                           * by the SQP kernel directly, under its own run time; a pageable one is copied) */
 } mpcc_cuda_config;
 
 typedef struct mpcc_cuda_handle mpcc_cuda_handle;

@@ -198,11 +198,16 @@ class BatchMPC:
         _check(lib().mpcc_cuda_reset(self.h))
 
     # ---- the control cycle ----
-    def run_cycle(self, x0, u0, obs=None, want_horizon=True):
+    def run_cycle(self, x0, u0, obs=None, want_horizon=True, horizon_out=None):
+        """horizon_out: optional caller-owned C-contiguous float64 array [B][N+1][17] for MPCReturn::mpc_horizon.  If it lives in pinned host
+        memory (e.g. torch.empty(...).pin_memory().numpy()) the SQP kernel writes it directly; any other buffer is filled by a copy."""
         x0 = _f64(x0).reshape(self.B, NX).copy()
         u0 = _f64(u0).reshape(self.B, NU)
         obs = None if obs is None else _f64(obs).reshape(self.B, 4)
         u = np.zeros((self.B, NU)); hor = np.zeros((self.B, self.S, HZ)) if want_horizon else None
+        if horizon_out is not None:
+            assert horizon_out.dtype == np.float64 and horizon_out.flags["C_CONTIGUOUS"] and horizon_out.size == self.B * self.S * HZ
+            hor = horizon_out
         st = np.zeros(self.B, np.int32); it = np.zeros(self.B, np.int32); ok = np.zeros(self.B, np.int32)
         _check(lib().mpcc_cuda_run_cycle(self.h, _p(x0), _p(u0), _p(obs), _p(u), _p(hor), _p(st), _p(it), _p(ok)))
         return dict(x0=x0, u0=u, horizon=hor, status=st, iters=it, ok=ok)

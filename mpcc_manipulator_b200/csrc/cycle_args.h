@@ -26,6 +26,8 @@ struct CycleArgs {
     double* rb;        // [150][B*S]
     double* u_out;     // [B][8]
     double* horizon;   // [B][S][17]
+    double* horizon_host;  // optional second destination of the horizon: the caller's PINNED host buffer, written by the SQP kernel as each instance finishes
+                           // (the 11.7 MB of mpc_horizon then cross PCIe under the kernel instead of in a copy behind it); nullptr: none
     int32_t* status; int32_t* iters; int32_t* ok; int32_t* qp_iters; int32_t* qp_fail; int32_t* accept_mask;
     long long* sqp_ns;  // per-instance duration of the SQP loop (ComputeTime::total analogue)
     int32_t* hist;      // per-instance history of SQP iteration counts (4 cycles, one byte each): scheduling hint only

@@ -207,6 +207,7 @@ struct mpcc_cuda_handle {
     double *d_warm = nullptr, *d_step = nullptr, *d_trial = nullptr, *d_filt = nullptr, *d_ws = nullptr, *d_qs = nullptr, *d_rb = nullptr;
     WarmFlags* d_flags = nullptr;
     double *d_u_out = nullptr, *d_horizon = nullptr;
+    double* horizon_host = nullptr;  // this cycle's mapped host destination of the horizon (mpcc_cuda_run_cycle with a pinned buffer), else nullptr
     int32_t *d_status = nullptr, *d_iters = nullptr, *d_ok = nullptr, *d_qp_iters = nullptr, *d_qp_fail = nullptr, *d_accept = nullptr;
     long long* d_sqp_ns = nullptr;
     int32_t *d_hist = nullptr, *d_order = nullptr;
@@ -262,7 +263,7 @@ static CycleArgs make_args(mpcc_cuda_handle* h, double* d_x0, const double* d_u0
     a.tracks = h->d_tracks; a.track_id = h->d_track_id;
     a.x0 = d_x0; a.u0 = d_u0; a.obs = d_obs;
     a.warm = h->d_warm; a.step = h->d_step; a.trial = h->d_trial; a.filt = h->d_filt; a.ws = h->d_ws; a.flags = h->d_flags;
-    a.qs = h->d_qs; a.rb = h->d_rb; a.u_out = h->d_u_out; a.horizon = h->d_horizon;
+    a.qs = h->d_qs; a.rb = h->d_rb; a.u_out = h->d_u_out; a.horizon = h->d_horizon; a.horizon_host = h->horizon_host;
     a.status = h->d_status; a.iters = h->d_iters; a.ok = h->d_ok; a.qp_iters = h->d_qp_iters; a.qp_fail = h->d_qp_fail; a.accept_mask = h->d_accept; a.sqp_ns = h->d_sqp_ns; a.hist = h->d_hist; a.order = h->d_order;
     a.qp = QpOptions{h->cfg.qp_max_iter, h->cfg.qp_eps};
     return a;
@@ -696,10 +697,20 @@ int mpcc_cuda_run_cycle(mpcc_cuda_handle* h, double* x0, const double* u0, const
     CK(cudaMemcpyAsync(h->d_x0, x0, B * NX * 8, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_u0, u0, B * NU * 8, cudaMemcpyHostToDevice, h->stream));
     if (obs) CK(cudaMemcpyAsync(h->d_obs, obs, B * 4 * 8, cudaMemcpyHostToDevice, h->stream));
+    // MPCReturn::mpc_horizon is by far the largest result (B x (N+1) x 17 doubles).  If the caller's buffer is pinned (mapped) host memory the SQP
+    // kernel writes it there directly as each instance finishes, so it crosses PCIe under the kernel; otherwise it is copied behind the kernel.
+    double* hor_mapped = nullptr;
+    if (horizon && !(h->cfg.reserved & 256)) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, horizon) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) hor_mapped = (double*)at.devicePointer;
+        else cudaGetLastError();
+    }
+    h->horizon_host = hor_mapped;
     rc = mpcc_cuda_run_cycle_device(h, h->d_x0, h->d_u0, obs ? h->d_obs : nullptr);
+    h->horizon_host = nullptr;
     if (rc) return rc;
     CK(cudaMemcpyAsync(x0, h->d_x0, B * NX * 8, cudaMemcpyDeviceToHost, h->stream));
-    return mpcc_cuda_read_results(h, u_out, horizon, status, sqp_iters, ok);
+    return mpcc_cuda_read_results(h, u_out, hor_mapped ? nullptr : horizon, status, sqp_iters, ok);
 }
 
 int mpcc_cuda_result_pointers(mpcc_cuda_handle* h, double** d_u_out, double** d_horizon, int32_t** d_status, int32_t** d_iters, int32_t** d_ok) {

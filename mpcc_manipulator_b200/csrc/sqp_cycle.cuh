@@ -35,7 +35,8 @@ __device__ __forceinline__ void sqp_group_cycle(const CycleArgs& a, double* wws,
     w.W.sync();
     const bool ok = r.status == SOLVED || (r.status == MAX_ITER_EXCEEDED && fl.failed < 5);
     double* h = a.horizon + (size_t)b * HN;
-    for (int e = lane; e < HN; e += NL) { const double v = w.GUESS[e]; a.warm[(size_t)e * B + b] = v; h[e] = v; }
+    double* hh = a.horizon_host ? a.horizon_host + (size_t)b * HN : nullptr;
+    for (int e = lane; e < HN; e += NL) { const double v = w.GUESS[e]; a.warm[(size_t)e * B + b] = v; h[e] = v; if (hh) hh[e] = v; }
     if (lane < NU) a.u_out[b * NU + lane] = w.GUESS[NX + lane];
     if (lane == 0) {
         a.flags[b] = fl;

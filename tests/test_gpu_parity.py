@@ -750,3 +750,30 @@ def test_gather_api_single_rank(M, O, ee_home):
         assert np.array_equal(g["u0"], r["u0"]) and np.array_equal(g["status"], r["status"]) and np.array_equal(g["iters"], r["iters"])
         u = r["u0"]; x = mpc.sim_time_step(r["x0"], u)
     mpc.close()
+
+
+def test_pinned_horizon_is_written_by_the_kernel(M, O, ee_home, rng):
+    """mpcc_cuda_run_cycle with a PINNED host buffer for MPCReturn::mpc_horizon: the SQP kernel writes it directly (it crosses PCIe under the
+    kernel).  Must equal, bit for bit, what a pageable buffer gets by the copy behind the kernel, what read_results returns afterwards from the
+    device copy, and the path with the direct write disabled (mpcc_cuda_config.reserved bit 8) -- over a cold and two warm cycles, for both
+    SQP kernels (warp per instance: B = 300; CTA per instance: B = 24)."""
+    import torch
+    for B, N in ((300, 12), (24, 20)):
+        x0 = np.tile(np.r_[O.Q_HOME, 0.0, 0.0], (B, 1)); x0[:, :7] += rng.uniform(-0.05, 0.05, (B, 7))
+        a = make_mpc(M, B, N, ee_home)
+        b = make_mpc(M, B, N, ee_home)
+        c = make_mpc(M, B, N, ee_home, flags=256)
+        pinned = torch.full((B, N + 1, 17), float("nan"), dtype=torch.float64).pin_memory()
+        pinned_c = torch.full((B, N + 1, 17), float("nan"), dtype=torch.float64).pin_memory()
+        x, u = x0.copy(), np.zeros((B, 8))
+        for cycle in range(3):
+            ra = a.run_cycle(x, u, horizon_out=pinned.numpy())
+            rb_ = b.run_cycle(x, u)
+            rc = c.run_cycle(x, u, horizon_out=pinned_c.numpy())
+            assert np.array_equal(ra["horizon"], rb_["horizon"]) and np.array_equal(rc["horizon"], rb_["horizon"]), cycle
+            assert np.array_equal(a.read_results(want_horizon=True)["horizon"], rb_["horizon"])
+            assert np.array_equal(ra["u0"], rb_["u0"]) and np.array_equal(ra["status"], rb_["status"])
+            assert np.array_equal(ra["horizon"][:, 0, 9:], ra["u0"])
+            u = ra["u0"]; x = a.sim_time_step(ra["x0"], u)
+        for m in (a, b, c):
+            m.close()
