@@ -55,4 +55,10 @@ void launch_sqp_cta(const CycleArgs& a, double* wws, cudaStream_t s);
 void launch_solve_ocp_cta(const CycleArgs& a, double* wws, double* guess, const double* rb, const double* cur_u, int n, double* steps, double* alphas,
                           int32_t* qp_ok, int max_log, int32_t* n_logged, cudaStream_t s);
 
+// the same two kernel families with the second-order correction compiled in (k_sqp_soc.cu); cta: one CTA per instance
+cudaError_t configure_sqp_soc();
+void launch_sqp_soc(const CycleArgs& a, double* wws, bool cta, cudaStream_t s);
+void launch_solve_ocp_soc(const CycleArgs& a, double* wws, bool cta, double* guess, const double* rb, const double* cur_u, int n, double* steps, double* alphas,
+                          int32_t* qp_ok, int max_log, int32_t* n_logged, cudaStream_t s);
+
 }  // namespace mpcc

@@ -220,6 +220,7 @@ struct mpcc_cuda_handle {
     int64_t launches = 0;
     bool profiling = false;
     bool use_cta = false;   // SQP kernel family of this handle: k_sqp_cta (one CTA per instance) or k_sqp_warp
+    bool soc = false;       // some parameter set has sqp.do_SOC: the kernels of k_sqp_soc.cu (second-order correction compiled in) run instead
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // prologue | kin | mlp | sqp boundaries
     cudaStream_t aux = nullptr;                 // high-priority stream of the exclusive-SM straggler launch
     cudaEvent_t ev_pre = nullptr, ev_order = nullptr, ev_aux = nullptr;
@@ -367,6 +368,7 @@ static int create_impl(mpcc_cuda_handle* h, const mpcc_cuda_config* cfg) {
     CK(cudaFuncSetAttribute(k_mlp_oz, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM_BYTES));
     CK(configure_sqp_warp(h->N));
     CK(configure_sqp_cta());
+    CK(configure_sqp_soc());
     // kernel family: one CTA per instance (latency path) when the batch cannot fill the machine with warps anyway
     h->use_cta = (h->cfg.reserved & 4) ? true : (h->cfg.reserved & 2) ? false : (h->B <= 2 * h->num_sms);
     CK(cudaStreamSynchronize(h->stream));
@@ -459,11 +461,13 @@ int mpcc_cuda_load_nn(mpcc_cuda_handle* h, const char* self_path, const char* en
 int mpcc_cuda_set_params(mpcc_cuda_handle* h, const double* params, int32_t n_sets) {
     if (!h || !params) return fail(MPCC_ERR_INVALID, "null argument");
     if (n_sets != 1 && n_sets != h->B) return fail(MPCC_ERR_INVALID, "n_sets must be 1 or batch");
+    bool any_soc = false;
     for (int s = 0; s < n_sets; s++) {
         const Params& p = *(const Params*)(params + (size_t)s * PARAMS_DOUBLES);
         if (p.max_iter < 1 || p.max_iter > MAX_SQP_ITER) return fail(MPCC_ERR_INVALID, "sqp.max_iter must be in [1, 128]");
         if (p.line_search_max_iter < 1) return fail(MPCC_ERR_INVALID, "sqp.line_search_max_iter must be >= 1");
-        if (p.do_SOC != 0 || p.use_BFGS != 0) return fail(MPCC_ERR_INVALID, "sqp.do_SOC / sqp.use_BFGS are not implemented on this path (reference defaults: false)");
+        if (p.use_BFGS != 0) return fail(MPCC_ERR_INVALID, "sqp.use_BFGS is not implemented on this path (reference default: false; DESIGN.md 9)");
+        any_soc = any_soc || p.do_SOC != 0;
         for (int i = 0; i < NX; i++) if (!(p.Tx[i] > 0)) return fail(MPCC_ERR_INVALID, "normalization entries must be positive");
         for (int i = 0; i < NU; i++) if (!(p.Tu[i] > 0)) return fail(MPCC_ERR_INVALID, "normalization entries must be positive");
     }
@@ -473,6 +477,7 @@ int mpcc_cuda_set_params(mpcc_cuda_handle* h, const double* params, int32_t n_se
     CK(cudaMemcpyAsync(h->d_params, params, (size_t)n_sets * sizeof(Params), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->n_param_sets = n_sets;
+    h->soc = any_soc;
     h->h_params.assign(params, params + PARAMS_DOUBLES);
     h->have_params = true;
     return MPCC_OK;
@@ -663,7 +668,8 @@ int mpcc_cuda_run_cycle_device(mpcc_cuda_handle* h, double* d_x0, const double* 
     rc = launch_robot_data(h, obs, h->S, prof);
     if (rc) return rc;
     if (prof) cudaEventRecord(h->ev[3], h->stream);
-    if (h->use_cta) launch_sqp_cta(a, h->d_wws, h->stream);
+    if (h->soc) launch_sqp_soc(a, h->d_wws, h->use_cta, h->stream);
+    else if (h->use_cta) launch_sqp_cta(a, h->d_wws, h->stream);
     else {
         launch_sqp_warp(a, h->d_wws, h->stream, (h->cfg.reserved & 1) ? nullptr : h->aux, h->ev_pre, h->ev_order, h->ev_aux, h->hint);
         h->launches += (h->cfg.reserved & 1) ? 1 : 2;  // + the launch-order kernel (+ the exclusive launch)
@@ -891,7 +897,8 @@ int mpcc_cuda_solve_ocp(mpcc_cuda_handle* h, double* guess, const double* rb, co
     CK(cudaMemcpyAsync(d_cu, cur_u, (size_t)n * NU * 8, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemsetAsync(d_nl, 0, (size_t)n * 4, h->stream));
     CycleArgs a = make_args(h, h->d_x0, h->d_u0, h->d_obs_dummy);
-    if (h->use_cta) launch_solve_ocp_cta(a, h->d_wws, d_g, d_rb, d_cu, n, d_steps, d_alphas, d_qpok, max_log, d_nl, h->stream);
+    if (h->soc) launch_solve_ocp_soc(a, h->d_wws, h->use_cta, d_g, d_rb, d_cu, n, d_steps, d_alphas, d_qpok, max_log, d_nl, h->stream);
+    else if (h->use_cta) launch_solve_ocp_cta(a, h->d_wws, d_g, d_rb, d_cu, n, d_steps, d_alphas, d_qpok, max_log, d_nl, h->stream);
     else launch_solve_ocp_warp(a, h->d_wws, d_g, d_rb, d_cu, n, d_steps, d_alphas, d_qpok, max_log, d_nl, h->stream);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(guess, d_g, n * HN * 8, cudaMemcpyDeviceToHost, h->stream));

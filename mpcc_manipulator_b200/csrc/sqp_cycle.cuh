@@ -7,13 +7,13 @@
 namespace mpcc {
 
 // b: instance; sm: this group's shared memory (group_smem_doubles<NL>(N) doubles); lane in [0, NL)
-template <int NL>
+template <int NL, bool SOC = false>
 __device__ __forceinline__ void sqp_group_cycle(const CycleArgs& a, double* wws, size_t ws_per, double* sm, int b, int lane) {
     const Params& P = a.params[a.params_per_instance ? b : 0];
     const TrackTable& T = a.tracks[a.track_id[b]];
     const size_t B = (size_t)a.B, NS = B * a.S;
     const int HN = a.S * HZ;
-    GroupSqp<NL> w{P, T, make_dyn(P, a.Ts), a.Ts, a.N, a.S, a.qp, Lanes<NL>{lane, nullptr}};
+    GroupSqp<NL, SOC> w{P, T, make_dyn(P, a.Ts), a.Ts, a.N, a.S, a.qp, Lanes<NL>{lane, nullptr}};
     w.carve(wws + (size_t)b * ws_per, sm);
     for (int e = lane; e < HN; e += NL) w.GUESS[e] = a.warm[(size_t)e * B + b];
     w.W.sync();
@@ -48,13 +48,13 @@ __device__ __forceinline__ void sqp_group_cycle(const CycleArgs& a, double* wws,
 }
 
 // SolverInterface::solveOCP probe for ONE instance: AoS guess / RobotData, optional iteration log
-template <int NL>
+template <int NL, bool SOC = false>
 __device__ __forceinline__ void solve_ocp_group(const CycleArgs& a, double* wws, size_t ws_per, double* sm, int b, int lane, double* guess, const double* rb,
                                                 const double* cur_u_all, double* steps, double* alphas, int32_t* qp_ok, int max_log, int32_t* n_logged) {
     const Params& P = a.params[a.params_per_instance ? b : 0];
     const TrackTable& T = a.tracks[a.track_id[b]];
     const int HN = a.S * HZ;
-    GroupSqp<NL> w{P, T, make_dyn(P, a.Ts), a.Ts, a.N, a.S, a.qp, Lanes<NL>{lane, nullptr}};
+    GroupSqp<NL, SOC> w{P, T, make_dyn(P, a.Ts), a.Ts, a.N, a.S, a.qp, Lanes<NL>{lane, nullptr}};
     w.carve(wws + (size_t)b * ws_per, sm);
     for (int e = lane; e < HN; e += NL) w.GUESS[e] = guess[(size_t)b * HN + e];
     w.W.sync();

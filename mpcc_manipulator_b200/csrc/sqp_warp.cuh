@@ -209,7 +209,10 @@ MPCC_HD void block9_pd_nan(const double* Qp, bool& pd, bool& nan) {
     }
 }
 
-template <int NL>
+// SOC: compile the reference's optional second-order correction (sqp.json "do_SOC", osqp_interface.cpp:506-533,658-681) into the loop.  It is a
+// template flag, not a run-time branch, so that the default kernels stay the exact code they were tuned as (the interior-point path is bound by
+// its instruction footprint); the SOC kernels live in their own translation unit (k_sqp_soc.cu) and are launched when a parameter set asks for it.
+template <int NL, bool SOC = false>
 struct GroupSqp {
     static constexpr int TS1 = 3 * NL, TS2 = NL;   // tile sizes of the streamed per-constraint passes (box + rate rows | polytopic rows)
     const Params& P;
@@ -1233,12 +1236,80 @@ struct GroupSqp {
         });
     }
 
+    // ---- SecondOrderCorrection (osqp_interface.cpp:658-681): the QP is solved again with the same P, q, A and the bounds shifted by
+    //      d = c(x (+) step) - A step, where (+) adds the NORMALISED step to the unnormalised iterate (:661).  Every row of c is affine in the
+    //      iterate once RobotData is frozen (quirk 6), so the shifted bounds follow in closed form from the point x~ = x (+) step, the step and the
+    //      rows already in LIN / CST; they overwrite the right-hand sides in LIN (dead after this QP: the next iteration linearises anew).
+    //      In:  XG iterate, XS step of the first QP (or the stale one).  Uses VAR for x~. ----
+    MPCC_HD void soc_right_hand_sides(const double* cur_u) const {
+        double* XT = VAR;
+        W.each([&](int lane) {
+            for (int e = lane; e < S * HZ; e += NL) {
+                const int kk = e / HZ, r = e - kk * HZ;
+                XT[e] = (r < NX || kk < N) ? XG[e] + XS[e] : 0.0;   // vectorToOptvar zeroes uk[N] (:835-845)
+            }
+        });
+        W.each([&](int lane) {
+            const double Lt = T.s[N_SPLINE - 1];
+            // state boxes incl. the mis-indexed input-bound rows (flat column o of the state block), dynamics defects
+            for (int o = lane; o < S * NX; o += NL) {
+                const int k = o / NX, m = o - k * NX;
+                const double x = XT[k * HZ + m], sv = XT[k * HZ + 7];
+                double lo = P.lx[m], hi = P.ux[m];
+                if (m == 7) { lo = fmax(sv - P.s_trust_region, 0.0); hi = fmin(sv + P.s_trust_region, Lt); }
+                double xlo = (lo - x) / P.Tx[m], xhi = (hi - x) / P.Tx[m];
+                if (o < NU * N) {
+                    const int i = o / NU, kk = o - i * NU;
+                    const double uv = XT[i * HZ + NX + kk];
+                    xlo = fmax(xlo, (P.lu[kk] - uv) / Tu(kk));
+                    xhi = fmin(xhi, (P.uu[kk] - uv) / Tu(kk));
+                }
+                const double sx = XS[k * HZ + m];
+                double* L = LIN + (size_t)k * WL_SIZE;
+                L[WL_XLO + m] = xlo + sx; L[WL_XHI + m] = xhi + sx;
+                if (k < N) {
+                    const double* xk = XT + k * HZ;
+                    double pred, as;   // prediction at x~ (osqp_interface.cpp:247) and the dynamics row applied to the step
+                    const double* sk = XS + k * HZ;
+                    if (m < 7) { pred = xk[m] + Ts * xk[NX + m]; as = XS[(k + 1) * HZ + m] - sk[m] - d_bq(m) * sk[NX + m]; }
+                    else if (m == 7) { pred = xk[7] + Ts * xk[8] + 0.5 * Ts * Ts * xk[NX + 7]; as = XS[(k + 1) * HZ + 7] - sk[7] - d_asv() * sk[8] - d_bs() * sk[NX + 7]; }
+                    else { pred = xk[8] + Ts * xk[NX + 7]; as = XS[(k + 1) * HZ + 8] - sk[8] - d_bv() * sk[NX + 7]; }
+                    const double c = (1.0 / P.Tx[m]) * (XT[(k + 1) * HZ + m] - pred);
+                    L[WL_b + m] = -c + as;
+                }
+            }
+            // joint-acceleration rows (osqp_interface.cpp:279-297)
+            for (int o = lane; o < N * DOF; o += NL) {
+                const int k = o / DOF, j = o - k * DOF;
+                const double uj = XT[k * HZ + NX + j];
+                double lo, hi, c;
+                if (k == 0) { c = 1. / Ts * uj; lo = P.ldd[j] + 1. / Ts * cur_u[j]; hi = P.udd[j] + 1. / Ts * cur_u[j]; }
+                else { c = 1. / Ts * (uj - XT[(k - 1) * HZ + NX + j]); lo = P.ldd[j]; hi = P.udd[j]; }
+                const double as = XS[k * HZ + NX + j] - (k > 0 ? XS[(k - 1) * HZ + NX + j] : 0.0);
+                double* L = LIN + (size_t)k * WL_SIZE;
+                L[WL_DLO + j] = (lo - c) * Ts / P.Tu[j] + as;
+                L[WL_DHI + j] = (hi - c) * Ts / P.Tu[j] + as;
+            }
+            // polytopic rows: c(x~) = -g' (u + nu) + RBF(frozen), A step = pd g' Tx xi - g' Tu nu with the rows [pd g Tx | -g Tu] of CST
+            for (int o = lane; o < N * NPOLY; o += NL) {
+                const int k = o / NPOLY, j = o - k * NPOLY;
+                const double* row = CST + ((size_t)k * NPOLY + j) * 14;
+                const double* sk = XS + k * HZ;
+                double add = 0;
+#pragma unroll
+                for (int m = 0; m < DOF; m++) add += row[m] * sk[m] + row[7 + m] * sk[NX + m] * (1.0 - 1.0 / Tu(m));
+                LIN[(size_t)k * WL_SIZE + WL_PRHS + j] += add;
+            }
+        });
+    }
+
     // ---- the SQP loop (solveOCP) ----
     MPCC_HD SqpResult run(const double* cur_u, const double* rb, size_t rb_stride, size_t rb_stage, SqpLogRef* log) {
         SqpResult res;
         res.status = SOLVED; res.iters = 0; res.qp_fail = 0; res.qp_iters = 0; res.accept_mask = 0;
         const int max_iter = (int)P.max_iter, ls_max = (int)P.line_search_max_iter;
         const int HN = S * HZ;
+        const bool soc_on = SOC && P.do_SOC != 0.0;
         init_scratch();
         W.each([&](int lane) { for (int e = lane; e < HN; e += NL) { XS[e] = 0.0; XG[e] = GUESS[e]; } });
         int n_filt = 0, it = 0;
@@ -1253,7 +1324,7 @@ struct GroupSqp {
             if (!have_lin) {
                 double obj, gap;
                 gather_point(0.0);
-                qp_known_infeasible = (it > 0) && qp_box_infeasible(VAR);  // (it == 0 also writes the cycle constants)
+                qp_known_infeasible = (it > 0) && !soc_on && qp_box_infeasible(VAR);  // (it == 0 also writes the cycle constants; the correction needs the assembled QP)
                 eval_horizon<true>(cur_u, rb, rb_stride, rb_stage, 0.0, it == 0, obj, gap, &lin_notpd, &lin_nan, !qp_known_infeasible, true);
             }
             have_lin = false; lin_infeasible = false;
@@ -1290,6 +1361,24 @@ struct GroupSqp {
                 res.qp_fail++;  // step keeps its previous value (osqp_interface.cpp:479-505)
                 if (!qp_known_infeasible) W.each([&](int lane) { for (int e = lane; e < HN; e += NL) XS[e] = SSTEP[e]; });
             }
+            if (SOC && soc_on) {
+                // second-order correction: second QP on the shifted bounds; its solution replaces the step, a failure only counts (:506-533, :646-647)
+                soc_right_hand_sides(cur_u);
+                W.each([&](int lane) { for (int e = lane; e < HN; e += NL) { GUESS[e] = XG[e]; SSTEP[e] = XS[e]; } });
+                const QpStats q2 = solve();
+                W.each([&](int lane) { for (int e = lane; e < HN; e += NL) XG[e] = GUESS[e]; });
+                res.qp_iters += q2.iters;
+                if (q2.ok) {
+                    inf_step = W.rmax([&](int lane) {
+                        double m = 0;
+                        for (int e = lane; e < HN; e += NL) { const int k = e / HZ, r = e - k * HZ; const double v = (r < NX || k < N) ? VAR[e] : 0.0; XS[e] = v; m = fmax(m, fabs(v)); }
+                        return m;
+                    });
+                } else {
+                    res.qp_fail++;
+                    W.each([&](int lane) { for (int e = lane; e < HN; e += NL) XS[e] = SSTEP[e]; });
+                }
+            }
             const double t_c = now_ns();
             tm_set_qp += t_b - t_a; tm_solve_qp += t_c - t_b;
             // ---- filterLineSearch (osqp_interface.cpp:759-808) ----
@@ -1304,7 +1393,7 @@ struct GroupSqp {
                     bool sp_notpd = false, sp_nan = false, sp_infeasible = false;
                     if (spec) {
                         gather_point(alpha);
-                        sp_infeasible = qp_box_infeasible(VAR);
+                        sp_infeasible = !soc_on && qp_box_infeasible(VAR);
                         eval_horizon<true>(cur_u, rb, rb_stride, rb_stage, alpha, false, o2, g2, &sp_notpd, &sp_nan, !sp_infeasible, true);
                     } else eval_horizon<false>(cur_u, rb, rb_stride, rb_stage, alpha, false, o2, g2, nullptr, nullptr);
                     if (W.any([&](int lane) {

@@ -1061,6 +1061,7 @@ struct Solver {
     std::vector<int> natural_accept;
     std::vector<double> accept_margin;
     std::vector<int> forced_accept;
+    int n_soc_fail = 0;  // failed second-order-correction QPs of the last solveOCP
 
     void init(int N_) {
         N = N_;
@@ -1299,6 +1300,7 @@ struct Solver {
         filter.clear();
         min_filter_margin = 1e300;
         natural_accept.clear(); accept_margin.clear();
+        n_soc_fail = 0;
         *time = ComputeTime();
         std::vector<OptVariables> zero_guess(N + 1);
         for (int i = 0; i <= N; i++) { zero_guess[i].xk = initial_guess[0].xk; for (double& v : zero_guess[i].uk.v) v = 0; }
@@ -1321,6 +1323,30 @@ struct Solver {
             QPResult r = qp.solve(Hess, grad_obj, jac, lq, uq, z);
             if (r.ok) step = z;
             else *status = QP_MaxIterReached;  // no break: step keeps its previous value (:479-505)
+            int qp_iters_total = r.iters;
+            if (sqp.do_SOC) {
+                // SecondOrderCorrection (:658-681): the same P, q and A, bounds shifted by d = c(x (+) step) - A step, where (+) adds the
+                // NORMALISED step to the unnormalised iterate (:661, no deNormalizeStep); solveQP overwrites step only on success (:646-647),
+                // a failure sets the status and the loop goes on (:506-533)
+                Vec v = OptvarToVector(initial_guess);
+                for (int k = 0; k < N_var; k++) v[k] += step[k];
+                std::vector<OptVariables> ug = vectorToOptvar(v);
+                Vec cs, ls, us;
+                setConstraints(ug, nullptr, &cs, &ls, &us);
+                Vec l2(N_constr), u2(N_constr), z2;
+                for (int i = 0; i < N_constr; i++) {
+                    const double* ai = jac.row(i);
+                    double as = 0;
+                    for (int k = 0; k < N_var; k++) as += ai[k] * step[k];
+                    const double d = cs[i] - as;
+                    l2[i] = ls[i] - d; u2[i] = us[i] - d;
+                }
+                QPResult r2 = qp.solve(Hess, grad_obj, jac, l2, u2, z2);
+                if (r2.ok) step = z2;
+                else *status = QP_MaxIterReached;
+                qp_iters_total += r2.iters;
+                n_soc_fail += r2.ok ? 0 : 1;
+            }
             auto a2 = std::chrono::high_resolution_clock::now();
             double alpha = filterLineSearch(initial_guess, step);
             auto a3 = std::chrono::high_resolution_clock::now();
@@ -1330,7 +1356,7 @@ struct Solver {
             double inf = 0;
             for (double v : step) inf = std::max(inf, std::fabs(v));
             double primal_step_norm = alpha * inf;
-            if (log) { log->steps.push_back(step); log->alphas.push_back(alpha); log->qp_ok.push_back(r.ok); log->qp_iters.push_back(r.iters); }
+            if (log) { log->steps.push_back(step); log->alphas.push_back(alpha); log->qp_ok.push_back(r.ok); log->qp_iters.push_back(qp_iters_total); }
             time->set_qp += std::chrono::duration<double>(a1 - a0).count();
             time->solve_qp += std::chrono::duration<double>(a2 - a1).count();
             time->get_alpha += std::chrono::duration<double>(a3 - a2).count();

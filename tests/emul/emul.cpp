@@ -87,7 +87,7 @@ int emu_epilogue(int N, int status, int iters, const double* x0, double* guess, 
 // The lanes-per-instance formulation (sqp_warp.cuh) executed phase by phase on the host; reverse = lane order.
 // NL = 32: the warp kernel (throughput); NL = 128: the CTA kernel (latency mode).
 }  // extern "C"
-template <int NL>
+template <int NL, bool SOC = false>
 static int group_solve_ocp(const double* params, const double* table, double Ts, int N, double* guess, const double* rb, const double* cur_u,
                            int qp_max_iter, double qp_eps, int reverse, int* status, int* iters, int* qp_iters, double* steps, double* alphas, int* qp_ok,
                            int max_log, int* n_logged, unsigned* accept_mask) {
@@ -95,7 +95,7 @@ static int group_solve_ocp(const double* params, const double* table, double Ts,
     const int S = N + 1, HN = S * HZ;
     std::vector<double> gws(warp_ws_doubles(N)), sm(group_smem_doubles<NL>(N), -3.0);
     Lanes<NL> wp; wp.reverse = reverse != 0;
-    GroupSqp<NL> w{P, *(const TrackTable*)table, make_dyn(P, Ts), Ts, N, S, QpOptions{qp_max_iter, qp_eps}, wp};
+    GroupSqp<NL, SOC> w{P, *(const TrackTable*)table, make_dyn(P, Ts), Ts, N, S, QpOptions{qp_max_iter, qp_eps}, wp};
     w.carve(gws.data(), sm.data());
     for (int e = 0; e < HN; e++) w.GUESS[e] = guess[e];
     SqpLogRef lg{steps, alphas, qp_ok, max_log, 0};
@@ -114,6 +114,17 @@ int emu_cta_solve_ocp(const double* params, const double* table, double Ts, int 
                       int qp_max_iter, double qp_eps, int reverse, int* status, int* iters, int* qp_iters, double* steps, double* alphas, int* qp_ok,
                       int max_log, int* n_logged, unsigned* accept_mask) {
     return group_solve_ocp<128>(params, table, Ts, N, guess, rb, cur_u, qp_max_iter, qp_eps, reverse, status, iters, qp_iters, steps, alphas, qp_ok, max_log, n_logged, accept_mask);
+}
+// the same with the second-order correction compiled in (sqp.json "do_SOC" in params decides at run time)
+int emu_warp_solve_ocp_soc(const double* params, const double* table, double Ts, int N, double* guess, const double* rb, const double* cur_u,
+                           int qp_max_iter, double qp_eps, int reverse, int* status, int* iters, int* qp_iters, double* steps, double* alphas, int* qp_ok,
+                           int max_log, int* n_logged, unsigned* accept_mask) {
+    return group_solve_ocp<32, true>(params, table, Ts, N, guess, rb, cur_u, qp_max_iter, qp_eps, reverse, status, iters, qp_iters, steps, alphas, qp_ok, max_log, n_logged, accept_mask);
+}
+int emu_cta_solve_ocp_soc(const double* params, const double* table, double Ts, int N, double* guess, const double* rb, const double* cur_u,
+                          int qp_max_iter, double qp_eps, int reverse, int* status, int* iters, int* qp_iters, double* steps, double* alphas, int* qp_ok,
+                          int max_log, int* n_logged, unsigned* accept_mask) {
+    return group_solve_ocp<128, true>(params, table, Ts, N, guess, rb, cur_u, qp_max_iter, qp_eps, reverse, status, iters, qp_iters, steps, alphas, qp_ok, max_log, n_logged, accept_mask);
 }
 // one QP of the warp formulation at the linearisation of `guess`
 int emu_warp_solve_qp(const double* params, const double* table, double Ts, int N, const double* guess, const double* rb, const double* cur_u,

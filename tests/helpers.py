@@ -84,12 +84,14 @@ class Emul:
         state[0], state[1], state[2] = g, v, f
         return dict(x0=x0n, u0=g[0, 9:].copy(), horizon=g, status=r["status"], iters=r["iters"], ok=ok, accept=[int(a == 1.0) for a in r["alphas"]], qp_ok=r["qp_ok"])
 
-    def warp_solve_ocp(self, params, table, Ts, N, guess, rb, cur_u, qp_max_iter=60, qp_eps=1e-9, max_log=100, reverse=False, lanes=32):
-        """lanes = 32: the warp kernel's code; lanes = 128: the CTA (latency-mode) kernel's code"""
+    def warp_solve_ocp(self, params, table, Ts, N, guess, rb, cur_u, qp_max_iter=60, qp_eps=1e-9, max_log=100, reverse=False, lanes=32, soc=False):
+        """lanes = 32: the warp kernel's code; lanes = 128: the CTA (latency-mode) kernel's code; soc: the instantiation with the second-order
+        correction compiled in (k_sqp_soc.cu's kernels; sqp.do_SOC in `params` switches it on)"""
         g = f64(guess).copy()
         st, it, qi, nl, am = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_uint()
         steps = np.zeros((max_log, N + 1, HZ)); al = np.zeros(max_log); ok_ = np.zeros(max_log, np.int32)
-        ok = (self.lib.emu_warp_solve_ocp if lanes == 32 else self.lib.emu_cta_solve_ocp)(_p(params), _p(table), C.c_double(Ts), N, _p(g), _p(f64(rb)), _p(f64(cur_u)), qp_max_iter, C.c_double(qp_eps), int(reverse),
+        fn = {(32, False): self.lib.emu_warp_solve_ocp, (128, False): self.lib.emu_cta_solve_ocp, (32, True): self.lib.emu_warp_solve_ocp_soc, (128, True): self.lib.emu_cta_solve_ocp_soc}[(lanes, bool(soc))]
+        ok = fn(_p(params), _p(table), C.c_double(Ts), N, _p(g), _p(f64(rb)), _p(f64(cur_u)), qp_max_iter, C.c_double(qp_eps), int(reverse),
                                          C.byref(st), C.byref(it), C.byref(qi), _p(steps), _p(al), _p(ok_), max_log, C.byref(nl), C.byref(am))
         k = nl.value
         return dict(ok=bool(ok), horizon=g, status=st.value, iters=it.value, qp_iters=qi.value, steps=steps[:k], alphas=al[:k], qp_ok=ok_[:k], accept_mask=am.value)

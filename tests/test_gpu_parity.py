@@ -611,9 +611,9 @@ def test_error_behaviour(M, ee_home):
     bad = M.load_default_params(); bad[84 + 2] = 1000  # sqp.max_iter beyond the device filter capacity
     with pytest.raises(RuntimeError, match="max_iter"):
         mpc.set_params(bad)
-    soc = M.load_default_params(overrides={"sqp.do_SOC": 1.0})
-    with pytest.raises(RuntimeError, match="do_SOC"):
-        mpc.set_params(soc)
+    bfgs = M.load_default_params(overrides={"sqp.use_BFGS": 1.0})
+    with pytest.raises(RuntimeError, match="use_BFGS"):
+        mpc.set_params(bfgs)
     mpc.close()
 
 
@@ -777,3 +777,59 @@ def test_pinned_horizon_is_written_by_the_kernel(M, O, ee_home, rng):
             u = ra["u0"]; x = a.sim_time_step(ra["x0"], u)
         for m in (a, b, c):
             m.close()
+
+
+def test_second_order_correction_closed_loop(M, O, nn, ee_home, track_wp, rng):
+    """sqp.do_SOC (osqp_interface.cpp:506-533,658-681; reference default false): the kernels of k_sqp_soc.cu against the oracle, closed loop,
+    replayed along the device's branch as every closed-loop test here.  Warp-per-instance kernel (forced) and CTA-per-instance kernel; the
+    correction must change the applied controls (compared with the default loop on the same first cycle)."""
+    N = 10
+    par = M.load_default_params(overrides={"sqp.do_SOC": 1.0})
+    po = O.load_params(overrides={"sqp": {"do_SOC": True}})
+    for flags, B, cycles in ((2, 6, 6), (4, 3, 4)):
+        mpc = M.BatchMPC(B, N, flags=flags)
+        mpc.setup_default(init_position=ee_home, params=par)
+        plain = make_mpc(M, B, N, ee_home, flags=flags)
+        oracles = []
+        for b in range(B):
+            o = O.OracleMPC(N=N, nn=nn, params=po); o.set_track(*track_wp); oracles.append(o)
+        x = np.tile(np.r_[O.Q_HOME, 0., 0.], (B, 1)); x[:, :7] += rng.uniform(-0.05, 0.05, (B, 7))
+        u = np.zeros((B, 8))
+        r_plain = plain.run_cycle(x, u)
+        r_soc = M.BatchMPC(B, N, flags=flags)
+        r_soc.setup_default(init_position=ee_home, params=par)
+        first = r_soc.run_cycle(x, u)
+        assert (np.abs(first["u0"] - r_plain["u0"]) / TU).max() > 1e-3      # not a no-op
+        st = r_soc.stats()
+        assert st["qp_iters"] > plain.stats()["qp_iters"]                   # two QPs per SQP iteration
+        r_soc.close(); plain.close()
+        n_cmp, n_tie, worst = _closed_loop_follow(mpc, oracles, x, u, cycles, 0.01, O, slack_outliers=1)
+        print(f"SOC flags={flags}: {n_cmp} comparisons, {n_tie} certified ties, worst |du0| = {worst:.2e}")
+        assert n_cmp == B * cycles
+        mpc.close()
+
+
+def test_second_order_correction_per_instance(M, O, nn, ee_home, track_wp, rng):
+    """A batch whose parameter sets differ in do_SOC: the instances without it must get exactly what the default kernels give them, the ones with
+    it what an all-SOC batch gives them (the flag is read per instance inside the SOC kernels)."""
+    B, N = 8, 10
+    p0 = M.load_default_params(); p1 = M.load_default_params(overrides={"sqp.do_SOC": 1.0})
+    mixed = np.stack([p1 if b % 2 else p0 for b in range(B)])
+    x = np.tile(np.r_[O.Q_HOME, 0., 0.], (B, 1)); x[:, :7] += rng.uniform(-0.05, 0.05, (B, 7))
+    u = np.zeros((B, 8))
+    res = {}
+    for name, par in (("mixed", mixed), ("plain", p0), ("soc", p1)):
+        mpc = M.BatchMPC(B, N, flags=2)
+        mpc.setup_default(init_position=ee_home, params=par)
+        r1 = mpc.run_cycle(x, u)
+        r2 = mpc.run_cycle(mpc.sim_time_step(r1["x0"], r1["u0"]), r1["u0"])
+        res[name] = (r1, r2)
+        mpc.close()
+    for c in range(2):
+        m, pl, so = res["mixed"][c], res["plain"][c], res["soc"][c]
+        # same kernel, same instance data: bit for bit
+        assert np.array_equal(m["u0"][1::2], so["u0"][1::2]) and np.array_equal(m["iters"][1::2], so["iters"][1::2])
+        # the plain batch ran k_sqp_warp, another instantiation of the same source: same iteration counts, controls to the QP tolerance
+        assert np.array_equal(m["iters"][0::2], pl["iters"][0::2]) or c == 1
+        assert (np.abs(m["u0"][0::2] - pl["u0"][0::2]) / TU).max() < QP_TOL
+    assert (np.abs(res["mixed"][0]["u0"][1::2] - res["plain"][0]["u0"][1::2]) / TU).max() > 1e-3

@@ -348,3 +348,46 @@ def test_primal_infeasibility_certificate(O, nn, track_wp):
     # the whole SQP cycle on it: the QP fails, the step stays zero, the reference's loop then reports SOLVED (quirk 10)
     r2 = emu.warp_solve_ocp(pf, table, p["Ts"], N, g["warm"], g["rb"], g["u"])
     assert r2["status"] == 0 and r2["iters"] == 1 and r2["qp_ok"][0] == 0 and r2["qp_iters"] < 30
+
+
+# ---- second-order correction (sqp.json "do_SOC", osqp_interface.cpp:506-533,658-681) ----------------------------
+@pytest.mark.parametrize("N,lanes", [(10, 32), (20, 32), (10, 128)])
+def test_second_order_correction_vs_oracle(O, nn, emu, track_wp, rng, N, lanes):
+    """solveOCP with do_SOC: after every QP a second QP with the same P, q, A and bounds shifted by d = c(x (+) step) - A step replaces the step.
+    The oracle restates that with the reference's dense matrices (setConstraints at the shifted point, jac * step); the product derives the
+    shifted bounds per stage in closed form (sqp_warp.cuh::soc_right_hand_sides).  Same statuses, iteration counts and line-search decisions
+    (replayed along the product's branch, ties certified), steps within the QP tolerance -- and the correction must actually change the steps
+    (compared with the same solve without it), otherwise the test would pass on a no-op."""
+    p = O.load_params(overrides={"sqp": {"do_SOC": True}})
+    assert p["sqp"][4] == 1.0
+    pf = flat_params(p)
+    p0 = O.load_params(); pf0 = flat_params(p0)
+    table = emu.fit_track(*track_wp)
+    Ts = p["Ts"]
+    o = O.OracleMPC(N=N, nn=nn, params=p)
+    o.set_track(*track_wp)
+    changed = 0.0
+    for trial in range(4):
+        q0 = O.Q_HOME + rng.uniform(-0.05, 0.05, 7)
+        hor = np.tile(np.r_[q0, 0.0, 0.0, np.zeros(8)], (N + 1, 1))
+        if trial >= 2:   # a warm-start-like guess with non-zero inputs and a moving path parameter
+            hor[:, 7] = np.linspace(0.0, 0.02, N + 1); hor[:, 8] = 0.1; hor[:N, 9:16] = rng.uniform(-0.05, 0.05, (N, 7)); hor[:N, 16] = 0.2
+        rb = np.stack([nn.robot_data(hor[k, :7]) for k in range(N + 1)])
+        cur_u = np.zeros(8) if trial < 2 else np.r_[hor[0, 9:16], 0.0]
+        a = emu.warp_solve_ocp(pf, table, Ts, N, hor, rb, cur_u, reverse=bool(trial % 2), lanes=lanes, soc=True)
+        o.set_forced_decisions([int(x == 1.0) for x in a["alphas"]])
+        b = o.solve_ocp(hor, rb, cur_u)
+        nat, mg = o.decision_log()
+        o.set_forced_decisions([])
+        assert a["status"] == b["status"] == 0 and a["iters"] == b["iters"], (a["status"], b["status"], a["iters"], b["iters"])
+        assert np.allclose(a["alphas"], b["alphas"])
+        for i in range(len(b["steps"])):
+            assert np.abs(step_to_flat(a["steps"][i], N) - b["steps"][i]).max() < 1e-4, (trial, i, np.abs(step_to_flat(a["steps"][i], N) - b["steps"][i]).max())
+            assert nat[i] == int(a["alphas"][i] == 1.0) or mg[i] < 1e-6
+        assert np.abs(a["horizon"] - b["horizon"]).max() < 1e-4
+        # the instantiation with the correction compiled in but switched off is the plain loop
+        c = emu.warp_solve_ocp(pf0, table, Ts, N, hor, rb, cur_u, lanes=lanes, soc=True)
+        d = emu.warp_solve_ocp(pf0, table, Ts, N, hor, rb, cur_u, lanes=lanes)
+        assert c["iters"] == d["iters"] and np.array_equal(c["horizon"], d["horizon"])
+        changed = max(changed, np.abs(a["steps"][0] - d["steps"][0]).max())
+    assert changed > 1e-3, changed
