@@ -138,7 +138,7 @@ struct MlpOzArgs {
     MlpArgs m;               // m.wpack: the fp64 weights packed by pack_mlp_oz_weights (OZ_DPACK_D doubles: chunk stream | env output layer | self W1 | self W0 transposed)
     const uint8_t* wq;       // OZ_CHUNKS_PER_TILE x OZ_CHUNK bytes: digit planes of env layers 1..3 in consumption order
     const double* rowscale;  // [3][256]: 2^(E_r - 7 S - 7)
-    int dbg_flags;           // experiments (timing only, results wrong): bit 0 = no weight stream (MMAs on whatever the ring holds), bit 1 = no per-CTA rotation of the stream
+    int dbg_flags;           // experiments (timing only, results wrong): bit 0 = no weight stream (MMAs on whatever the ring holds), bit 1 = no proxy fence per chunk, bit 2 = every pass issued twice (cold / warm instruction fetch)
     long long* dbg;          // optional: cycles of CTA 0 per phase [first layers + staging | split | MMA pass (issue .. accumulators ready) | epilogue | env output | self net | tiles]
 };
 
@@ -436,7 +436,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp_oz(MlpOzArgs oa) {
     uint64_t* bars = reinterpret_cast<uint64_t*>(misc + OZ_MISC_BARS);       // full[NSLOT] | empty[NSLOT] | accumulator complete [S] | accumulators read
     uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(misc + OZ_MISC_TMEM);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // the shuffle makes the warp index provably warp-uniform for the compiler
     const int fr = lane >> 2, fq = lane & 3;
     const int bslot = xslot(fq, fr);
     const uint32_t bar_full = oz_smem_u32(bars), bar_empty = oz_smem_u32(bars + OZ_NSLOT), bar_group = oz_smem_u32(bars + 2 * OZ_NSLOT),
@@ -509,7 +509,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp_oz(MlpOzArgs oa) {
     const bool dbg_on = oa.dbg != nullptr && blockIdx.x == 0 && tid == 0;
 #define OZ_MARK(w, e) if (oa.dbg != nullptr && blockIdx.x == 0 && tile_iter == 1 && lane == 0) oa.dbg[8 + (w) * 16 + (e)] = clock64();
 #define OZ_DBG(i) if (dbg_on) { const long long t_ = clock64(); dbg_t[i] += t_ - dbg_c; dbg_c = t_; }
-    if (dbg_on) dbg_c = clock64();
+    if (dbg_on) { dbg_c = clock64(); oa.dbg[40] = 0; oa.dbg[41] = 0; }
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, tile_iter++) {
         const int s0 = tile * MLP_TILE_S;
         dbg_t[6]++;
@@ -732,7 +732,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp_oz(MlpOzArgs oa) {
                         if (warp == 0) {
                             // ---- MMA issuer ----
                             if (layer == 0) { OZ_MARK(0, 3 * mb) }
-                            dbg_wait += oz_issue_pass(tmem, ring_addr, planes_addr, bar_full, bar_empty, bar_group, bar_tfree, pass_first, 0u, no_stream, (oa.dbg_flags & 2) != 0);
+                            dbg_wait += oz_issue_pass(tmem, ring_addr, planes_addr, bar_full, bar_empty, bar_group, bar_tfree, pass_first, (uint32_t)(oa.dbg_flags >> 3) & 1u, no_stream, (oa.dbg_flags & 2) != 0);
                             if (layer == 0) { OZ_MARK(0, 3 * mb + 1) }
                         } else if (producer && !no_stream) {
                             // ---- weight-digit stream: the rest of this pass's chunks and the first NSLOT of the next pass's (they land during the epilogue / split) ----

@@ -281,7 +281,7 @@ static int launch_robot_data(mpcc_cuda_handle* h, const double* d_obs, int S_for
     int grid = m.n_tiles < h->num_sms ? m.n_tiles : h->num_sms;
     if (h->mlp_oz) {
         MlpOzArgs oa;
-        oa.m = m; oa.m.wpack = h->d_oz_dpack; oa.wq = h->d_oz_wq; oa.rowscale = h->d_oz_rowscale; oa.dbg = h->d_oz_dbg; oa.dbg_flags = (h->cfg.reserved >> 5) & 3;
+        oa.m = m; oa.m.wpack = h->d_oz_dpack; oa.wq = h->d_oz_wq; oa.rowscale = h->d_oz_rowscale; oa.dbg = h->d_oz_dbg; oa.dbg_flags = ((h->cfg.reserved >> 5) & 3) | (((h->cfg.reserved >> 9) & 1) << 2);
         if (h->cfg.reserved & 128) grid = 16;  // experiment: few CTAs (is the weight stream limited per SM or by the whole chip's L2 traffic?)
         k_mlp_oz<<<grid, MLP_THREADS, OZ_SMEM_BYTES, h->stream>>>(oa);
     } else {
@@ -815,6 +815,7 @@ int mpcc_cuda_eval_robot_data(mpcc_cuda_handle* h, const double* q, const double
                 t[0] / t[6], t[1] / t[6], t[2] / t[6], t[3] / t[6], t[4] / t[6], t[5] / t[6], t[7] / t[6]);
         fprintf(stderr, "  trace (tile 1, layer 0): pass 0: issue %lld, until complete %lld | epilogue + barrier %lld | pass 1: issue %lld, until complete %lld ; chunk waits of the issuer per tile %lld\n",
                 t[9] - t[8], t[10] - t[8], t[11] - t[10], t[12] - t[11], t[13] - t[11], t[7] / t[6]);
+        if (h->cfg.reserved & 512) fprintf(stderr, "  passes issued twice: first (cold) %lld, second (warm) %lld cycles per pass\n", t[40] / (6 * t[6]), t[41] / (6 * t[6]));
         fprintf(stderr, "  first layers (tile 1): env: staging %lld | 4 chunks of DFMA %lld | epilogue + column maxima %lld | barrier %lld ;  self: staging %lld | DFMA %lld | epilogue %lld | barrier %lld\n",
                 t[25] - t[24], t[26] - t[25], t[27] - t[26], t[28] - t[27], t[30] - t[29], t[31] - t[30], t[32] - t[31], t[33] - t[32]);
     }
