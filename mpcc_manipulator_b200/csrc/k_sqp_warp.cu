@@ -48,14 +48,16 @@ constexpr int SQPW_EXCL_CTAS = 8;            // CTAs of the exclusive launch (on
 // excl: 1 = exclusive launch (the first slots only), 0 = main launch (skips them), -1 = single launch (everything)
 extern __shared__ __align__(16) double sqpw_smem[];
 __device__ __forceinline__ void sqp_warp_cycle(const CycleArgs& a, double* wws, size_t ws_per, size_t sm_per, int excl) {
-    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index and instance number go through a shuffle: provably warp-uniform for the compiler (uniform registers for everything derived
+    // from them -- the workspace pointers --, no convergence barriers around warp-uniform branches)
+    const int wid = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
     const int slot = blockIdx.x * SQPW_WARPS + wid;
     if (slot >= a.B) return;  // whole warps leave together
     if (excl >= 0) {
         const int n_excl = min(a.order[a.B], SQPW_EXCL_CTAS * SQPW_WARPS);
         if ((excl == 1) != (slot < n_excl)) return;
     }
-    sqp_group_cycle<32>(a, wws, ws_per, sqpw_smem + (size_t)wid * sm_per, a.order[slot], lane);
+    sqp_group_cycle<32>(a, wws, ws_per, sqpw_smem + (size_t)wid * sm_per, __shfl_sync(0xffffffffu, a.order[slot], 0), lane);
 }
 // Two builds of the same code.  k_sqp_warp: 5 CTAs per SM (168 registers, 2.8 KB of spills) -- a steady-state batch (every
 // instance one QP) wants resident warps: 5.0 ms against 5.45.  k_sqp_warp_r255: the full register file (255 registers, 0.8 KB
