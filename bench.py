@@ -34,6 +34,9 @@ METRIC = "batched MPCC SQP solves/sec (4096xN=20)"
 UNIT = "solves/s"
 # algorithmic FLOPs: minimal MAC counts of both networks with 7 forward-mode tangent columns
 MLP_FLOP_PER_STAGE = 2.0 * 1746688
+# what the default kernel executes since the self net runs in reverse mode (value forwards + one adjoint sweep: 43 605 instead of 142 336 MAC per sample);
+# the roofline keeps SURVEY's figure (the contract's per-unit work), this one is reported next to it
+MLP_EXECUTED_FLOP_PER_STAGE = 2.0 * (1604352 + 43605)
 KIN_FLOP_PER_STAGE = 2.0 * 9000
 # SQP kernel, per interior-point iteration and stage: Riccati factorisation 4.2 k MAC (polytopic rank-11
 # update 1155, L^-1 Mnx 576, cost-to-go update 2048, blocks / Cholesky ~400), two sweeps 2 x 384, two gradients ~500,
@@ -531,10 +534,13 @@ def run_ours(args):
             # default kernel: the three 256 x 256 env layers (88 % of the MACs) as exact int8 digit products on tcgen05 (kind::i8, TMEM accumulators);
             # the same algorithmic fp64 FLOPs are reported against the FP64 pipe (the roof of the fp64 formulation: above 1.0 means the contraction
             # has left that pipe), and the int8 work actually issued against the tensor peak
-            roof_mlp = roof_of("k_mlp_oz", mlp_flop, km[2], "both networks + 7 forward-mode tangents; the three 256 x 256 env layers run as exact int8 digit products (7 digits of 7 bits per operand, "
+            roof_mlp = roof_of("k_mlp_oz", mlp_flop, km[2], "both networks with their joint Jacobians (env net: 7 forward-mode tangents; self net: reverse mode); the three 256 x 256 env layers run as exact int8 digit products (7 digits of 7 bits per operand, "
                                "28 products per layer) on tcgen05.mma kind::i8 with TMEM accumulators and recombine in int64 -- fp64-equivalent results (1e-13 of the fp64 kernel). `achieved` / `frac` "
                                "are the ALGORITHMIC fp64 FLOPs against the measured FP64 pipe peak: the roof of the fp64 formulation, exceeded because the contraction no longer runs there; "
                                "`tensor_int8` is the int8 work actually issued against the tensor-core peak", "tensor")
+            roof_mlp["executed_flops_per_launch"] = B * S * MLP_EXECUTED_FLOP_PER_STAGE
+            roof_mlp["executed_note"] = ("`algorithmic_flops_per_launch` is SURVEY 8d's minimal forward-mode count (1 746 688 MAC per sample); the kernel executes 1 647 957: "
+                                         "its self net runs in reverse mode (one adjoint sweep instead of seven tangent columns)")
             tiles = -(-(B * S) // 8)
             int8_ops = 2.0 * OZ_INT8_MAC_PER_TILE * tiles
             bf16_burst = bf16_sust = None

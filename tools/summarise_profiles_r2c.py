@@ -1,0 +1,144 @@
+#!/usr/bin/env python
+"""Round 2, build with the int8-split MLP kernel: regenerate the tracked summaries under profiles/ from the scratch captures in gpurun_out/
+(tools/gpu_profile_round2c.sh).  Writes profiles/r2c_launches.md, profiles/r2c_ncu_full_steady.md, profiles/r2c_sass_census.md and updates
+profiles/dram_traffic.json (entries k_mlp_oz, k_sqp_warp; the older entries stay: k_mlp = the fp64 kernel, k_sqp_cta)."""
+import collections, csv, io, json, re, subprocess
+from pathlib import Path
+ROOT = Path(__file__).resolve().parent.parent
+OUT, PROF = ROOT / "gpurun_out", ROOT / "profiles"
+SHA = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True, cwd=ROOT).stdout.strip()
+CMD = "python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-secondary   (40 settle cycles from the cold start first: steady state, one SQP iteration per instance)"
+
+
+def num(s):
+    try:
+        return float(s.replace(",", ""))
+    except Exception:
+        return None
+
+
+def launches():
+    text = (OUT / "r2c_launches.csv").read_text()
+    rows = list(csv.DictReader(io.StringIO(text[text.index('"ID"'):])))
+    seq = []
+    for r in rows:
+        if r.get("Metric Name") != "gpu__time_duration.sum":
+            continue
+        v = num(r["Metric Value"]); unit = r["Metric Unit"]
+        ms = v / 1e6 if unit.startswith("ns") else v / 1e3 if unit.startswith("us") else v
+        seq.append((r["Kernel Name"].split("(")[0].replace("mpcc::", ""), ms))
+    idx = [i for i, (n, _) in enumerate(seq) if n == "k_prologue"]
+    ncyc = len(idx) - 1
+    steady = seq[idx[0]:idx[ncyc]]
+    cyc = collections.OrderedDict()
+    for n, ms in steady:
+        cyc[n] = cyc.get(n, 0.0) + ms / ncyc
+    own = {k: v for k, v in cyc.items() if k.startswith("k_")}
+    tot = sum(own.values())
+    live = json.loads([l for l in (OUT / "r2c_plain.log").read_text().splitlines() if l.startswith("{")][-1])
+    lk, ls = live["kernels_ms"], live["roofline"]["kernel_share_of_step"]
+    alias = {"k_mlp_oz": "k_mlp"}
+    lines = ["# Round 2 (int8-split MLP kernel) - ncu launch list, steady state", "",
+             f"Command: `ncu --metrics gpu__time_duration.sum --clock-control none -s 240 -c 60 --csv {CMD}`, run after the same command exited 0 without ncu (build {SHA}).",
+             f"{len(seq)} launches captured (launches 241..300 of the process), {ncyc} whole control cycles; the table is their mean.",
+             "Per-launch times under ncu are serialised and cold-cache: compare SHARES with the live CUDA-event numbers (right column, same command without ncu).", "",
+             "| kernel | ms per cycle (ncu) | share of the cycle's own kernels | live CUDA events, ms (share of step) |", "|---|---|---|---|"]
+    for k, v in cyc.items():
+        kk = alias.get(k, k)
+        lv = f"{lk[kk]:.3f} ({100 * ls[kk]:.1f} %)" if kk in lk else ""
+        if k in own:
+            lines.append(f"| `{k}` | {v:.3f} | {100 * v / tot:.2f} % | {lv} |")
+        else:
+            lines.append(f"| `{k[:60]}` (torch: L2 flush / copies of the harness) | {v:.3f} | - | |")
+    lines += ["", f"Own kernels of one steady-state cycle under ncu: {tot:.2f} ms; live step {live['ms_per_step']:.2f} ms ({live['value']:.0f} solves/s)."]
+    (PROF / "r2c_launches.md").write_text("\n".join(lines) + "\n")
+
+
+WANT = [("gpu__time_duration.sum", "duration"), ("dram__bytes_read.sum", "DRAM read"), ("dram__bytes_write.sum", "DRAM write"), ("lts__t_sector_hit_rate.pct", "L2 hit rate"),
+        ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM throughput"),
+        ("sm__ops_path_tensor_op_utcimma_src_int8_sparsity_off.sum", "int8 tensor operations executed (tcgen05.mma kind::i8)"),
+        ("sm__ops_path_tensor_op_utcimma_src_int8_sparsity_off.sum.pct_of_peak_sustained_elapsed", "... of the int8 tensor peak (16384 ops / cycle / SM)"),
+        ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor pipe active"),
+        ("sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "tensor memory (TMEM) active"),
+        ("l1tex__data_pipe_tc_wavefronts_mem_shared_op_utccp.sum", "shared-memory wavefronts of tcgen05.cp (A chunks -> TMEM)"),
+        ("sm__pipe_shared_cycles_active.avg.pct_of_peak_sustained_active", "shared fp64 + DMMA pipe active"), ("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "fp64 (DFMA) pipe active"),
+        ("smsp__inst_executed.sum", "warp instructions"), ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots busy"), ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps active"),
+        ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "shared-memory bank conflicts"), ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "shared-memory wavefronts"),
+        ("launch__registers_per_thread", "registers / thread"), ("launch__grid_size", "grid"), ("launch__block_size", "block")]
+
+
+def full():
+    note = (f"`ncu --set full --clock-control none --import-source on -k regex:\"k_mlp_oz|k_sqp_warp\" -s 130 -c 3 {CMD}`: the 131st..133rd matching launches = "
+            "one whole steady-state cycle (k_mlp_oz, the -- empty -- exclusive-SM launch k_sqp_warp_r255, the k_sqp_warp main launch).")
+    raw = subprocess.run(["ncu", "-i", str(OUT / "r2c_prof_steady.ncu-rep"), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    out = ["# Round 2 (int8-split MLP kernel) - ncu --set full, one steady-state cycle of C2 (4096 x N = 20)", "",
+           "Regenerate with tools/summarise_profiles_r2b.py from gpurun_out/r2c_prof_steady.ncu-rep (tools/gpu_profile_round2c.sh).", "", note, ""]
+    traffic = {}
+    for r in rows[2:]:
+        name = r[idx["Kernel Name"]].split("(")[0].replace("mpcc::", "")
+        if name == "k_sqp_warp_r255":
+            continue
+        out += [f"## `{name}`", "", "| metric | value |", "|---|---|"]
+        for m, label in WANT:
+            if m in idx and r[idx[m]] not in ("", "n/a", "0"):
+                out.append(f"| {label} (`{m}`) | {r[idx[m]]} {units[idx[m]]} |")
+        stalls = sorted([(num(r[i]) or 0.0, h) for h, i in idx.items() if "issue_stalled" in h and h.endswith("per_issue_active.ratio")], reverse=True)[:6]
+        out += ["", "Largest warp-stall reasons (cycles per issued instruction): " + ", ".join(f"{h.split('issue_stalled_')[1].split('_per_issue')[0]} {v:.2f}" for v, h in stalls), ""]
+        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+        b = num(r[idx["dram__bytes_read.sum"]]) * scale[units[idx["dram__bytes_read.sum"]]] + num(r[idx["dram__bytes_write.sum"]]) * scale[units[idx["dram__bytes_write.sum"]]]
+        traffic[name] = {"dram_bytes_per_launch": b, "kernel_duration_under_ncu": r[idx["gpu__time_duration.sum"]] + " " + units[idx["gpu__time_duration.sum"]], "capture": note, "build": SHA}
+    out += ["## Reading", "",
+            "* `k_mlp_oz`: the int8 operation count ncu reports (7.576e12) is exactly what bench.py derives from the tile / pass / product structure "
+            "(`roofline_mlp.tensor_int8.int8_ops_per_launch`): 24 % of the int8 tensor peak over the whole launch, the tensor pipe is active a third of the time -- "
+            "the other two thirds are the fp64 <-> digit conversions (split, epilogue), the first layers (DFMA), the 64-neuron and output layers (DMMA: the shared "
+            "fp64 pipe is still 39 % active) and the CTA barriers between those phases (largest stall: barrier).  DRAM traffic is 11.5 MB per launch against "
+            "7.1 MB of algorithmic input + output: weights and digit planes live in L2 (hit rate 99.4 %).",
+            "* `k_sqp_warp`: unchanged since the first round-2 capture (profiles/r2_ncu_full_steady.md): latency-bound, 8 GB of DRAM traffic per launch "
+            "(1480 resident instances x 158 KB of workspace against 126 MB of L2)."]
+    (PROF / "r2c_ncu_full_steady.md").write_text("\n".join(out) + "\n")
+    cur = json.loads((PROF / "dram_traffic.json").read_text())
+    cur.update(traffic)
+    (PROF / "dram_traffic.json").write_text(json.dumps(cur, indent=1) + "\n")
+
+
+def sass():
+    lib = ROOT / "mpcc_manipulator_b200" / "libmpcc_b200.so"
+    txt = subprocess.run(["cuobjdump", "-sass", str(lib)], capture_output=True, text=True).stdout
+    per, cur = collections.OrderedDict(), None
+    pats = ["UTCIMMA", "UTCCP", "UTCBAR", "LDTM", "STTM", "UTCATOMSWS", "LDGSTS", "UBLKCP", "DMMA", "DFMA", "SYNCS", "REDUX", "I2F.F64.S64", "HMMA", "IMMA"]
+    for line in txt.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            per[cur] = collections.Counter()
+            continue
+        if cur is None:
+            continue
+        m = re.search(r"/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
+        if m:
+            op = m.group(1)
+            for p in pats:
+                if op.startswith(p):
+                    per[cur][p] += 1
+    lines = ["# Round 2 (int8-split MLP kernel) - SASS census of libmpcc_b200.so", "",
+             f"`cuobjdump -sass mpcc_manipulator_b200/libmpcc_b200.so` (sm_100a only), build {SHA}; regenerate with tools/summarise_profiles_r2b.py.",
+             "`UTCIMMA` = tcgen05.mma kind::i8, `UTCCP` = tcgen05.cp (shared memory -> TMEM), `UTCBAR` = tcgen05.commit, `LDTM` = tcgen05.ld, `UTCATOMSWS` = tcgen05.alloc / dealloc, "
+             "`SYNCS` = mbarrier operations, `LDGSTS` = cp.async, `DMMA` = mma.sync.m8n8k4.f64.", "",
+             "| kernel | " + " | ".join(pats) + " |", "|---|" + "---|" * len(pats)]
+    for k, c in per.items():
+        if not any(c.values()):
+            continue
+        short = re.sub(r"^_ZN4mpcc\d+", "", k)
+        short = re.sub(r"E.*$", "", short)
+        lines.append(f"| `{short}` | " + " | ".join(str(c.get(p, 0)) for p in pats) + " |")
+    (PROF / "r2c_sass_census.md").write_text("\n".join(lines) + "\n")
+
+
+if __name__ == "__main__":
+    launches()
+    full()
+    sass()
+    print("written: profiles/r2c_launches.md, profiles/r2c_ncu_full_steady.md, profiles/r2c_sass_census.md, profiles/dram_traffic.json")
