@@ -38,7 +38,7 @@ def launches():
     live = json.loads([l for l in (OUT / "r2c_plain.log").read_text().splitlines() if l.startswith("{")][-1])
     lk, ls = live["kernels_ms"], live["roofline"]["kernel_share_of_step"]
     alias = {"k_mlp_oz": "k_mlp"}
-    lines = ["# Round 2 (int8-split MLP kernel) - ncu launch list, steady state", "",
+    lines = ["# Round 2, last session (reverse-mode self net, uniform warp indices, direct horizon write) - ncu launch list, steady state", "",
              f"Command: `ncu --metrics gpu__time_duration.sum --clock-control none -s 240 -c 60 --csv {CMD}`, run after the same command exited 0 without ncu (build {SHA}).",
              f"{len(seq)} launches captured (launches 241..300 of the process), {ncyc} whole control cycles; the table is their mean.",
              "Per-launch times under ncu are serialised and cold-cache: compare SHARES with the live CUDA-event numbers (right column, same command without ncu).", "",
@@ -74,8 +74,8 @@ def full():
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     idx = {h: i for i, h in enumerate(hdr)}
-    out = ["# Round 2 (int8-split MLP kernel) - ncu --set full, one steady-state cycle of C2 (4096 x N = 20)", "",
-           "Regenerate with tools/summarise_profiles_r2b.py from gpurun_out/r2c_prof_steady.ncu-rep (tools/gpu_profile_round2c.sh).", "", note, ""]
+    out = ["# Round 2, last session (reverse-mode self net, uniform warp indices, direct horizon write) - ncu --set full, one steady-state cycle of C2 (4096 x N = 20)", "",
+           "Regenerate with tools/summarise_profiles_r2c.py from gpurun_out/r2c_prof_steady.ncu-rep (tools/gpu_profile_round2c.sh).", "", note, ""]
     traffic = {}
     for r in rows[2:]:
         name = r[idx["Kernel Name"]].split("(")[0].replace("mpcc::", "")
@@ -91,13 +91,15 @@ def full():
         b = num(r[idx["dram__bytes_read.sum"]]) * scale[units[idx["dram__bytes_read.sum"]]] + num(r[idx["dram__bytes_write.sum"]]) * scale[units[idx["dram__bytes_write.sum"]]]
         traffic[name] = {"dram_bytes_per_launch": b, "kernel_duration_under_ncu": r[idx["gpu__time_duration.sum"]] + " " + units[idx["gpu__time_duration.sum"]], "capture": note, "build": SHA}
     out += ["## Reading", "",
-            "* `k_mlp_oz`: the int8 operation count ncu reports (7.576e12) is exactly what bench.py derives from the tile / pass / product structure "
-            "(`roofline_mlp.tensor_int8.int8_ops_per_launch`): 24 % of the int8 tensor peak over the whole launch, the tensor pipe is active a third of the time -- "
-            "the other two thirds are the fp64 <-> digit conversions (split, epilogue), the first layers (DFMA), the 64-neuron and output layers (DMMA: the shared "
-            "fp64 pipe is still 39 % active) and the CTA barriers between those phases (largest stall: barrier).  DRAM traffic is 11.5 MB per launch against "
-            "7.1 MB of algorithmic input + output: weights and digit planes live in L2 (hit rate 99.4 %).",
-            "* `k_sqp_warp`: unchanged since the first round-2 capture (profiles/r2_ncu_full_steady.md): latency-bound, 8 GB of DRAM traffic per launch "
-            "(1480 resident instances x 158 KB of workspace against 126 MB of L2)."]
+            "* `k_mlp_oz` (5.20 ms; the capture of the round's first half, profiles/r2b_ncu_full_steady.md: 6.93 ms): the int8 operation count ncu reports (7.576e12) is "
+            "exactly what bench.py derives from the tile / pass / product structure (`roofline_mlp.tensor_int8.int8_ops_per_launch`), now 32 % of the int8 tensor peak "
+            "over the whole launch (was 24 %), tensor pipe active 40 % of the time.  Warp instructions 1.59e9 -> 1.37e9 (reverse-mode self net, no convergence "
+            "barriers around the issuer's single-thread regions).  The rest of the time is the fp64 <-> digit conversions (split, epilogue), the first layers (DFMA), "
+            "the self net and the output layer (DMMA: shared fp64 pipe 44 % active) and the CTA barriers between those phases (largest stall: barrier).  DRAM traffic "
+            "11.9 MB per launch against 7.1 MB of algorithmic input + output: weights and digit planes live in L2 (hit rate 98.9 %).",
+            "* `k_sqp_warp` (4.11 ms; first half of the round: 5.01 ms with four interior-point iterations per QP, now three): latency-bound as before "
+            "(long_scoreboard 4.3 and wait 2.5 stall cycles per issue), 6.6 GB of DRAM traffic per launch (1480 resident instances x 158 KB of workspace against "
+            "126 MB of L2; was 8.0 GB), warp instructions 1.37e9 -> 1.06e9."]
     (PROF / "r2c_ncu_full_steady.md").write_text("\n".join(out) + "\n")
     cur = json.loads((PROF / "dram_traffic.json").read_text())
     cur.update(traffic)
@@ -123,8 +125,8 @@ def sass():
             for p in pats:
                 if op.startswith(p):
                     per[cur][p] += 1
-    lines = ["# Round 2 (int8-split MLP kernel) - SASS census of libmpcc_b200.so", "",
-             f"`cuobjdump -sass mpcc_manipulator_b200/libmpcc_b200.so` (sm_100a only), build {SHA}; regenerate with tools/summarise_profiles_r2b.py.",
+    lines = ["# Round 2, last session (reverse-mode self net, uniform warp indices, direct horizon write) - SASS census of libmpcc_b200.so", "",
+             f"`cuobjdump -sass mpcc_manipulator_b200/libmpcc_b200.so` (sm_100a only), build {SHA}; regenerate with tools/summarise_profiles_r2c.py.",
              "`UTCIMMA` = tcgen05.mma kind::i8, `UTCCP` = tcgen05.cp (shared memory -> TMEM), `UTCBAR` = tcgen05.commit, `LDTM` = tcgen05.ld, `UTCATOMSWS` = tcgen05.alloc / dealloc, "
              "`SYNCS` = mbarrier operations, `LDGSTS` = cp.async, `DMMA` = mma.sync.m8n8k4.f64.", "",
              "| kernel | " + " | ".join(pats) + " |", "|---|" + "---|" * len(pats)]
