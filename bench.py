@@ -433,12 +433,15 @@ def measure(M, name, args, steps, warmup, world, rank, local, dist, full):
     iters_max = np.zeros(e2e_steps, int)
     hit_np = hit.numpy()   # (a first torch reduction on the pinned tensor costs milliseconds of one-time set-up: keep the bookkeeping in numpy)
     hit_np.max()
+    inst_ms = []
     t0 = time.perf_counter()
     for i in range(e2e_steps):
         ta = time.perf_counter()
         e2e_step()
         lat[i] = (time.perf_counter() - ta) * 1e3
         iters_max[i] = int(hit_np.max())
+        if name == "c5":   # per-instance solve times of this cycle (device timer around each instance's SQP loop), read outside the timed call
+            inst_ms.append(mpc.compute_time()[:, 0] * 1e3)
     t_e2e = time.perf_counter() - t0
     if world > 1:
         t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
@@ -455,6 +458,12 @@ def measure(M, name, args, steps, warmup, world, rank, local, dist, full):
                    "latency_ms": {"p50": float(np.percentile(lat, 50)), "p90": float(np.percentile(lat, 90)), "p99": float(np.percentile(lat, 99)), "max": float(lat.max())},
                    "max_sqp_iters_per_cycle": {"p50": int(np.percentile(iters_max, 50)), "p99": int(np.percentile(iters_max, 99)), "max": int(iters_max.max())}},
            "info": info, "cold_start": cold}
+    if inst_ms:
+        a = np.concatenate(inst_ms)
+        res["e2e"]["per_instance_sqp_ms"] = {"p50": float(np.percentile(a, 50)), "p90": float(np.percentile(a, 90)), "p99": float(np.percentile(a, 99)), "max": float(a.max()),
+                                             "what": "SQP time of each single instance (ComputeTime::total analogue) over all instances and cycles of the e2e run: the batch call returns with its "
+                                                     "slowest instance, and which instances wander into the reference algorithm's 30..100-iteration regime at eps_prim = 0.01 is chaotic "
+                                                     "(it changes with the last bit of RobotData), so the per-cycle percentiles above move from build to build while these do not"}
     mpc.close()
     return res
 
