@@ -86,7 +86,9 @@ int mpcc_cuda_upload_nn(mpcc_cuda_handle* h, const double* self_w, const double*
 /* either this repo's packed file (*.f64) or the reference's directory of weight_k.txt / bias_k.txt */
 int mpcc_cuda_load_nn(mpcc_cuda_handle* h, const char* self_path, const char* env_path);
 
-/* n_sets == 1: one parameter set for the whole batch; n_sets == batch: one per instance */
+/* n_sets == 1: one parameter set for the whole batch; n_sets == batch: one per instance.
+ * sqp.do_SOC (osqp_interface.cpp:506-533,658-681) is honoured per instance: a handle with at least one such set runs the SQP kernels that have the
+ * second-order correction compiled in.  sqp.use_BFGS != 0 is rejected (MPCC_ERR_INVALID); sqp.max_iter must be in [1, 128]. */
 int mpcc_cuda_set_params(mpcc_cuda_handle* h, const double* params, int32_t n_sets);
 /* the reference's PathToJson (types.h:127-134); overrides: n_over (key, value) pairs with keys written
  * "file.key", e.g. "cost.qC" (the reference's ParamValue maps, types.h:143-150) */
