@@ -37,29 +37,50 @@ MPCC_HDN void cycle_prologue(const Params& P, const TrackTable& T, double Ts, in
     x0[8] = vs;
     if (fabs(last_s - x0[7]) > P.max_dist_proj) { fl.valid = 0; fl.failed++; }
     const double L = T.s[N_SPLINE - 1];
+    // unwrapInitialGuess (mpc.cpp:70-77) clamps s of the stages 1..N to the track length: applied as the stages are written
     if (fl.valid) {
-        // updateInitialGuess (mpc.cpp:54-68)
-        for (int i = 1; i < N; i++)
-            for (int e = 0; e < HZ; e++) warm[(i - 1) * HZ + e] = warm[i * HZ + e];
-        for (int e = 0; e < NX; e++) warm[e] = x0[e];
-        for (int e = 0; e < HZ; e++) warm[(N - 1) * HZ + e] = warm[(N - 2) * HZ + e];
-        // RK4 of the linear model is exact (integrator.cpp:29-43 on model.cpp:31-45)
+        // updateInitialGuess (mpc.cpp:54-68): g[i-1] = g[i] for i = 1..N-1, g[0].xk = x0, g[N-1] = g[N-2], g[N].xk = RK4(g[N-1]), g[N].uk = 0.
+        // One thread shifts one instance's warm start through global memory: the loads of stage i + 1 are issued BEFORE the stores of stage i
+        // (same array: the compiler must otherwise keep every load behind the previous store -- 340 dependent memory round trips, 0.1 ms).
+        double cur[HZ], nxt[HZ];
+#pragma unroll
+        for (int e = 0; e < HZ; e++) cur[e] = warm[HZ + e];
+        for (int i = 1; i < N; i++) {
+            if (i + 1 < N) {
+#pragma unroll
+                for (int e = 0; e < HZ; e++) nxt[e] = warm[(i + 1) * HZ + e];
+            }
+#pragma unroll
+            for (int e = 0; e < HZ; e++) {
+                double v = cur[e];
+                if (i == 1 && e < NX) v = x0[e];               // g[0].xk = x0 (keeps the shifted uk)
+                else if (e == 7 && i > 1) v = fmin(v, L);
+                warm[(i - 1) * HZ + e] = v;
+            }
+            if (i + 1 < N) {
+#pragma unroll
+                for (int e = 0; e < HZ; e++) cur[e] = nxt[e];
+            }
+        }
+        // cur = the old last stage g[N-1], now also at N-2: g[N-1] = g[N-2] leaves it where it is (only the clamp applies)
         double xs[NX], us[NU];
-        for (int e = 0; e < NX; e++) xs[e] = warm[(N - 1) * HZ + e];
-        for (int e = 0; e < NU; e++) us[e] = warm[(N - 1) * HZ + NX + e];
+        for (int e = 0; e < NX; e++) xs[e] = (N == 2 && e < NX) ? x0[e] : cur[e];
+        for (int e = 0; e < NU; e++) us[e] = cur[NX + e];
+        if (N == 2) { for (int e = 0; e < NX; e++) warm[HZ + e] = x0[e]; }   // N = 2: g[N-2] is g[0], whose xk is x0
+        warm[(N - 1) * HZ + 7] = fmin(xs[7], L);
+        // RK4 of the linear model is exact (integrator.cpp:29-43 on model.cpp:31-45); it reads the UNclamped g[N-1] (the clamp comes after it in the reference)
         for (int j = 0; j < DOF; j++) warm[N * HZ + j] = xs[j] + Ts * us[j];
-        warm[N * HZ + 7] = xs[7] + Ts * xs[8] + 0.5 * Ts * Ts * us[7];
+        warm[N * HZ + 7] = fmin(xs[7] + Ts * xs[8] + 0.5 * Ts * Ts * us[7], L);
         warm[N * HZ + 8] = xs[8] + Ts * us[7];
         for (int e = 0; e < NU; e++) warm[N * HZ + NX + e] = 0;
     } else {
         // generateNewInitialGuess (mpc.cpp:79-89)
         for (int i = 0; i <= N; i++) {
-            for (int e = 0; e < NX; e++) warm[i * HZ + e] = x0[e];
+            for (int e = 0; e < NX; e++) warm[i * HZ + e] = (e == 7 && i > 0) ? fmin(x0[e], L) : x0[e];
             for (int e = 0; e < NU; e++) warm[i * HZ + NX + e] = 0;
         }
         fl.valid = 1;
     }
-    for (int i = 1; i <= N; i++) warm[i * HZ + 7] = fmin(warm[i * HZ + 7], L);  // unwrapInitialGuess (mpc.cpp:70-77)
 }
 
 // accept_mask: bit i = the filter accepted the first line-search trial of SQP iteration i (i < 32)
