@@ -957,33 +957,62 @@ struct GroupSqp {
                 }
                 return bad;
             })) return st;
-        // initial point: nu = 0, xi = rollout of the defects (lane = state component), t = max(h - Gz, QP_INIT_SLACK), lam = QP_INIT_SLACK / t
+        // initial point: nu = 0, xi = rollout of the defects (lane = state component), t = max(h - Gz, QP_INIT_SLACK), lam = QP_INIT_SLACK / t.
+        // The loops below read the stage records from global memory; each lane issues FOUR independent loads before the first use (a rolled
+        // load -> use -> store loop pays one memory round trip per item: the next load may not pass the store), and the defects b are staged in
+        // shared memory (STEP is free here and again after the last iteration) before the sequential rollouts walk them.
+        auto stage_defects = [&]() {
+            W.each([&](int lane) {
+                const int nb = N * NX;
+                MPCC_ROLLED
+                for (int o = lane; o < nb; o += 4 * NL) {
+                    double t[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) { const int i = o + u * NL; t[u] = (i < nb) ? LIN[(size_t)(i / NX) * WL_SIZE + WL_b + (i % NX)] : 0.0; }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) { const int i = o + u * NL; if (i < nb) STEP[i] = t[u]; }
+                }
+            });
+        };
+        stage_defects();
         const double qn = W.rmax([&](int lane) {
             double q = 0;
             MPCC_ROLLED
-            for (int o = lane; o < S * HZ; o += NL) {
-                const int k = o / HZ, r = o - k * HZ;
-                const double* L = LIN + (size_t)k * WL_SIZE;
-                if (r < NX) q = fmax(q, fabs(L[WL_q + r]));
-                else { VAR[o] = 0.0; G[o] = 0.0; if (k < N) q = fmax(q, fabs(L[WL_r + r - NX])); }
+            for (int o = lane; o < S * HZ; o += 4 * NL) {
+                double t[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int i = o + u * NL, k = i / HZ, r = i - k * HZ;
+                    const double* L = LIN + (size_t)k * WL_SIZE;
+                    t[u] = (i >= S * HZ) ? 0.0 : (r < NX) ? L[WL_q + r] : (k < N) ? L[WL_r + r - NX] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int i = o + u * NL;
+                    if (i < S * HZ) { q = fmax(q, fabs(t[u])); if (i - (i / HZ) * HZ >= NX) { VAR[i] = 0.0; G[i] = 0.0; } }
+                }
             }
             if (lane < NX && lane != 7) {
                 double x = 0;
-                for (int k = 0; k <= N; k++) { VAR[k * HZ + lane] = x; if (k < N) x += LIN[(size_t)k * WL_SIZE + WL_b + lane]; }
+                for (int k = 0; k <= N; k++) { VAR[k * HZ + lane] = x; if (k < N) x += STEP[k * NX + lane]; }
             }
             return q;
         });
         W.each([&](int lane) {
             if (lane == 7) {
                 double x = 0;
-                for (int k = 0; k <= N; k++) { VAR[k * HZ + 7] = x; if (k < N) x += d_asv() * VAR[k * HZ + 8] + LIN[(size_t)k * WL_SIZE + WL_b + 7]; }
+                for (int k = 0; k <= N; k++) { VAR[k * HZ + 7] = x; if (k < N) x += d_asv() * VAR[k * HZ + 8] + STEP[k * NX + 7]; }
             }
             MPCC_ROLLED
             for (int i = lane; i < tot; i += NL) { IT[i] = 1.0; ILAM[i] = 0.0; IW[i] = 0.0; IV[i] = 0.0; IRP[i] = 0.0; IDT[i] = 0.0; IDLAM[i] = 0.0; }
         });
         const double s0 = QP_INIT_SLACK;
         W.each([&](int lane) {
-            for_present(lane, VAR, true, [&](int i, double g, double h) { const double t0 = fmax(h - g, s0); IT[i] = t0; ILAM[i] = s0 / t0; IH[i] = h; });
+            for_present4(lane, VAR, true, [&](const int* idx, const double* g, const double* h) {
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (idx[u] >= 0) { const double t0 = fmax(h[u] - g[u], s0); IT[idx[u]] = t0; ILAM[idx[u]] = s0 / t0; IH[idx[u]] = h[u]; }
+            });
         });
         const double m_tot = 43.0 * N;
         // The certificate test sits OUTSIDE the iteration loop (the loop leaves for it and is re-entered): with a call inside the
@@ -1073,13 +1102,14 @@ struct GroupSqp {
         }
         if (st.ok) {
             // make the equalities exact: xi = rollout(nu)
+            stage_defects();
             W.each([&](int lane) {
                 if (lane < NX && lane != 7) {
                     double x = 0;
                     for (int k = 0; k <= N; k++) {
                         VAR[k * HZ + lane] = x;
                         if (k < N) {
-                            const double b = LIN[(size_t)k * WL_SIZE + WL_b + lane];
+                            const double b = STEP[k * NX + lane];
                             x = (lane < 7) ? x + d_bq(lane) * VAR[k * HZ + NX + lane] + b : x + d_bv() * VAR[k * HZ + NX + 7] + b;
                         }
                     }
@@ -1090,7 +1120,7 @@ struct GroupSqp {
                     double x = 0;
                     for (int k = 0; k <= N; k++) {
                         VAR[k * HZ + 7] = x;
-                        if (k < N) x = x + d_asv() * VAR[k * HZ + 8] + d_bs() * VAR[k * HZ + NX + 7] + LIN[(size_t)k * WL_SIZE + WL_b + 7];
+                        if (k < N) x = x + d_asv() * VAR[k * HZ + 8] + d_bs() * VAR[k * HZ + NX + 7] + STEP[k * NX + 7];
                     }
                 }
             });

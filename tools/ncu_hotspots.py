@@ -17,7 +17,7 @@ def main():
     rows = list(csv.reader(open(src)))
     hdr, data = rows[1], rows[2:]
     col = {n: hdr.index(n) for n in ["# Samples", "stall_no_inst", "Instructions Executed", "stall_long_sb", "stall_wait", "stall_short_sb", "stall_branch_resolving"]}
-    chains = chains_of(dis, lambda line: 'k_sqp_warp' in line and 'solve_ocp' not in line)
+    chains = chains_of(dis, lambda line: 'k_sqp_warp' in line and 'solve_ocp' not in line and 'r255' not in line)
     if len(chains) != len(data):
         sys.exit(f"report ({len(data)} instr) and disassembly ({len(chains)}) are different builds")
     root = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'mpcc_manipulator_b200', 'csrc')
