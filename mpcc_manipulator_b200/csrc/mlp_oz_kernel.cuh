@@ -759,8 +759,12 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp_oz(MlpOzArgs oa) {
                 cp_async_wait_all();
                 __syncthreads();  // the output layer's weights are in place
                 d_topup();  // all MMAs of the tile are done: the ring region is the DMMA layers' again
-                // ---- env output layer: 9 x 256 as two m-fragments (rows 0..7, row 8) on DMMA; warp = column kind ----
-                double o[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+                // ---- env output layer (9 x 256); warp = column kind.  Rows 0..7: one m-fragment on DMMA.  Row 8 alone would waste seven eighths of a
+                //      second fragment (2 k cycles of the FP64 pipe per tile): it rides along as DFMA on the B-fragment elements the lane holds
+                //      anyway (k = 4 kb + fq of sample fr), summed over fq at the end ----
+                double o[2][2] = {{0.0, 0.0}, {0.0, 0.0}};   // (four accumulator chains instead of two: no change -- the layer is not bound by the DMMA latency)
+                double r8[2] = {0.0, 0.0};
+                const double bias_fr = (warp == 0) ? __ldg(a.bias + MLP_BIAS_ENV_OUT + fr) : 0.0, bias_8 = (warp == 0) ? __ldg(a.bias + MLP_BIAS_ENV_OUT + 8) : 0.0;   // requested before the loop
                 const double* xb = Xd + ((warp >> 1) * 32 + bslot) * 2 + (warp & 1);
                 const double* Wo0 = reinterpret_cast<const double*>(smem_raw + OZ_OFF_WOUT);  // rows 0..7 as A fragments [kb 64][lane 32]
                 const double* Wo1 = Wo0 + 8 * 256;                                            // row 8 [256]
@@ -769,22 +773,29 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) k_mlp_oz(MlpOzArgs oa) {
 #pragma unroll
                     for (int h = 0; h < 2; h++) {
                         const double bx = xb[(kb + h) * 256];
-                        const double a0 = Wo0[(kb + h) * 32 + lane], a1 = (lane < 4) ? Wo1[(kb + h) * 4 + lane] : 0.0;
-                        dmma884(o[h][0][0], o[h][0][1], a0, bx);
-                        dmma884(o[h][1][0], o[h][1][1], a1, bx);
+                        dmma884(o[h][0], o[h][1], Wo0[(kb + h) * 32 + lane], bx);
+                        r8[h] = fma(Wo1[(kb + h) * 4 + fq], bx, r8[h]);
                     }
                 }
 #pragma unroll
-                for (int mb = 0; mb < 2; mb++)
-#pragma unroll
-                    for (int e = 0; e < 2; e++) {
-                        const int l = mb * 8 + fr, ns = s0 + 2 * fq + e;
-                        if (l < 9 && ns < a.NS) {
-                            const double v = o[0][mb][e] + o[1][mb][e];
-                            if (warp == 0) a.rb[(size_t)(RB_ENV + l) * a.NS + ns] = v + a.bias[MLP_BIAS_ENV_OUT + l];
-                            else a.rb[(size_t)(RB_DENV + l * 7 + (warp - 1)) * a.NS + ns] = v;
-                        }
+                for (int e = 0; e < 2; e++) {
+                    const int ns = s0 + 2 * fq + e;
+                    if (ns < a.NS) {
+                        const double v = o[0][e] + o[1][e];
+                        if (warp == 0) a.rb[(size_t)(RB_ENV + fr) * a.NS + ns] = v + bias_fr;
+                        else a.rb[(size_t)(RB_DENV + fr * 7 + (warp - 1)) * a.NS + ns] = v;
                     }
+                }
+                {
+                    double v = r8[0] + r8[1];
+                    v += __shfl_xor_sync(0xffffffffu, v, 1);
+                    v += __shfl_xor_sync(0xffffffffu, v, 2);
+                    const int ns = s0 + fr;   // the lane's B-fragment column is sample fr
+                    if (fq == 0 && ns < a.NS) {
+                        if (warp == 0) a.rb[(size_t)(RB_ENV + 8) * a.NS + ns] = v + bias_8;
+                        else a.rb[(size_t)(RB_DENV + 8 * 7 + (warp - 1)) * a.NS + ns] = v;
+                    }
+                }
                 if (tid < 8 && (s0 + tid) < a.NS) {
                     const int n2 = s0 + tid;
                     a.rb[(size_t)RB_OBSR * a.NS + n2] = a.obs[(size_t)(n2 / a.S) * 4 + 3];
