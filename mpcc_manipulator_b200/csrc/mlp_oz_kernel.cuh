@@ -198,6 +198,18 @@ __device__ __forceinline__ void oz_tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) 
     asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
 
+// the same load without the wait (several loads in flight; oz_tmem_wait_ld() before the first use of any of them)
+__device__ __forceinline__ void oz_tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+          "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]),
+          "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void oz_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+
 // first layer, one chunk of 8 encoded inputs (K0 .. K0 + 7) on DFMA: mlp_layer0_chunk of mlp_kernel.cuh with an 8-row chunk
 //   Wc: the warp's slice [k 8][row 32]    Zs: [k 32][sample 8]
 template <int NIN, int K0>
@@ -384,20 +396,22 @@ __device__ __forceinline__ void oz_epilogue_pass(double2* Xs, uint32_t* colmax, 
     const int qd = warp & 3, hh = warp >> 2;
     const int row = mb * 128 + qd * 32 + lane;
     const double rs = __ldg(rowscale + row), bv = __ldg(bias + row);
-    // Horner with the accumulators taken in pairs: G_g 128 + G_(g+1) still fits int32 (|G_g| <= (g + 1) 2^20), so the 64-bit steps are halved
+    // Horner with the accumulators taken in pairs: G_g 128 + G_(g+1) still fits int32 (|G_g| <= (g + 1) 2^20), so the 64-bit steps are halved;
+    // the two TMEM loads of a pair are in flight together (one wait per pair instead of one per accumulator)
     long long acc[32];
-    int pair[32];
 #pragma unroll
-    for (int g = 0; g < OZ_S; g++) {
-        uint32_t v[32];
-        oz_tmem_ld32(tmem + ((uint32_t)(qd * 32) << 16) + g * 64 + hh * 32, v);
+    for (int g = 0; g < OZ_S; g += 2) {
+        uint32_t va[32], vb[32];
+        const uint32_t ta = tmem + ((uint32_t)(qd * 32) << 16) + g * 64 + hh * 32;
+        oz_tmem_ld32_nowait(ta, va);
+        if (g + 1 < OZ_S) oz_tmem_ld32_nowait(ta + 64, vb);
+        oz_tmem_wait_ld();
 #pragma unroll
         for (int c = 0; c < 32; c++) {
-            if ((g & 1) == 0 && g + 1 < OZ_S) pair[c] = (int)v[c];
-            else if (g & 1) {
-                pair[c] = pair[c] * 128 + (int)v[c];
-                acc[c] = (g == 1) ? (long long)pair[c] : acc[c] * 16384 + (long long)pair[c];
-            } else acc[c] = (g == 0) ? (long long)(int)v[c] : acc[c] * 128 + (long long)(int)v[c];
+            if (g + 1 < OZ_S) {
+                const int p = (int)va[c] * 128 + (int)vb[c];
+                acc[c] = (g == 0) ? (long long)p : acc[c] * 16384 + (long long)p;
+            } else acc[c] = (g == 0) ? (long long)(int)va[c] : acc[c] * 128 + (long long)(int)va[c];
         }
     }
     uint32_t mymax = 0;  // lane c: largest |entry| (high word) of column 32 hh + c over this warp's 32 neurons
