@@ -143,3 +143,41 @@ def test_qp_optimum_against_osqp_algorithm(O, nn, track_wp, rng, N):
         x2, _, it2, st2 = osqp_admm(P, q, A[keep], lo[keep], hi[keep], eps_abs=1e-9, eps_rel=1e-9, max_iter=200000)
         assert st2 == "solved" and np.abs(x2 - z_ipm).max() < 2e-5
         print(f"N={N}: at 1e-9 tolerances the ADMM point and the interior-point optimum differ by {np.abs(x2 - z_ipm).max():.2e} ({it2} iterations)")
+
+
+def test_second_order_correction_formula_in_numpy(O, nn, track_wp, rng):
+    """SecondOrderCorrection (osqp_interface.cpp:658-681) written out in numpy on the oracle's flat matrices: QP at the iterate -> step z1; constraint
+    values and bounds at x (+) z1 (the normalised step added to the unnormalised iterate, :661); d = c~ - A z1; second QP with the SAME P, q, A and
+    the bounds l~ - d, u~ - d.  The first step the oracle's solveOCP logs with do_SOC must be that z2 (same dense solver: 1e-7), it must differ from z1
+    (otherwise nothing was corrected), and the product's host-compiled code must agree with it to the QP tolerance."""
+    from helpers import Emul, flat_params, step_to_flat
+    N = 10
+    p = O.load_params(overrides={"sqp": {"do_SOC": True}})
+    o_soc = O.OracleMPC(N=N, nn=nn, params=p); o_soc.set_track(*track_wp)
+    o = O.OracleMPC(N=N, nn=nn); o.set_track(*track_wp)
+    emu = Emul()
+    table = emu.fit_track(*track_wp)
+    for trial in range(3):
+        q0 = O.Q_HOME + rng.uniform(-0.05, 0.05, 7)
+        hor = np.tile(np.r_[q0, 0.0, 0.0, np.zeros(8)], (N + 1, 1))
+        if trial == 2:
+            hor[:, 7] = np.linspace(0.0, 0.02, N + 1); hor[:, 8] = 0.1; hor[:N, 9:16] = rng.uniform(-0.05, 0.05, (N, 7))
+        rb = np.stack([nn.robot_data(hor[k, :7]) for k in range(N + 1)])
+        cur_u = np.zeros(8)
+        qp0 = o.build_qp(hor, rb, cur_u)
+        ok1, z1, _ = O.solve_qp_dense(qp0["P"], qp0["q"], qp0["A"], qp0["l"] - qp0["c"], qp0["u"] - qp0["c"])
+        assert ok1
+        # x (+) z1 in horizon layout: all states first, then the inputs of stages 0..N-1 (osqp_interface.cpp:835-857); uk[N] = 0
+        hor_t = hor.copy()
+        hor_t[:, :9] += z1[:9 * (N + 1)].reshape(N + 1, 9)
+        hor_t[:N, 9:] += z1[9 * (N + 1):].reshape(N, 8)
+        hor_t[N, 9:] = 0.0
+        qp1 = o.build_qp(hor_t, rb, cur_u)          # RobotData stays frozen (quirk 6): the same rb
+        d = qp1["c"] - qp0["A"] @ z1
+        ok2, z2, _ = O.solve_qp_dense(qp0["P"], qp0["q"], qp0["A"], qp1["l"] - d, qp1["u"] - d)
+        assert ok2
+        assert np.abs(z2 - z1).max() > 1e-3
+        ref = o_soc.solve_ocp(hor, rb, cur_u)
+        assert np.abs(ref["steps"][0] - z2).max() < 1e-7, np.abs(ref["steps"][0] - z2).max()
+        a = emu.warp_solve_ocp(flat_params(p), table, p["Ts"], N, hor, rb, cur_u, soc=True)
+        assert np.abs(step_to_flat(a["steps"][0], N) - z2).max() < 1e-4
